@@ -1,0 +1,523 @@
+// Row-wise epilogues of the GraphSAGE layers and the train-step tail:
+//   LayerNorm + ReLU        /root/reference/src/components/graphs/models.py:34-37,64-66
+//   ReLU + L2 row normalise models.py:167-169 (MeanSAGE)
+//   weighted cross entropy  /root/reference/src/models/model_train.py:171,327-328
+//   Adam with L2 decay      model_train.py:168,330-332
+// All HBM-bound, one warp per row, fixed-order reductions (no atomics).
+#include "gte_common.cuh"
+
+#include <math.h>
+
+namespace gte {
+
+constexpr int ROW_THREADS = 256;
+constexpr int ROW_WARPS = ROW_THREADS / 32;
+
+// ------------------------------------------------------------ LayerNorm ---
+template <int MAXC>
+__global__ void __launch_bounds__(ROW_THREADS)
+    k_layernorm_act_fwd(const float* __restrict__ z, int64_t ldz, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, int relu, float* __restrict__ y, int64_t ldy,
+                        float* __restrict__ mean_out, float* __restrict__ rstd_out, int32_t n, int32_t f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* zr = z + row * ldz;
+  float v[MAXC];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    v[c] = col < f ? zr[col] : 0.f;
+    s += v[c];
+  }
+  const float mean = warp_sum(s) / (float)f;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    const float d = col < f ? v[c] - mean : 0.f;
+    q = fmaf(d, d, q);
+  }
+  const float var = warp_sum(q) / (float)f;  // biased, like nn.LayerNorm
+  const float rstd = 1.0f / sqrtf(var + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  float* yr = y + row * ldy;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    if (col < f) {
+      float o = (v[c] - mean) * rstd * __ldg(gamma + col) + __ldg(beta + col);
+      if (relu) o = fmaxf(o, 0.f);
+      yr[col] = o;
+    }
+  }
+}
+
+// dz per row + per-block partial sums of dgamma / dbeta: partial[block][2][f]
+template <int MAXC>
+__global__ void __launch_bounds__(ROW_THREADS)
+    k_layernorm_act_bwd(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z, int64_t ldz,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                        float* __restrict__ dz, int64_t lddz, float* __restrict__ partial, int32_t n, int32_t f) {
+  extern __shared__ float sm[];  // [ROW_WARPS][2][f]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float gam[MAXC], bet[MAXC], dg[MAXC], db[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    gam[c] = col < f ? __ldg(gamma + col) : 0.f;
+    bet[c] = col < f ? __ldg(beta + col) : 0.f;
+    dg[c] = 0.f;
+    db[c] = 0.f;
+  }
+  const float inv_f = 1.0f / (float)f;
+  for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < n; row += (int64_t)gridDim.x * ROW_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* zr = z + row * ldz;
+    const float* gr = dy + row * lddy;
+    float xh[MAXC], a[MAXC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = lane + 32 * c;
+      float g = 0.f;
+      xh[c] = 0.f;
+      if (col < f) {
+        xh[c] = (zr[col] - mu) * rs;
+        g = gr[col];
+        if (relu && !(xh[c] * gam[c] + bet[c] > 0.f)) g = 0.f;
+      }
+      db[c] += g;
+      dg[c] = fmaf(g, xh[c], dg[c]);
+      a[c] = g * gam[c];
+      s1 += a[c];
+      s2 = fmaf(a[c], xh[c], s2);
+    }
+    const float c1 = warp_sum(s1) * inv_f;
+    const float c2 = warp_sum(s2) * inv_f;
+    float* dr = dz + row * lddz;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = lane + 32 * c;
+      if (col < f) dr[col] = rs * (a[c] - c1 - xh[c] * c2);
+    }
+  }
+  // block combine, warps in fixed order
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    if (col < f) {
+      sm[(warp * 2 + 0) * f + col] = dg[c];
+      sm[(warp * 2 + 1) * f + col] = db[c];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * f; i += ROW_THREADS) {
+    const int which = i / f, col = i % f;
+    float s = 0.f;
+    for (int w = 0; w < ROW_WARPS; ++w) s += sm[(w * 2 + which) * f + col];
+    partial[(int64_t)blockIdx.x * 2 * f + i] = s;
+  }
+}
+
+// out[i] (+)= sum_b partial[b*stride + i], b ascending
+__global__ void k_reduce_partials(const float* __restrict__ partial, int nb, int64_t stride, int32_t count,
+                                  float* __restrict__ out, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * stride + i];
+  if (accumulate) s += out[i];
+  out[i] = s;
+}
+
+static int ln_bwd_grid(int32_t n) {
+  int64_t b = ceil_div64(n, ROW_WARPS);
+  if (b > 592) b = 592;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------- ReLU + L2 normalise ----
+template <int MAXC>
+__global__ void __launch_bounds__(ROW_THREADS)
+    k_relu_l2norm_fwd(const float* __restrict__ z, int64_t ldz, float eps, float* __restrict__ y, int64_t ldy,
+                      int32_t n, int32_t f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* zr = z + row * ldz;
+  float v[MAXC];
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    v[c] = col < f ? fmaxf(zr[col], 0.f) : 0.f;
+    q = fmaf(v[c], v[c], q);
+  }
+  const float nrm = fmaxf(sqrtf(warp_sum(q)), eps);  // F.normalize: x / max(||x||_2, eps)
+  float* yr = y + row * ldy;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    if (col < f) yr[col] = v[c] / nrm;
+  }
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(ROW_THREADS)
+    k_relu_l2norm_bwd(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z, int64_t ldz, float eps,
+                      float* __restrict__ dz, int64_t lddz, int32_t n, int32_t f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* zr = z + row * ldz;
+  const float* gr = dy + row * lddy;
+  float r[MAXC], g[MAXC];
+  float q = 0.f, dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    r[c] = col < f ? fmaxf(zr[col], 0.f) : 0.f;
+    g[c] = col < f ? gr[col] : 0.f;
+    q = fmaf(r[c], r[c], q);
+    dot = fmaf(r[c], g[c], dot);
+  }
+  const float nrm_raw = sqrtf(warp_sum(q));
+  dot = warp_sum(dot);
+  const bool clamped = !(nrm_raw > eps);
+  const float nrm = clamped ? eps : nrm_raw;
+  float* dr = dz + row * lddz;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = lane + 32 * c;
+    if (col < f) {
+      // y = r/nrm ; d r = g/nrm - r * (r.g)/nrm^3   (no second term while the norm is clamped)
+      float d = g[c] / nrm;
+      if (!clamped) d -= r[c] * dot / (nrm * nrm * nrm);
+      dr[col] = r[c] > 0.f ? d : 0.f;
+    }
+  }
+}
+
+__global__ void k_relu_fwd(const float* __restrict__ z, int64_t ldz, float* __restrict__ y, int64_t ldy, int32_t n,
+                           int32_t f) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)n * f;
+  for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / f;
+    const int c = (int)(i % f);
+    y[r * ldy + c] = fmaxf(z[r * ldz + c], 0.f);
+  }
+}
+
+__global__ void k_relu_bwd(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z, int64_t ldz,
+                           float* __restrict__ dz, int64_t lddz, int32_t n, int32_t f) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)n * f;
+  for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / f;
+    const int c = (int)(i % f);
+    dz[r * lddz + c] = z[r * ldz + c] > 0.f ? dy[r * lddy + c] : 0.f;
+  }
+}
+
+// -------------------------------------------------------- cross entropy ---
+__device__ __forceinline__ int64_t load_label(const void* labels, int dtype, int64_t i) {
+  if (dtype == GTE_LABEL_I64) return static_cast<const int64_t*>(labels)[i];
+  if (dtype == GTE_LABEL_I32) return static_cast<const int32_t*>(labels)[i];
+  return (int64_t)static_cast<const float*>(labels)[i];  // `.type(torch.long)` truncation, model_train.py:327
+}
+
+constexpr int CE_THREADS = 256;
+
+// per-block partials: [block][3] = {sum w*nll, sum w, #correct}
+__global__ void __launch_bounds__(CE_THREADS)
+    k_ce_fwd(const float* __restrict__ logits, int64_t ld, const void* __restrict__ labels, int label_dtype,
+             const float* __restrict__ class_w, int32_t n, int32_t c, float* __restrict__ partial) {
+  __shared__ float red[3][CE_THREADS / 32];
+  float loss = 0.f, wsum = 0.f, correct = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * CE_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * CE_THREADS) {
+    const float* lr = logits + i * ld;
+    const int64_t yv = load_label(labels, label_dtype, i);
+    float mx = -INFINITY;
+    int arg = 0;
+    for (int j = 0; j < c; ++j) {
+      const float v = lr[j];
+      if (v > mx) {
+        mx = v;
+        arg = j;
+      }
+    }
+    float se = 0.f;
+    for (int j = 0; j < c; ++j) se += expf(lr[j] - mx);
+    if (yv >= 0 && yv < c) {
+      const float wv = class_w ? __ldg(class_w + yv) : 1.0f;
+      const float nll = (mx + logf(se)) - lr[yv];
+      loss = fmaf(wv, nll, loss);
+      wsum += wv;
+    }
+    correct += (arg == (int)yv) ? 1.f : 0.f;
+  }
+  loss = warp_sum(loss);
+  wsum = warp_sum(wsum);
+  correct = warp_sum(correct);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = loss;
+    red[1][threadIdx.x >> 5] = wsum;
+    red[2][threadIdx.x >> 5] = correct;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int w = 0; w < CE_THREADS / 32; ++w) s += red[threadIdx.x][w];
+    partial[(int64_t)blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void k_ce_bwd(const float* __restrict__ logits, int64_t ld, const void* __restrict__ labels,
+                         int label_dtype, const float* __restrict__ class_w, int32_t n, int32_t c,
+                         const float* __restrict__ denominator, float* __restrict__ dl, int64_t lddl) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* lr = logits + i * ld;
+  float* dr = dl + i * lddl;
+  const int64_t yv = load_label(labels, label_dtype, i);
+  const bool valid = yv >= 0 && yv < c;
+  const float den = *denominator;
+  const float wv = valid ? (class_w ? __ldg(class_w + yv) : 1.0f) : 0.f;
+  const float scale = wv / den;
+  float mx = -INFINITY;
+  for (int j = 0; j < c; ++j) mx = fmaxf(mx, lr[j]);
+  float se = 0.f;
+  for (int j = 0; j < c; ++j) se += expf(lr[j] - mx);
+  const float inv = 1.0f / se;
+  for (int j = 0; j < c; ++j) {
+    float p = expf(lr[j] - mx) * inv;
+    if (j == (int)yv) p -= 1.0f;
+    dr[j] = p * scale;
+  }
+}
+
+static int ce_grid(int32_t n) {
+  int64_t b = ceil_div64(n, CE_THREADS);
+  if (b > 296) b = 296;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ----------------------------------------------------------------- Adam ---
+__global__ void k_step_inc(int64_t* step) { *step += 1; }
+
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, int64_t count, float lr, float b1, float b2, float eps, float wd,
+                       int64_t step_host, const int64_t* __restrict__ step_dev, float grad_scale) {
+  const int64_t t = step_dev ? *step_dev : step_host;
+  // bias corrections exactly as torch.optim.Adam's single-tensor path (double maths, then fp32 use)
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    float gi = g[i] * grad_scale;
+    gi = fmaf(wd, pi, gi);  // grad = grad + weight_decay * param
+    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+}  // namespace gte
+
+using namespace gte;
+
+#define GTE_ROW_DISPATCH(KERNEL, F, ...)                                                            \
+  do {                                                                                              \
+    if ((F) <= 32) KERNEL<1> __VA_ARGS__;                                                           \
+    else if ((F) <= 64) KERNEL<2> __VA_ARGS__;                                                      \
+    else if ((F) <= 128) KERNEL<4> __VA_ARGS__;                                                     \
+    else if ((F) <= 256) KERNEL<8> __VA_ARGS__;                                                     \
+    else if ((F) <= 512) KERNEL<16> __VA_ARGS__;                                                    \
+    else KERNEL<32> __VA_ARGS__;                                                                    \
+  } while (0)
+
+extern "C" {
+
+int gte_layernorm_act_fwd(const float* z, int64_t ldz, const float* gamma, const float* beta, float eps, int relu,
+                          float* y, int64_t ldy, float* mean, float* rstd, int32_t n, int32_t f,
+                          gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && f > 0, "gte_layernorm_act_fwd: bad size");
+  if (f > 1024) return fail(GTE_ERR_UNSUPPORTED, "gte_layernorm_act_fwd: f=%d > 1024 not supported", f);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(z && gamma && beta && y && mean && rstd, "gte_layernorm_act_fwd: null argument");
+  GTE_CHECK_ARG(ldz >= f && ldy >= f, "gte_layernorm_act_fwd: leading dimension < f");
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = (unsigned)ceil_div64(n, ROW_WARPS);
+  GTE_ROW_DISPATCH(k_layernorm_act_fwd, f,
+                   <<<grid, ROW_THREADS, 0, st>>>(z, ldz, gamma, beta, eps, relu, y, ldy, mean, rstd, n, f));
+  GTE_CHECK_LAUNCH("k_layernorm_act_fwd");
+  return GTE_OK;
+}
+
+size_t gte_layernorm_act_bwd_workspace_bytes(int32_t n, int32_t f) {
+  if (n < 0 || f <= 0) return 0;
+  return (size_t)ln_bwd_grid(n) * 2 * (size_t)f * 4 + 256;
+}
+
+int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* mean,
+                          const float* rstd, const float* gamma, const float* beta, int relu, float* dz,
+                          int64_t lddz, float* dgamma, float* dbeta, int accumulate, int32_t n, int32_t f, void* ws,
+                          size_t ws_bytes, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && f > 0, "gte_layernorm_act_bwd: bad size");
+  if (f > 1024) return fail(GTE_ERR_UNSUPPORTED, "gte_layernorm_act_bwd: f=%d > 1024 not supported", f);
+  GTE_CHECK_ARG(dgamma && dbeta, "gte_layernorm_act_bwd: null dgamma/dbeta");
+  GTE_CHECK_ARG(n == 0 || (dy && z && mean && rstd && gamma && beta && dz), "gte_layernorm_act_bwd: null argument");
+  GTE_CHECK_ARG(lddy >= f && ldz >= f && lddz >= f, "gte_layernorm_act_bwd: leading dimension < f");
+  const size_t need = gte_layernorm_act_bwd_workspace_bytes(n, f);
+  if (ws == nullptr || ws_bytes < need)
+    return fail(GTE_ERR_WORKSPACE, "gte_layernorm_act_bwd: workspace %zu < required %zu", ws_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  float* partial = static_cast<float*>(ws);
+  const int grid = ln_bwd_grid(n);
+  if (n > 0) {
+    const size_t smem = (size_t)ROW_WARPS * 2 * f * 4;
+    if (smem > 48 * 1024)
+      GTE_CHECK_CUDA(cudaFuncSetAttribute(k_layernorm_act_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem),
+                     "gte_layernorm_act_bwd(smem attr)");
+    GTE_ROW_DISPATCH(k_layernorm_act_bwd, f,
+                     <<<grid, ROW_THREADS, smem, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, beta, relu, dz, lddz,
+                                                      partial, n, f));
+    GTE_CHECK_LAUNCH("k_layernorm_act_bwd");
+  }
+  const int nb = n > 0 ? grid : 0;
+  k_reduce_partials<<<(unsigned)ceil_div64(f, 256), 256, 0, st>>>(partial, nb, 2 * (int64_t)f, f, dgamma, accumulate);
+  GTE_CHECK_LAUNCH("k_reduce_partials");
+  k_reduce_partials<<<(unsigned)ceil_div64(f, 256), 256, 0, st>>>(partial + f, nb, 2 * (int64_t)f, f, dbeta,
+                                                                 accumulate);
+  GTE_CHECK_LAUNCH("k_reduce_partials");
+  return GTE_OK;
+}
+
+int gte_relu_l2norm_fwd(const float* z, int64_t ldz, float eps, float* y, int64_t ldy, int32_t n, int32_t f,
+                        gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && f > 0, "gte_relu_l2norm_fwd: bad size");
+  if (f > 1024) return fail(GTE_ERR_UNSUPPORTED, "gte_relu_l2norm_fwd: f=%d > 1024 not supported", f);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(z && y && ldz >= f && ldy >= f, "gte_relu_l2norm_fwd: bad argument");
+  const unsigned grid = (unsigned)ceil_div64(n, ROW_WARPS);
+  cudaStream_t st = as_stream(stream);
+  GTE_ROW_DISPATCH(k_relu_l2norm_fwd, f, <<<grid, ROW_THREADS, 0, st>>>(z, ldz, eps, y, ldy, n, f));
+  GTE_CHECK_LAUNCH("k_relu_l2norm_fwd");
+  return GTE_OK;
+}
+
+int gte_relu_l2norm_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, float eps, float* dz,
+                        int64_t lddz, int32_t n, int32_t f, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && f > 0, "gte_relu_l2norm_bwd: bad size");
+  if (f > 1024) return fail(GTE_ERR_UNSUPPORTED, "gte_relu_l2norm_bwd: f=%d > 1024 not supported", f);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(dy && z && dz && lddy >= f && ldz >= f && lddz >= f, "gte_relu_l2norm_bwd: bad argument");
+  const unsigned grid = (unsigned)ceil_div64(n, ROW_WARPS);
+  cudaStream_t st = as_stream(stream);
+  GTE_ROW_DISPATCH(k_relu_l2norm_bwd, f, <<<grid, ROW_THREADS, 0, st>>>(dy, lddy, z, ldz, eps, dz, lddz, n, f));
+  GTE_CHECK_LAUNCH("k_relu_l2norm_bwd");
+  return GTE_OK;
+}
+
+static unsigned ew_grid(int64_t total) {
+  int64_t b = ceil_div64(total, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int gte_relu_fwd(const float* z, int64_t ldz, float* y, int64_t ldy, int32_t n, int32_t f, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && f >= 0, "gte_relu_fwd: bad size");
+  if (n == 0 || f == 0) return GTE_OK;
+  GTE_CHECK_ARG(z && y && ldz >= f && ldy >= f, "gte_relu_fwd: bad argument");
+  k_relu_fwd<<<ew_grid((int64_t)n * f), 256, 0, as_stream(stream)>>>(z, ldz, y, ldy, n, f);
+  GTE_CHECK_LAUNCH("k_relu_fwd");
+  return GTE_OK;
+}
+
+int gte_relu_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, float* dz, int64_t lddz, int32_t n,
+                 int32_t f, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && f >= 0, "gte_relu_bwd: bad size");
+  if (n == 0 || f == 0) return GTE_OK;
+  GTE_CHECK_ARG(dy && z && dz && lddy >= f && ldz >= f && lddz >= f, "gte_relu_bwd: bad argument");
+  k_relu_bwd<<<ew_grid((int64_t)n * f), 256, 0, as_stream(stream)>>>(dy, lddy, z, ldz, dz, lddz, n, f);
+  GTE_CHECK_LAUNCH("k_relu_bwd");
+  return GTE_OK;
+}
+
+size_t gte_cross_entropy_workspace_bytes(int32_t n) {
+  if (n < 0) return 0;
+  return (size_t)ce_grid(n) * 3 * 4 + 256;
+}
+
+int gte_cross_entropy_fwd(const float* logits, int64_t ld, const void* labels, int label_dtype, const float* class_w,
+                          int32_t n, int32_t c, float* stats, void* ws, size_t ws_bytes, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && c > 0, "gte_cross_entropy_fwd: bad size");
+  GTE_CHECK_ARG(label_dtype >= GTE_LABEL_I64 && label_dtype <= GTE_LABEL_F32, "gte_cross_entropy_fwd: bad label dtype");
+  GTE_CHECK_ARG(stats != nullptr, "gte_cross_entropy_fwd: stats is null");
+  GTE_CHECK_ARG(n == 0 || (logits && labels && ld >= c), "gte_cross_entropy_fwd: bad argument");
+  const size_t need = gte_cross_entropy_workspace_bytes(n);
+  if (ws == nullptr || ws_bytes < need)
+    return fail(GTE_ERR_WORKSPACE, "gte_cross_entropy_fwd: workspace %zu < required %zu", ws_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  float* partial = static_cast<float*>(ws);
+  const int grid = ce_grid(n);
+  if (n > 0) {
+    k_ce_fwd<<<grid, CE_THREADS, 0, st>>>(logits, ld, labels, label_dtype, class_w, n, c, partial);
+    GTE_CHECK_LAUNCH("k_ce_fwd");
+  }
+  k_reduce_partials<<<1, 32, 0, st>>>(partial, n > 0 ? grid : 0, 3, 3, stats, 0);
+  GTE_CHECK_LAUNCH("k_reduce_partials(ce)");
+  return GTE_OK;
+}
+
+int gte_cross_entropy_bwd(const float* logits, int64_t ld, const void* labels, int label_dtype, const float* class_w,
+                          int32_t n, int32_t c, const float* denominator, float* dlogits, int64_t lddl,
+                          gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && c > 0, "gte_cross_entropy_bwd: bad size");
+  GTE_CHECK_ARG(label_dtype >= GTE_LABEL_I64 && label_dtype <= GTE_LABEL_F32, "gte_cross_entropy_bwd: bad label dtype");
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(logits && labels && denominator && dlogits && ld >= c && lddl >= c, "gte_cross_entropy_bwd: bad argument");
+  k_ce_bwd<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(logits, ld, labels, label_dtype, class_w, n, c,
+                                                                       denominator, dlogits, lddl);
+  GTE_CHECK_LAUNCH("k_ce_bwd");
+  return GTE_OK;
+}
+
+int gte_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step_host, int64_t* step_dev,
+                  float grad_scale, gte_stream_t stream) {
+  GTE_CHECK_ARG(count >= 0, "gte_adam_step: negative count");
+  GTE_CHECK_ARG(step_dev != nullptr || step_host >= 1, "gte_adam_step: step must be >= 1");
+  if (count == 0) return GTE_OK;
+  GTE_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "gte_adam_step: null argument");
+  cudaStream_t st = as_stream(stream);
+  if (step_dev) {
+    k_step_inc<<<1, 1, 0, st>>>(step_dev);
+    GTE_CHECK_LAUNCH("k_step_inc");
+  }
+  k_adam<<<ew_grid(count), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, weight_decay,
+                                        step_host, step_dev, grad_scale);
+  GTE_CHECK_LAUNCH("k_adam");
+  return GTE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+"""Train / inference step engine for ``GcnSAGE`` on the sm_100a kernels.
+
+Restates the train-step envelope of the reference
+(/root/reference/src/models/model_train.py:297,320-332):
+
+    batch_graph = dgl.batch(train_batch).to(device)      -> H2D of one pinned host batch
+    logits = model(batch_graph)                           -> layer kernels (layers.py)
+    loss = CrossEntropyLoss(weight)(logits, labels.long())-> gte_cross_entropy_fwd/bwd
+    optimizer.zero_grad(); loss.backward(); optimizer.step()
+                                                          -> explicit backward kernels writing
+                                                             one flat gradient buffer, one
+                                                             (optional) all-reduce, fused Adam
+
+without autograd bookkeeping, without the per-step ``.item()`` sync, and -- for
+fixed-shape batches -- replayed from a CUDA graph.  Data parallel by graph
+(pages are independent): every rank runs the same step on its own pages; the
+loss is normalised by the GLOBAL label-weight sum (all-reduce of 3 floats) so a
+SUM all-reduce of the flat gradient reproduces the single-GPU result exactly
+(not a mean of per-rank means).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import layers as L
+from . import ops
+from ._lib import GteError
+from .graph import PageGraphBatch
+from .nn import GcnSAGE, _is_relu
+
+
+class SageTrainer:
+    def __init__(self, model: GcnSAGE, lr: float = 0.01, weight_decay: float = 5e-4, betas=(0.9, 0.999),
+                 eps: float = 1e-8, class_weights: Optional[torch.Tensor] = None, process_group=None):
+        self.model = model
+        params = list(model.parameters())
+        if not params or not params[0].is_cuda:
+            raise GteError("SageTrainer: move the model to a CUDA device first (no CPU path)")
+        self.device = params[0].device
+        for layer in model.layers:
+            if layer.activation is not None and not _is_relu(layer.activation):
+                raise GteError("SageTrainer: only activation=F.relu/None is fused; use the nn.Module path otherwise")
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.class_w = None if class_weights is None else class_weights.to(self.device, torch.float32).contiguous()
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+
+        # one flat fp32 buffer for parameters, gradients and both Adam moments;
+        # the nn.Parameters become views, so state_dict()/load_state_dict() keep working
+        total = sum(p.numel() for p in params)
+        # every tensor starts on a 16-byte boundary so the kernels can vectorise
+        offs, o = [], 0
+        for p in params:
+            offs.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        self.flat_param = torch.zeros(o, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(o, dtype=torch.float32, device=self.device)
+        self.exp_avg = torch.zeros(o, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(o, dtype=torch.float32, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.num_params = total
+        self._grad_views: Dict[int, torch.Tensor] = {}
+        with torch.no_grad():
+            for p, off in zip(params, offs):
+                view = self.flat_param[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                gv = self.flat_grad[off:off + p.numel()].view_as(p)
+                p.grad = gv
+                self._grad_views[id(p)] = gv
+        self.stats = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self._graph = None
+        self._static: Optional[Dict[str, torch.Tensor]] = None
+
+    # ----------------------------------------------------------- pieces ----
+    def _layer_args(self, layer):
+        has_ln = isinstance(layer.lynorm, nn.LayerNorm)
+        return (layer.linear.weight.data, None if layer.linear.bias is None else layer.linear.bias.data,
+                layer.lynorm.weight.data if has_ln else None, layer.lynorm.bias.data if has_ln else None, has_ln,
+                layer.lynorm.eps if has_ln else 1e-5, _is_relu(layer.activation))
+
+    def forward(self, g: PageGraphBatch, keep_ctx: bool = True):
+        h = g.ndata["feat"]
+        w_edge = g.edata["feat"]
+        ctxs: List[L.LayerCtx] = []
+        for layer in self.model.layers:
+            W, b, gamma, beta, has_ln, eps, relu = self._layer_args(layer)
+            h, ctx = L.sage_layer_forward(g, h, w_edge, W, b, gamma, beta, ln=has_ln, relu=relu, eps=eps, agg=L.GCN,
+                                          use_pp=layer.use_pp)
+            ctxs.append(ctx if keep_ctx else None)
+        return h, ctxs
+
+    def backward(self, g: PageGraphBatch, ctxs: List[L.LayerCtx], dlogits: torch.Tensor):
+        dy = dlogits
+        layers = list(self.model.layers)
+        for i in range(len(layers) - 1, -1, -1):
+            layer = layers[i]
+            W, b, gamma, beta, has_ln, eps, relu = self._layer_args(layer)
+            gv = self._grad_views
+            dy = L.sage_layer_backward(
+                g, ctxs[i], dy, W, gamma, beta, gv[id(layer.linear.weight)],
+                None if layer.linear.bias is None else gv[id(layer.linear.bias)],
+                gv[id(layer.lynorm.weight)] if has_ln else None, gv[id(layer.lynorm.bias)] if has_ln else None,
+                need_dh=(i > 0), accumulate=False)
+
+    def _all_reduce(self, t: torch.Tensor):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def _step_impl(self, g: PageGraphBatch, labels: torch.Tensor):
+        logits, ctxs = self.forward(g)
+        ops.cross_entropy_fwd(logits, labels, self.class_w, stats=self.stats)
+        self._all_reduce(self.stats)  # global sum w*nll, sum w, #correct
+        dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, self.stats[1:2])
+        self.backward(g, ctxs, dlogits)
+        self._all_reduce(self.flat_grad)
+        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
+                      beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step_dev=self.step_dev)
+        return logits
+
+    # ------------------------------------------------------------- API -----
+    def train_step(self, g: PageGraphBatch, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step.  Returns the device tensor
+        ``[sum w*nll, sum w, #correct]`` (global over ranks); loss = [0]/[1].
+        No host synchronisation happens here."""
+        if labels is None:
+            labels = g.ndata["label"]
+        with torch.cuda.device(self.device):
+            self._step_impl(g, labels)
+        return self.stats
+
+    @torch.no_grad()
+    def predict(self, g: PageGraphBatch) -> torch.Tensor:
+        """Batched inference logits (model_predict.py:144-146 does this page by page)."""
+        with torch.cuda.device(self.device):
+            logits, _ = self.forward(g, keep_ctx=False)
+        return logits
+
+    # ----------------------------------------------------- CUDA graphs -----
+    def capture(self, host_batch: Dict[str, torch.Tensor]):
+        """Capture the whole step (format build + forward + loss + backward +
+        optimiser) for batches with exactly this node / edge count.  Later
+        batches are fed with ``load_batch`` + ``replay``."""
+        dev = self.device
+        n, e = int(host_batch["num_nodes"]), int(host_batch["src"].numel())
+        f = int(host_batch["feat"].shape[1])
+        st = {
+            "src": torch.empty(e, dtype=torch.int32, device=dev),
+            "dst": torch.empty(e, dtype=torch.int32, device=dev),
+            "weight": torch.empty(e, dtype=torch.float32, device=dev),
+            "feat": torch.empty((n, f), dtype=torch.float32, device=dev),
+            "label": torch.empty(n, dtype=torch.float32, device=dev),
+        }
+        self._static = st
+        self._static_meta = (n, e, host_batch["batch_num_nodes"], host_batch["batch_num_edges"])
+        self.load_batch(host_batch)
+
+        def body():
+            g = PageGraphBatch(st["src"], st["dst"], n, self._static_meta[2], self._static_meta[3])
+            g.edata["feat"] = st["weight"]
+            g.ndata["feat"] = st["feat"]
+            self._step_impl(g, st["label"])
+
+        # warm-up on a side stream (allocator + lazy module state), restoring the optimiser state afterwards
+        snap = (self.flat_param.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone())
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        self.flat_param.copy_(snap[0])
+        self.exp_avg.copy_(snap[1])
+        self.exp_avg_sq.copy_(snap[2])
+        self.step_dev.copy_(snap[3])
+        self._graph = graph
+        return graph
+
+    def load_batch(self, host_batch: Dict[str, torch.Tensor]):
+        st = self._static
+        if st is None:
+            raise GteError("load_batch: call capture() first")
+        if int(host_batch["num_nodes"]) != self._static_meta[0] or int(host_batch["src"].numel()) != self._static_meta[1]:
+            raise GteError("load_batch: batch shape differs from the captured one")
+        for k in ("src", "dst", "weight", "feat", "label"):
+            st[k].copy_(host_batch[k], non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
+        self._graph.replay()
+        return self.stats

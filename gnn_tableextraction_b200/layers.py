@@ -1,0 +1,242 @@
+"""Forward / backward of one GraphSAGE layer on the CUDA kernels.
+
+Restates ``GcnSAGELayer.forward`` (/root/reference/src/components/graphs/models.py:46-78)
+and ``WeightedMeanSAGELayer.forward`` (models.py:133-152) plus what torch/DGL
+autograd derives from them, as explicit kernel sequences:
+
+    ah  = post(v) * sum_{u->v} w_e h[u]           gte_spmm on the CSC
+    z   = [h | ah] W^T + b                        gte_linear_fwd (no concat buffer)
+    out = relu(LayerNorm(z))                      gte_layernorm_act_fwd
+
+Two algebraically equal orders are used (A.(H W2^T) = (A.H) W2^T):
+  * ``agg``  aggregate-then-project  (Fin <= Fout: aggregate the narrow input)
+  * ``proj`` project-then-aggregate  (Fout <  Fin: e.g. 218 -> 9 aggregates 9 columns)
+
+Backward (dz -> dW, db, dh) is the transposed pipeline with the reversed-graph
+SpMM on the CSR (deterministic, no atomics).  Nothing here runs on the CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+from .graph import PageGraphBatch
+
+GCN = "gcn"    # sum, then * 1/in_deg (0 for isolated nodes)  -- GcnSAGELayer
+MEAN = "mean"  # sum / max(in_deg, 1)                          -- WeightedMeanSAGELayer (DGL fn.mean)
+
+
+@dataclass
+class LayerCtx:
+    strategy: str = "agg"
+    agg: str = GCN
+    h: Optional[torch.Tensor] = None
+    ah: Optional[torch.Tensor] = None
+    z: Optional[torch.Tensor] = None
+    mean: Optional[torch.Tensor] = None
+    rstd: Optional[torch.Tensor] = None
+    w_edge: Optional[torch.Tensor] = None
+    ln: bool = False
+    relu: bool = False
+    fin: int = 0
+    fout: int = 0
+
+
+def pick_strategy(fin: int, fout: int, use_pp: bool) -> str:
+    if use_pp:
+        return "pp"
+    return "proj" if fout < fin else "agg"
+
+
+def _agg_mode(agg: str) -> int:
+    return _lib.GTE_AGG_SUM_NORM if agg == GCN else _lib.GTE_AGG_MEAN
+
+
+def aggregate_forward(g: PageGraphBatch, h: torch.Tensor, w_edge: torch.Tensor, agg: str = GCN,
+                      addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``update_all(u_mul_e, sum|mean)`` (+ ``* norm``): models.py:53-54,69-71,149."""
+    indptr, indices, _ = g.csc()
+    return ops.spmm(indptr, indices, g.weights_csc(w_edge), h, mode=_agg_mode(agg),
+                    row_norm=g.norm() if agg == GCN else None, addend=addend)
+
+
+def aggregate_backward(g: PageGraphBatch, d_out: torch.Tensor, w_edge: torch.Tensor,
+                       addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """d h[u] = sum_{u->v} w_e * norm[v] * d_out[v] (+ addend[u]) on the CSR (reverse graph)."""
+    indptr, indices, _ = g.csr()
+    return ops.spmm(indptr, indices, g.weights_csr(w_edge), d_out, mode=_lib.GTE_AGG_SUM, pre_scale=g.norm(),
+                    addend=addend)
+
+
+def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Optional[torch.Tensor],
+                       W: torch.Tensor, b: Optional[torch.Tensor], gamma: Optional[torch.Tensor],
+                       beta: Optional[torch.Tensor], *, ln: bool, relu: bool, eps: float = 1e-5, agg: str = GCN,
+                       use_pp: bool = False, strategy: Optional[str] = None):
+    """Returns (out [N, Fout], LayerCtx)."""
+    fout = W.shape[0]
+    fin = W.shape[1] if use_pp else W.shape[1] // 2
+    if h.shape[1] != (W.shape[1] if use_pp else fin):
+        raise _lib.GteError(f"layer expects {W.shape[1] if use_pp else fin} input features, got {h.shape[1]}")
+    st = strategy or pick_strategy(fin, fout, use_pp)
+    ctx = LayerCtx(strategy=st, agg=agg, h=h, ln=ln, relu=relu, fin=fin, fout=fout, w_edge=w_edge)
+    if st == "pp":  # pre-propagated input: plain linear (models.py:49)
+        z = ops.linear_fwd(h, None, W, b)
+    elif st == "agg":
+        ah = aggregate_forward(g, h, w_edge, agg)
+        ctx.ah = ah
+        z = ops.linear_fwd(h, ah, W, b)
+    elif st == "proj":
+        s = ops.linear_fwd(h, None, W, b, w_col0=0)
+        p = ops.linear_fwd(h, None, W, None, w_col0=fin)
+        z = aggregate_forward(g, p, w_edge, agg, addend=s)
+    else:
+        raise _lib.GteError(f"unknown strategy {st}")
+    ctx.z = z
+    if ln:
+        out, ctx.mean, ctx.rstd = ops.layernorm_act_fwd(z, gamma, beta, eps, relu)
+    elif relu:
+        out = ops.relu_fwd(z)
+    else:
+        out = z
+    return out, ctx
+
+
+def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Tensor, W: torch.Tensor,
+                        gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], dW: torch.Tensor,
+                        db: Optional[torch.Tensor], dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor],
+                        *, need_dh: bool, accumulate: bool = False) -> Optional[torch.Tensor]:
+    """Writes dW/db/dgamma/dbeta (overwrite or accumulate) and returns dh (or None)."""
+    fin, fout = ctx.fin, ctx.fout
+    if ctx.ln:
+        dz = ops.layernorm_act_bwd(dy, ctx.z, ctx.mean, ctx.rstd, gamma, beta, ctx.relu, dgamma, dbeta, accumulate)
+    elif ctx.relu:
+        dz = ops.relu_bwd(dy, ctx.z)
+    else:
+        dz = dy
+    if ctx.strategy == "pp":
+        ops.linear_bwd_weight(dz, ctx.h, None, dW, db, accumulate)
+        return ops.linear_bwd_data(dz, W, 0, W.shape[1]) if need_dh else None
+    if ctx.strategy == "agg":
+        ops.linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
+        if not need_dh:
+            return None
+        d_self = ops.linear_bwd_data(dz, W, 0, fin)
+        d_ah = ops.linear_bwd_data(dz, W, fin, fin)
+        return aggregate_backward(g, d_ah, ctx.w_edge, addend=d_self)
+    # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
+    #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn
+    gq = aggregate_backward(g, dz, ctx.w_edge)
+    ops.linear_bwd_weight(dz, ctx.h, None, dW, db, accumulate, w_col0=0)
+    ops.linear_bwd_weight(gq, ctx.h, None, dW, None, accumulate, w_col0=fin)
+    if not need_dh:
+        return None
+    dh = ops.linear_bwd_data(dz, W, 0, fin)
+    ops.linear_bwd_data(gq, W, fin, fin, out=dh, accumulate=True)
+    return dh
+
+
+# ------------------------------------------------------------- autograd ----
+def _as_mat(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2:
+        raise _lib.GteError(f"expected a 2-D feature matrix, got {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+class SageLayerFunction(torch.autograd.Function):
+    """One fused autograd node per layer (replaces ~10 ATen/DGL nodes of the reference)."""
+
+    @staticmethod
+    def forward(ctx, h, W, b, gamma, beta, w_edge, g, ln, relu, eps, agg, use_pp):
+        h = _as_mat(h.detach())
+        out, lctx = sage_layer_forward(g, h, None if w_edge is None else w_edge.detach(), W.detach(),
+                                       None if b is None else b.detach(),
+                                       None if gamma is None else gamma.detach(),
+                                       None if beta is None else beta.detach(),
+                                       ln=ln, relu=relu, eps=eps, agg=agg, use_pp=use_pp)
+        ctx.lctx = lctx
+        ctx.g = g
+        ctx.save_for_backward(W, gamma, beta)
+        ctx.has_b = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        W, gamma, beta = ctx.saved_tensors
+        lctx = ctx.lctx
+        dy = _as_mat(dy)
+        dev = dy.device
+        dW = torch.empty_like(W)
+        db = torch.empty(W.shape[0], dtype=torch.float32, device=dev) if ctx.has_b else None
+        dgamma = torch.empty_like(gamma) if lctx.ln else None
+        dbeta = torch.empty_like(beta) if lctx.ln else None
+        with torch.cuda.device(dev):
+            dh = sage_layer_backward(ctx.g, lctx, dy, W.detach(), None if gamma is None else gamma.detach(),
+                                     None if beta is None else beta.detach(), dW, db, dgamma, dbeta,
+                                     need_dh=ctx.needs_input_grad[0])
+        ctx.lctx = None
+        return dh, dW, db, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+class AggregateFunction(torch.autograd.Function):
+    """``update_all(u_mul_e, sum|mean)`` (+ norm) as a stand-alone differentiable op."""
+
+    @staticmethod
+    def forward(ctx, h, w_edge, g, agg):
+        h = _as_mat(h.detach())
+        ctx.g, ctx.w_edge = g, w_edge.detach()
+        return aggregate_forward(g, h, ctx.w_edge, agg)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _as_mat(dy)
+        with torch.cuda.device(dy.device):
+            dh = aggregate_backward(ctx.g, dy, ctx.w_edge)
+        return dh, None, None, None
+
+
+class ReluL2NormFunction(torch.autograd.Function):
+    """``F.normalize(F.relu(z))`` (models.py:167-169)."""
+
+    @staticmethod
+    def forward(ctx, z, eps):
+        z = _as_mat(z.detach())
+        ctx.z, ctx.eps = z, eps
+        return ops.relu_l2norm_fwd(z, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _as_mat(dy)
+        with torch.cuda.device(dy.device):
+            return ops.relu_l2norm_bwd(dy, ctx.z, ctx.eps), None
+
+
+class CrossEntropyFunction(torch.autograd.Function):
+    """``nn.CrossEntropyLoss(weight)(logits, labels)`` (model_train.py:171,327)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, class_w):
+        logits = _as_mat(logits.detach())
+        stats = ops.cross_entropy_fwd(logits, labels, class_w)
+        ctx.logits, ctx.labels, ctx.class_w, ctx.stats = logits, labels, class_w, stats
+        return stats[0] / stats[1]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        with torch.cuda.device(ctx.logits.device):
+            dl = ops.cross_entropy_bwd(ctx.logits, ctx.labels, ctx.class_w, ctx.stats[1:2])
+        return dl * dloss, None, None
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if labels.dtype not in (torch.int64, torch.int32, torch.float32):
+        labels = labels.long()
+    return CrossEntropyFunction.apply(logits, labels.contiguous(), weight)

@@ -1,0 +1,371 @@
+"""Tensor-level wrappers over the C ABI (``include/gte.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every
+function below validates its tensors, then passes raw device pointers, sizes and
+``torch.cuda.current_stream()`` to ``libgte_b200.so``.  CPU tensors are rejected
+(no CPU fallback).  Matrices are 2-D fp32 with unit column stride; the row stride
+is passed as the leading dimension, so padded / sliced views work unchanged.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GteError, check, lib
+
+_WS = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise GteError("gnn_tableextraction_b200: CPU tensor passed to the CUDA hot path (no CPU fallback exists)")
+
+
+def _mat(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
+    """(ptr, ld, cols) of a 2-D fp32 CUDA matrix with unit column stride."""
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise GteError(f"{name}: expected a 2-D float32 tensor, got {t.dtype} {tuple(t.shape)}")
+    _req_cuda(t)
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise GteError(f"{name}: column stride must be 1 (got strides {t.stride()})")
+    ld = t.stride(0) if t.shape[0] > 1 else max(int(t.shape[1]), 1)
+    if ld < t.shape[1]:
+        raise GteError(f"{name}: row stride {ld} < columns {t.shape[1]}")
+    return t.data_ptr(), int(ld), int(t.shape[1])
+
+
+def _vec(t: Optional[torch.Tensor], name: str, dtype=torch.float32, n: Optional[int] = None) -> Optional[int]:
+    if t is None:
+        return None
+    _req_cuda(t)
+    if t.dtype != dtype or not t.is_contiguous():
+        raise GteError(f"{name}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+    if n is not None and t.numel() < n:
+        raise GteError(f"{name}: {t.numel()} elements < required {n}")
+    return t.data_ptr()
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer that only ever grows.  Kernels on one
+    stream serialise, so sharing it across calls is safe."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def padded_cols(f: int) -> int:
+    """Leading dimension used for internally allocated feature matrices (rows 16-byte aligned)."""
+    return (f + 3) // 4 * 4
+
+
+def empty_padded(n: int, f: int, device) -> torch.Tensor:
+    """[n, f] view of an [n, round_up(f, 4)] buffer so that rows are 128-bit aligned."""
+    return torch.empty((n, padded_cols(f)), dtype=torch.float32, device=device)[:, :f]
+
+
+# ------------------------------------------------------------------ graph ---
+def csx_from_coo(key: torch.Tensor, other: torch.Tensor, n: int):
+    """Stable compressed rows over ``key``: (indptr[n+1], indices[E], eid[E]) int32."""
+    _req_cuda(key, other)
+    if key.dtype != torch.int32 or other.dtype != torch.int32:
+        raise GteError("csx_from_coo: ids must be int32 (builder.py:425)")
+    key, other = key.contiguous(), other.contiguous()
+    e = key.numel()
+    dev = key.device
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(e, dtype=torch.int32, device=dev)
+    eid = torch.empty(e, dtype=torch.int32, device=dev)
+    l = lib()
+    need = l.gte_csx_from_coo_workspace_bytes(n, e)
+    ws = workspace(need, dev)
+    check(
+        l.gte_csx_from_coo(key.data_ptr(), other.data_ptr(), n, e, indptr.data_ptr(), indices.data_ptr(),
+                           eid.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+        "gte_csx_from_coo",
+    )
+    return indptr, indices, eid
+
+
+def batch_concat_csx(pool_indptr, pool_indices, pool_eid, pool_w, pool_node_off, pool_edge_off, page_ids,
+                     batch_node_off, batch_edge_off, n_total: int, e_total: int):
+    dev = pool_indptr.device
+    _req_cuda(pool_indptr, pool_indices, pool_eid, pool_w, pool_node_off, pool_edge_off, page_ids, batch_node_off,
+              batch_edge_off)
+    p = int(page_ids.numel())
+    indptr = torch.empty(n_total + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(e_total, dtype=torch.int32, device=dev)
+    eid = torch.empty(e_total, dtype=torch.int32, device=dev) if pool_eid is not None else None
+    w = torch.empty(e_total, dtype=torch.float32, device=dev) if pool_w is not None else None
+    if p == 0:
+        indptr.zero_()
+    check(
+        lib().gte_batch_concat_csx(_ptr(pool_indptr), _ptr(pool_indices), _ptr(pool_eid), _ptr(pool_w),
+                                   _ptr(pool_node_off), _ptr(pool_edge_off), _ptr(page_ids), _ptr(batch_node_off),
+                                   _ptr(batch_edge_off), p, _ptr(indptr), _ptr(indices), _ptr(eid), _ptr(w),
+                                   _stream()),
+        "gte_batch_concat_csx",
+    )
+    return indptr, indices, eid, w
+
+
+def gather_f32(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _req_cuda(src, idx)
+    out = torch.empty(idx.numel(), dtype=torch.float32, device=src.device)
+    check(lib().gte_gather_f32(_vec(src, "gather.in"), _vec(idx, "gather.idx", torch.int32), out.data_ptr(),
+                               idx.numel(), _stream()), "gte_gather_f32")
+    return out
+
+
+def degree_norm(indptr: torch.Tensor, mode: int = _lib.GTE_NORM_INV_DEG_ZERO) -> torch.Tensor:
+    n = indptr.numel() - 1
+    out = torch.empty(n, dtype=torch.float32, device=indptr.device)
+    check(lib().gte_degree_norm(_vec(indptr, "indptr", torch.int32), n, mode, out.data_ptr(), _stream()),
+          "gte_degree_norm")
+    return out
+
+
+# ------------------------------------------------------------ aggregation ---
+def spmm(indptr, indices, w, x, *, mode=_lib.GTE_AGG_SUM, row_norm=None, pre_scale=None, addend=None, out=None):
+    """y[r] = post(r) * sum_j w[j] * pre[c_j] * x[c_j] (+ addend[r]); see gte.h."""
+    xp, ldx, f = _mat(x, "spmm.x")
+    n_rows = indptr.numel() - 1
+    if out is None:
+        out = empty_padded(n_rows, f, x.device)
+    yp, ldy, fy = _mat(out, "spmm.y")
+    if fy != f or out.shape[0] != n_rows:
+        raise GteError("spmm: output shape mismatch")
+    ap, lda = None, 0
+    if addend is not None:
+        ap, lda, fa = _mat(addend, "spmm.addend")
+        if fa != f or addend.shape[0] != n_rows:
+            raise GteError("spmm: addend shape mismatch")
+    check(
+        lib().gte_spmm(_vec(indptr, "indptr", torch.int32), _vec(indices, "indices", torch.int32),
+                       _vec(w, "w", n=indices.numel()), _vec(pre_scale, "pre_scale"), _vec(row_norm, "row_norm", n=n_rows),
+                       mode, xp, ldx, ap, lda, yp, ldy, n_rows, f, _stream()),
+        "gte_spmm",
+    )
+    return out
+
+
+# ------------------------------------------------------------------ dense ---
+def linear_fwd(x1, x2, W, bias, out=None, w_col0: int = 0):
+    """z = x1 W[:, c0:c0+k1]^T + x2 W[:, c0+k1:c0+k1+k2]^T + bias (x2 may be None)."""
+    x1p, ld1, k1 = _mat(x1, "linear.x1")
+    n = x1.shape[0]
+    x2p, ld2, k2 = (None, 0, 0)
+    if x2 is not None:
+        x2p, ld2, k2 = _mat(x2, "linear.x2")
+        if x2.shape[0] != n:
+            raise GteError("linear_fwd: x1/x2 row mismatch")
+    Wp, ldw, kw = _mat(W, "linear.W")
+    fo = W.shape[0]
+    if w_col0 + k1 + k2 > kw:
+        raise GteError(f"linear_fwd: W has {kw} columns < {w_col0 + k1 + k2}")
+    if out is None:
+        out = empty_padded(n, fo, x1.device)
+    zp, ldz, fz = _mat(out, "linear.z")
+    if fz != fo or out.shape[0] != n:
+        raise GteError("linear_fwd: output shape mismatch")
+    check(
+        lib().gte_linear_fwd(x1p, ld1, k1, x2p, ld2, k2, Wp + 4 * w_col0, ldw, _vec(bias, "bias", n=fo), zp, ldz, n, fo,
+                             _stream()),
+        "gte_linear_fwd",
+    )
+    return out
+
+
+def linear_bwd_data(dz, W, col0: int, k: int, row_scale=None, out=None, accumulate=False):
+    dzp, lddz, fo = _mat(dz, "bwd_data.dz")
+    Wp, ldw, kw = _mat(W, "bwd_data.W")
+    if W.shape[0] != fo or col0 + k > kw:
+        raise GteError("linear_bwd_data: W shape mismatch")
+    n = dz.shape[0]
+    if out is None:
+        if accumulate:
+            raise GteError("linear_bwd_data: accumulate needs an output")
+        out = empty_padded(n, k, dz.device)
+    dxp, lddx, kx = _mat(out, "bwd_data.dx")
+    if kx != k or out.shape[0] != n:
+        raise GteError("linear_bwd_data: output shape mismatch")
+    check(
+        lib().gte_linear_bwd_data(dzp, lddz, fo, Wp, ldw, col0, k, _vec(row_scale, "row_scale", n=n), dxp, lddx, n,
+                                  1 if accumulate else 0, _stream()),
+        "gte_linear_bwd_data",
+    )
+    return out
+
+
+def linear_bwd_weight(dz, x1, x2, dW, db, accumulate=False, w_col0: int = 0):
+    """dW[:, c0:c0+k1+k2] (+)= dz^T [x1 | x2]; db (+)= colsum(dz) (db may be None)."""
+    dzp, lddz, fo = _mat(dz, "bwd_weight.dz")
+    n = dz.shape[0]
+    x1p, ld1, k1 = _mat(x1, "bwd_weight.x1")
+    x2p, ld2, k2 = (None, 0, 0)
+    if x2 is not None:
+        x2p, ld2, k2 = _mat(x2, "bwd_weight.x2")
+    dWp, lddw, kw = _mat(dW, "bwd_weight.dW")
+    if dW.shape[0] != fo or w_col0 + k1 + k2 > kw:
+        raise GteError("linear_bwd_weight: dW shape mismatch")
+    l = lib()
+    need = l.gte_linear_bwd_weight_workspace_bytes(n, fo, k1, k2)
+    ws = workspace(need, dz.device)
+    check(
+        l.gte_linear_bwd_weight(dzp, lddz, fo, x1p, ld1, k1, x2p, ld2, k2, dWp + 4 * w_col0, lddw,
+                                _vec(db, "db", n=fo), 1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),
+        "gte_linear_bwd_weight",
+    )
+
+
+# ---------------------------------------------------------------- row ops ---
+def layernorm_act_fwd(z, gamma, beta, eps: float, relu: bool, out=None):
+    zp, ldz, f = _mat(z, "ln.z")
+    n = z.shape[0]
+    if out is None:
+        out = empty_padded(n, f, z.device)
+    yp, ldy, _ = _mat(out, "ln.y")
+    mean = torch.empty(n, dtype=torch.float32, device=z.device)
+    rstd = torch.empty(n, dtype=torch.float32, device=z.device)
+    check(
+        lib().gte_layernorm_act_fwd(zp, ldz, _vec(gamma, "gamma", n=f), _vec(beta, "beta", n=f), float(eps),
+                                    1 if relu else 0, yp, ldy, mean.data_ptr(), rstd.data_ptr(), n, f, _stream()),
+        "gte_layernorm_act_fwd",
+    )
+    return out, mean, rstd
+
+
+def layernorm_act_bwd(dy, z, mean, rstd, gamma, beta, relu: bool, dgamma, dbeta, accumulate=False, out=None):
+    dyp, lddy, f = _mat(dy, "ln_bwd.dy")
+    zp, ldz, _ = _mat(z, "ln_bwd.z")
+    n = dy.shape[0]
+    if out is None:
+        out = empty_padded(n, f, dy.device)
+    dzp, lddz, _ = _mat(out, "ln_bwd.dz")
+    l = lib()
+    need = l.gte_layernorm_act_bwd_workspace_bytes(n, f)
+    ws = workspace(need, dy.device)
+    check(
+        l.gte_layernorm_act_bwd(dyp, lddy, zp, ldz, _vec(mean, "mean", n=n), _vec(rstd, "rstd", n=n),
+                                _vec(gamma, "gamma", n=f), _vec(beta, "beta", n=f), 1 if relu else 0, dzp, lddz,
+                                _vec(dgamma, "dgamma", n=f), _vec(dbeta, "dbeta", n=f), 1 if accumulate else 0, n, f,
+                                ws.data_ptr(), ws.numel(), _stream()),
+        "gte_layernorm_act_bwd",
+    )
+    return out
+
+
+def relu_l2norm_fwd(z, eps: float = 1e-12, out=None):
+    zp, ldz, f = _mat(z, "l2.z")
+    n = z.shape[0]
+    if out is None:
+        out = empty_padded(n, f, z.device)
+    yp, ldy, _ = _mat(out, "l2.y")
+    check(lib().gte_relu_l2norm_fwd(zp, ldz, float(eps), yp, ldy, n, f, _stream()), "gte_relu_l2norm_fwd")
+    return out
+
+
+def relu_l2norm_bwd(dy, z, eps: float = 1e-12, out=None):
+    dyp, lddy, f = _mat(dy, "l2_bwd.dy")
+    zp, ldz, _ = _mat(z, "l2_bwd.z")
+    n = dy.shape[0]
+    if out is None:
+        out = empty_padded(n, f, dy.device)
+    dzp, lddz, _ = _mat(out, "l2_bwd.dz")
+    check(lib().gte_relu_l2norm_bwd(dyp, lddy, zp, ldz, float(eps), dzp, lddz, n, f, _stream()), "gte_relu_l2norm_bwd")
+    return out
+
+
+def relu_fwd(z, out=None):
+    zp, ldz, f = _mat(z, "relu.z")
+    n = z.shape[0]
+    if out is None:
+        out = empty_padded(n, f, z.device)
+    yp, ldy, _ = _mat(out, "relu.y")
+    check(lib().gte_relu_fwd(zp, ldz, yp, ldy, n, f, _stream()), "gte_relu_fwd")
+    return out
+
+
+def relu_bwd(dy, z, out=None):
+    dyp, lddy, f = _mat(dy, "relu_bwd.dy")
+    zp, ldz, _ = _mat(z, "relu_bwd.z")
+    n = dy.shape[0]
+    if out is None:
+        out = empty_padded(n, f, dy.device)
+    dzp, lddz, _ = _mat(out, "relu_bwd.dz")
+    check(lib().gte_relu_bwd(dyp, lddy, zp, ldz, dzp, lddz, n, f, _stream()), "gte_relu_bwd")
+    return out
+
+
+# ------------------------------------------------------- loss / optimiser ---
+_LABEL_DT = {torch.int64: _lib.GTE_LABEL_I64, torch.int32: _lib.GTE_LABEL_I32, torch.float32: _lib.GTE_LABEL_F32}
+
+
+def _labels(labels: torch.Tensor):
+    _req_cuda(labels)
+    if labels.dtype not in _LABEL_DT or not labels.is_contiguous():
+        raise GteError(f"labels: expected contiguous int64/int32/float32, got {labels.dtype}")
+    return labels.data_ptr(), _LABEL_DT[labels.dtype]
+
+
+def cross_entropy_fwd(logits, labels, class_w=None, stats=None):
+    """stats = [sum w*nll, sum w, #correct] (float32[3], device)."""
+    lp, ld, c = _mat(logits, "ce.logits")
+    n = logits.shape[0]
+    yp, ydt = _labels(labels)
+    if labels.numel() != n:
+        raise GteError("cross_entropy: labels/logits row mismatch")
+    if stats is None:
+        stats = torch.empty(3, dtype=torch.float32, device=logits.device)
+    l = lib()
+    ws = workspace(l.gte_cross_entropy_workspace_bytes(n), logits.device)
+    check(
+        l.gte_cross_entropy_fwd(lp, ld, yp, ydt, _vec(class_w, "class_w", n=c), n, c, _vec(stats, "stats", n=3),
+                                ws.data_ptr(), ws.numel(), _stream()),
+        "gte_cross_entropy_fwd",
+    )
+    return stats
+
+
+def cross_entropy_bwd(logits, labels, class_w, denominator, out=None):
+    lp, ld, c = _mat(logits, "ce.logits")
+    n = logits.shape[0]
+    yp, ydt = _labels(labels)
+    if out is None:
+        out = empty_padded(n, c, logits.device)
+    dp, ldd, _ = _mat(out, "ce.dlogits")
+    _req_cuda(denominator)
+    check(
+        lib().gte_cross_entropy_bwd(lp, ld, yp, ydt, _vec(class_w, "class_w", n=c), n, c, denominator.data_ptr(), dp,
+                                    ldd, _stream()),
+        "gte_cross_entropy_bwd",
+    )
+    return out
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+              step: int = 0, step_dev: Optional[torch.Tensor] = None, grad_scale: float = 1.0):
+    count = param.numel()
+    for t, nm in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _vec(t, nm, n=count)
+    if step_dev is not None:
+        _vec(step_dev, "step_dev", torch.int64, 1)
+    check(
+        lib().gte_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), count,
+                            float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                            _ptr(step_dev), float(grad_scale), _stream()),
+        "gte_adam_step",
+    )

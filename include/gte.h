@@ -1,0 +1,224 @@
+/*
+ * gte.h -- C ABI of libgte_b200.so: the B200-native (sm_100a) graph-convolution
+ * hot path of AILab-UniFI/GNN-TableExtraction.
+ *
+ * The reference has no FFI of its own: the path sits behind the Python
+ * nn.Module API of /root/reference/src/components/graphs/models.py and reaches
+ * its arithmetic through DGL (`g.update_all`, `g.in_degrees`) and ATen
+ * (`nn.Linear`, `nn.LayerNorm`, `F.relu`).  Each entry point below names the
+ * reference call site (file:line under /root/reference) that it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned (PyTorch) storage,
+ *     unless the parameter name ends in `_host`;
+ *   - the library never allocates or frees user-visible memory and keeps no
+ *     reference after return; scratch space is passed in (`ws`, `ws_bytes`,
+ *     sizes from the matching `*_workspace_bytes` query);
+ *   - every launch goes to the `stream` passed in (a cudaStream_t); nothing
+ *     synchronises the device, so all entries are CUDA-graph capturable;
+ *   - every entry returns 0 on success and a negative GTE_ERR_* otherwise;
+ *     `gte_last_error_string()` (thread-local) explains the failure.  No C++
+ *     exception crosses the ABI.  There is NO CPU fallback: host pointers are
+ *     rejected where detectable, and the Python host layer refuses to run
+ *     without this library;
+ *   - node / edge ids are int32 (builder.py:425), row offsets are computed in
+ *     64-bit; features, weights and parameters are fp32 (model_train.py:295);
+ *   - feature matrices are row-major with an explicit leading dimension `ld*`
+ *     (in floats).  Kernels vectorise to 128-bit accesses when the pointers are
+ *     16-byte aligned and the leading dimensions are multiples of 4; columns in
+ *     [f, ld) are padding and are never interpreted.
+ */
+#ifndef GTE_H_
+#define GTE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gte_stream_t; /* cudaStream_t */
+
+#define GTE_ABI_VERSION 1
+
+#define GTE_OK 0
+#define GTE_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, bad enum) */
+#define GTE_ERR_UNSUPPORTED (-2) /* shape / device not supported by this build */
+#define GTE_ERR_CUDA (-3)        /* a CUDA runtime call or launch failed */
+#define GTE_ERR_WORKSPACE (-4)   /* workspace missing or too small */
+
+/* aggregation modes of gte_spmm */
+#define GTE_AGG_SUM 0       /* y = sum_e w_e x[src]                      (models.py:53-54) */
+#define GTE_AGG_SUM_NORM 1  /* y = norm[v] * sum_e w_e x[src]            (models.py:69-71) */
+#define GTE_AGG_MEAN 2      /* y = (sum_e w_e x[src]) / max(deg[v], 1)   (models.py:149)   */
+
+/* degree-normaliser modes of gte_degree_norm */
+#define GTE_NORM_INV_DEG_ZERO 0 /* 1/deg, 0 where deg == 0  (models.py:74-78 get_norm)     */
+#define GTE_NORM_INV_DEG_CLAMP 1 /* 1/max(deg,1)            (DGL fn.mean, models.py:149)   */
+
+/* label dtypes of the cross-entropy entries */
+#define GTE_LABEL_I64 0
+#define GTE_LABEL_I32 1
+#define GTE_LABEL_F32 2 /* the reference stores labels as float32 (loader.py:350-354) */
+
+/* ---------------------------------------------------------------- misc -- */
+int gte_abi_version(void);
+const char* gte_last_error_string(void);
+/* Kernels launched by this library since it was loaded (process-wide diagnostic counter). */
+int64_t gte_launch_count(void);
+/* SM count and compute capability of the current device. */
+int gte_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ----------------------------------------------------- graph formats ---- */
+/*
+ * Stable COO -> compressed rows over `key` (key = dst gives the CSC that
+ * `update_all` aggregates over, models.py:53-54; key = src gives the CSR that
+ * autograd's reverse-graph SpMM needs).  Replaces DGL's lazy per-batch format
+ * build.  Output is bit-identical to a stable sort of the COO by `key`:
+ *   indptr [n+1], indices [e] (= `other` in row order), eid [e] (= original
+ *   edge position; ties inside a row ascending by eid).
+ */
+size_t gte_csx_from_coo_workspace_bytes(int32_t n, int64_t e);
+int gte_csx_from_coo(const int32_t* key, const int32_t* other, int32_t n, int64_t e,
+                     int32_t* indptr, int32_t* indices, int32_t* eid,
+                     void* ws, size_t ws_bytes, gte_stream_t stream);
+
+/*
+ * Batch assembly from device-resident per-page compressed rows: replaces
+ * `dgl.batch(train_batch).to(device)` + the lazy format build
+ * (model_train.py:297).  `pool_*` hold every page of the dataset back to back
+ * with page-local ids (`pool_indptr` has n_i+1 entries per page).  Page p of the
+ * batch is dataset page `page_ids[p]`; `pool_node_off/pool_edge_off` index the
+ * pools ([num_pool_pages+1], with pool_indptr offset = node_off + page index),
+ * `batch_node_off/batch_edge_off` ([num_pages+1]) are the exclusive scans of
+ * the batch's page sizes.  Result equals gte_csx_from_coo on the batched COO.
+ * `pool_w`/`w_out` (row-order edge weights) may both be NULL.
+ */
+int gte_batch_concat_csx(const int32_t* pool_indptr, const int32_t* pool_indices,
+                         const int32_t* pool_eid, const float* pool_w,
+                         const int64_t* pool_node_off, const int64_t* pool_edge_off,
+                         const int32_t* page_ids, const int64_t* batch_node_off,
+                         const int64_t* batch_edge_off, int32_t num_pages,
+                         int32_t* indptr, int32_t* indices, int32_t* eid, float* w_out,
+                         gte_stream_t stream);
+
+/* out[i] = in[idx[i]]  (edge weights into row order: w_row = edata['feat'][eid]) */
+int gte_gather_f32(const float* in, const int32_t* idx, float* out, int64_t count, gte_stream_t stream);
+
+/* norm[v] from in-degrees (indptr differences).  models.py:74-78 */
+int gte_degree_norm(const int32_t* indptr, int32_t n, int mode, float* norm, gte_stream_t stream);
+
+/* ------------------------------------------------------- aggregation ---- */
+/*
+ * Gather + segment-reduce SpMM over compressed rows (forward on the CSC,
+ * backward on the CSR of the same graph -- deterministic, no atomics):
+ *
+ *   y[r,:] = post(r) * sum_{j in [indptr[r], indptr[r+1])} w[j] * pre[c_j] * x[c_j,:]  (+ addend[r,:])
+ *
+ * with c_j = indices[j]; `w` (row order) NULL = 1; `pre_scale` [n_cols-side]
+ * NULL = 1; post(r) by `mode`: SUM -> 1, SUM_NORM -> row_norm[r], MEAN ->
+ * 1/max(deg r,1) (true division).  `addend` NULL = 0.
+ * Forward  (models.py:53-54,69-71): mode SUM_NORM, row_norm = norm.
+ * Backward (DGL GSpMM.backward on the reversed graph): CSR rows, w in CSR
+ * order, pre_scale = norm (d(ah*norm)), addend = the self-path gradient.
+ */
+int gte_spmm(const int32_t* indptr, const int32_t* indices, const float* w,
+             const float* pre_scale, const float* row_norm, int mode,
+             const float* x, int64_t ldx, const float* addend, int64_t ldadd,
+             float* y, int64_t ldy, int32_t n_rows, int32_t f, gte_stream_t stream);
+
+/* ------------------------------------------------- dense projection ----- */
+/*
+ * z[n,fo] = x1[n,k1] W[:, 0:k1]^T + x2[n,k2] W[:, k1:k1+k2]^T + bias
+ * = nn.Linear over cat(h, ah*norm) without materialising the concatenation
+ * (models.py:63,69-72; W is [fo, k1+k2] row-major with leading dimension ldw;
+ * the self block comes first).  x2 may be NULL (k2 = 0); bias may be NULL.
+ */
+int gte_linear_fwd(const float* x1, int64_t ldx1, int32_t k1,
+                   const float* x2, int64_t ldx2, int32_t k2,
+                   const float* W, int64_t ldw, const float* bias,
+                   float* z, int64_t ldz, int32_t n, int32_t fo, gte_stream_t stream);
+
+/*
+ * dx[n,k] (+)= (dz[n,fo] W[:, col0:col0+k]) * row_scale[r]   (autograd of nn.Linear
+ * w.r.t. its input, one column block at a time; row_scale NULL = 1;
+ * accumulate != 0 adds into dx).
+ */
+int gte_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo,
+                        const float* W, int64_t ldw, int32_t col0, int32_t k,
+                        const float* row_scale, float* dx, int64_t lddx, int32_t n,
+                        int accumulate, gte_stream_t stream);
+
+/*
+ * dW[fo, k1+k2] = dz^T [x1 | x2]  and  db[fo] = column sums of dz (db may be
+ * NULL).  Deterministic: fixed-shape split over the rows + fixed-order
+ * reduction, no atomics.  `accumulate` != 0 adds into dW/db (autograd .grad
+ * semantics), otherwise overwrites.
+ */
+size_t gte_linear_bwd_weight_workspace_bytes(int32_t n, int32_t fo, int32_t k1, int32_t k2);
+int gte_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo,
+                          const float* x1, int64_t ldx1, int32_t k1,
+                          const float* x2, int64_t ldx2, int32_t k2,
+                          float* dW, int64_t lddw, float* db, int accumulate, int32_t n,
+                          void* ws, size_t ws_bytes, gte_stream_t stream);
+
+/* ------------------------------------------- row normalisation + act ---- */
+/*
+ * y = act(LayerNorm(z; gamma, beta, eps)) per row over the first f columns
+ * (models.py:64-66; nn.LayerNorm biased variance).  relu != 0 applies F.relu.
+ * Saves mean/rstd [n] for the backward.  y may alias z.
+ */
+int gte_layernorm_act_fwd(const float* z, int64_t ldz, const float* gamma, const float* beta,
+                          float eps, int relu, float* y, int64_t ldy, float* mean, float* rstd,
+                          int32_t n, int32_t f, gte_stream_t stream);
+size_t gte_layernorm_act_bwd_workspace_bytes(int32_t n, int32_t f);
+/* dz may alias dy.  dgamma/dbeta [f]: deterministic two-stage reduction. */
+int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz,
+                          const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, int relu, float* dz, int64_t lddz,
+                          float* dgamma, float* dbeta, int accumulate, int32_t n, int32_t f,
+                          void* ws, size_t ws_bytes, gte_stream_t stream);
+
+/* y = normalize(relu(z)) : F.relu + F.normalize(p=2, dim=1, eps) (models.py:168-169) */
+int gte_relu_l2norm_fwd(const float* z, int64_t ldz, float eps, float* y, int64_t ldy,
+                        int32_t n, int32_t f, gte_stream_t stream);
+int gte_relu_l2norm_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, float eps,
+                        float* dz, int64_t lddz, int32_t n, int32_t f, gte_stream_t stream);
+/* elementwise relu helpers for activation=F.relu without LayerNorm */
+int gte_relu_fwd(const float* z, int64_t ldz, float* y, int64_t ldy, int32_t n, int32_t f, gte_stream_t stream);
+int gte_relu_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, float* dz, int64_t lddz,
+                 int32_t n, int32_t f, gte_stream_t stream);
+
+/* ------------------------------------------------ loss and optimiser ---- */
+/*
+ * nn.CrossEntropyLoss(weight=class_w) forward statistics (model_train.py:171,327-328):
+ * stats[0] = sum_i w[y_i] * nll_i, stats[1] = sum_i w[y_i], stats[2] = #(argmax == y).
+ * The loss is stats[0]/stats[1].  class_w NULL = all ones.  Deterministic.
+ */
+size_t gte_cross_entropy_workspace_bytes(int32_t n);
+int gte_cross_entropy_fwd(const float* logits, int64_t ld, const void* labels, int label_dtype,
+                          const float* class_w, int32_t n, int32_t c, float* stats,
+                          void* ws, size_t ws_bytes, gte_stream_t stream);
+/* dlogits[i,:] = w[y_i] * (softmax(logits[i]) - onehot(y_i)) / *denominator   (device scalar:
+ * the GLOBAL sum of w[y_i]; single GPU: &stats[1]; data parallel: its all-reduce). */
+int gte_cross_entropy_bwd(const float* logits, int64_t ld, const void* labels, int label_dtype,
+                          const float* class_w, int32_t n, int32_t c, const float* denominator,
+                          float* dlogits, int64_t lddl, gte_stream_t stream);
+
+/*
+ * torch.optim.Adam(lr, betas, eps, weight_decay) with L2-in-gradient decay over
+ * a flat parameter buffer (model_train.py:168,332).  The 1-based step count is
+ * `step_host`, or -- when `step_dev` is non-NULL -- a device counter that this
+ * call increments first and then uses (CUDA-graph replay safe).  grad_scale
+ * multiplies the gradient first.
+ */
+int gte_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  int64_t count, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int64_t step_host, int64_t* step_dev, float grad_scale,
+                  gte_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTE_H_ */

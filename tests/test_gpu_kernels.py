@@ -1,0 +1,312 @@
+"""GPU parity tests of the individual C-ABI entry points against the CPU oracle
+(bit-exact for the integer formats, <= 1e-5 relative -- usually 1e-6 -- for fp32)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import TOL, rel_err
+from gnn_tableextraction_b200 import _lib, ops, synth
+from oracle import csx
+from oracle import sage_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _i32(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.int32, device=DEV)
+
+
+def _f32(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float32, device=DEV)
+
+
+def _padded(t):
+    """copy a CPU [n, f] tensor into a 16-byte-aligned padded device view"""
+    out = ops.empty_padded(t.shape[0], t.shape[1], DEV)
+    out.copy_(t)
+    return out
+
+
+# ----------------------------------------------------------- formats --------
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (5, 0, 1), (1, 7, 2), (50, 400, 3), (1000, 20000, 4), (37, 5000, 5),
+                                      (200_000, 1_000_000, 6)])
+def test_csx_from_coo_bit_exact(n, e, seed):
+    src, dst, _ = synth.random_multigraph(seed, n, e) if e else (np.zeros(0, np.int32),) * 2 + (None,)
+    for key, other in ((dst, src), (src, dst)):  # CSC and CSR
+        ip, ix, ei = csx.csx_from_coo(key, other, n)
+        gp, gx, ge = ops.csx_from_coo(_i32(key), _i32(other), n)
+        assert np.array_equal(gp.cpu().numpy(), ip)
+        assert np.array_equal(gx.cpu().numpy(), ix)
+        assert np.array_equal(ge.cpu().numpy(), ei)
+
+
+def test_csx_hub_rows_longer_than_a_warp():
+    rng = np.random.default_rng(0)
+    n, e = 64, 6000
+    dst = np.where(rng.random(e) < 0.6, 3, rng.integers(0, n, e)).astype(np.int32)  # row 3 has ~3600 entries
+    src = rng.integers(0, n, e).astype(np.int32)
+    ip, ix, ei = csx.csx_from_coo(dst, src, n)
+    gp, gx, ge = ops.csx_from_coo(_i32(dst), _i32(src), n)
+    assert np.array_equal(gp.cpu().numpy(), ip) and np.array_equal(gx.cpu().numpy(), ix)
+    assert np.array_equal(ge.cpu().numpy(), ei)
+
+
+def test_csx_batched_pages_and_concat_kernel():
+    pages = synth.make_pages(24, ragged=True, k=6)
+    s, d, w, noff, eoff = csx.batch_coo(pages)
+    n = int(noff[-1])
+    for key, other in ((d, s), (s, d)):
+        ip, ix, ei = csx.csx_from_coo(key, other, n)
+        gp, gx, ge = ops.csx_from_coo(_i32(key), _i32(other), n)
+        assert np.array_equal(gp.cpu().numpy(), ip) and np.array_equal(gx.cpu().numpy(), ix)
+        assert np.array_equal(ge.cpu().numpy(), ei)
+    # device-resident per-page pool -> batch by offset concatenation == stable sort of the batched COO
+    from gnn_tableextraction_b200.pool import PagePool
+
+    pool = PagePool(pages, device=DEV)
+    order = [5, 0, 23, 7, 7, 11]
+    sub = [pages[i] for i in order]
+    s2, d2, w2, noff2, _ = csx.batch_coo(sub)
+    g = pool.batch(order)
+    ip, ix, ei = csx.csx_from_coo(d2, s2, int(noff2[-1]))
+    assert np.array_equal(g.csc()[0].cpu().numpy(), ip)
+    assert np.array_equal(g.csc()[1].cpu().numpy(), ix)
+    assert np.array_equal(g.csc()[2].cpu().numpy(), ei)
+    ip, ix, ei = csx.csx_from_coo(s2, d2, int(noff2[-1]))
+    assert np.array_equal(g.csr()[0].cpu().numpy(), ip)
+    assert np.array_equal(g.csr()[1].cpu().numpy(), ix)
+    assert np.array_equal(g.csr()[2].cpu().numpy(), ei)
+    assert np.array_equal(g.edges()[0].cpu().numpy(), s2) and np.array_equal(g.edges()[1].cpu().numpy(), d2)
+    assert np.array_equal(g.edata["feat"].cpu().numpy(), w2)
+    assert np.array_equal(g.weights_csc(g.edata["feat"]).cpu().numpy(), w2[csx.csx_from_coo(d2, s2, int(noff2[-1]))[2]])
+    assert np.array_equal(g.ndata["feat"].cpu().numpy(), np.concatenate([p.feat for p in sub]))
+
+
+def test_degree_norm_and_gather():
+    src, dst, w = synth.random_multigraph(1, 300, 2000)
+    ip, _, ei = csx.csx_from_coo(dst, src, 300)
+    deg = np.diff(ip).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        n0 = np.where(deg > 0, 1.0 / deg, 0.0).astype(np.float32)
+    assert np.array_equal(ops.degree_norm(_i32(ip), _lib.GTE_NORM_INV_DEG_ZERO).cpu().numpy(), n0)
+    n1 = (1.0 / np.maximum(deg, 1)).astype(np.float32)
+    assert np.array_equal(ops.degree_norm(_i32(ip), _lib.GTE_NORM_INV_DEG_CLAMP).cpu().numpy(), n1)
+    assert np.array_equal(ops.gather_f32(_f32(w), _i32(ei)).cpu().numpy(), w[ei])
+
+
+# -------------------------------------------------------------- spmm --------
+@pytest.mark.parametrize("f", [1, 3, 4, 9, 13, 16, 31, 64, 100, 128, 218, 256, 300, 512, 700])
+@pytest.mark.parametrize("padded", [True, False])
+def test_spmm_matches_oracle(f, padded):
+    n, e = 500, 6000
+    src, dst, w = synth.random_multigraph(f, n, e)
+    h = torch.randn(n, f, generator=torch.Generator().manual_seed(f))
+    st, dt, wt = torch.from_numpy(src), torch.from_numpy(dst), torch.from_numpy(w)
+    ip, ix, ei = ops.csx_from_coo(_i32(dst), _i32(src), n)
+    w_row = ops.gather_f32(_f32(w), ei)
+    hd = _padded(h) if padded else h.to(DEV)
+    out_pad = None if padded else torch.empty(n, f, device=DEV)
+    # GcnSAGE: sum * norm
+    norm = ops.degree_norm(ip)
+    y = ops.spmm(ip, ix, w_row, hd, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm, out=out_pad)
+    deg = so.in_degrees(dt, n).float().unsqueeze(1)
+    nrm = torch.where(deg > 0, 1.0 / deg, torch.zeros_like(deg))
+    exp = so.u_mul_e_sum(st, dt, wt, h, n) * nrm
+    assert rel_err(y, exp) < 2e-6
+    assert torch.all(y.cpu()[deg.squeeze(1) == 0] == 0)  # isolated nodes exactly 0
+    # mean
+    y = ops.spmm(ip, ix, w_row, hd, mode=_lib.GTE_AGG_MEAN)
+    assert rel_err(y, so.u_mul_e_mean(st, dt, wt, h, n)) < 2e-6
+    # plain sum, unweighted, with addend and source-side scale (the backward form)
+    pre = torch.rand(n)
+    add = torch.randn(n, f)
+    y = ops.spmm(ip, ix, None, hd, mode=_lib.GTE_AGG_SUM, pre_scale=pre.to(DEV), addend=_padded(add) if padded else add.to(DEV))
+    exp = so.u_mul_e_sum(st, dt, torch.ones(e), h * pre.unsqueeze(1), n) + add
+    assert rel_err(y, exp) < 2e-6
+
+
+def test_spmm_transposed_is_autograd_of_forward():
+    pages = synth.make_pages(4, n=120, k=7)
+    s, d, w, noff, _ = csx.batch_coo(pages)
+    n, f = int(noff[-1]), 50
+    h = torch.randn(n, f, requires_grad=True)
+    up = torch.randn(n, f)
+    st, dt, wt = torch.from_numpy(s), torch.from_numpy(d), torch.from_numpy(w)
+    deg = so.in_degrees(dt, n).float().unsqueeze(1)
+    nrm = torch.where(deg > 0, 1.0 / deg, torch.zeros_like(deg))
+    ((so.u_mul_e_sum(st, dt, wt, h, n) * nrm) * up).sum().backward()
+    ipc, _, _ = ops.csx_from_coo(_i32(d), _i32(s), n)
+    ip, ix, ei = ops.csx_from_coo(_i32(s), _i32(d), n)  # CSR: rows = sources
+    dh = ops.spmm(ip, ix, ops.gather_f32(_f32(w), ei), _padded(up), mode=_lib.GTE_AGG_SUM, pre_scale=ops.degree_norm(ipc))
+    assert rel_err(dh, h.grad) < 2e-6
+
+
+def test_spmm_large_linearity_and_determinism():
+    """Size-independent properties at config-2 scale (512 pages x 300 nodes, F=218)."""
+    pages = synth.make_pages(512, distinct=16)
+    s, d, w, noff, _ = csx.batch_coo(pages)
+    n, f = int(noff[-1]), 218
+    ip, ix, ei = ops.csx_from_coo(_i32(d), _i32(s), n)
+    w_row = ops.gather_f32(_f32(w), ei)
+    norm = ops.degree_norm(ip)
+    a = _padded(torch.randn(n, f))
+    b = _padded(torch.randn(n, f))
+    run = lambda x: ops.spmm(ip, ix, w_row, x, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
+    ya, yb = run(a), run(b)
+    c = ops.empty_padded(n, f, DEV)
+    torch.add(a, b, alpha=2.0, out=c)
+    assert rel_err(run(c), ya + 2.0 * yb) < 1e-5
+    assert torch.equal(run(a), ya)  # deterministic: fixed summation order, no atomics
+    # constant rows: y = norm * sum(w) for every column
+    ones = _padded(torch.ones(n, f))
+    wsum = torch.zeros(n).index_add(0, torch.from_numpy(d).long(), torch.from_numpy(w)) / 10.0
+    assert rel_err(run(ones)[:, 7], wsum) < 2e-6
+
+
+# ------------------------------------------------------------- dense --------
+@pytest.mark.parametrize("n,k1,k2,fo", [(1000, 13, 13, 218), (777, 218, 218, 218), (513, 218, 218, 9), (5, 7, 7, 20),
+                                        (300, 64, 0, 33), (129, 100, 100, 130), (0, 13, 13, 8)])
+@pytest.mark.parametrize("aligned", [True, False])
+def test_linear_fwd_bwd(n, k1, k2, fo, aligned):
+    gen = torch.Generator().manual_seed(n + fo)
+    x1 = torch.randn(n, k1, generator=gen)
+    x2 = torch.randn(n, k2, generator=gen) if k2 else None
+    W = torch.randn(fo, k1 + k2, generator=gen) * 0.2
+    b = torch.randn(fo, generator=gen)
+    dz = torch.randn(n, fo, generator=gen)
+    X = torch.cat([x1, x2], 1) if k2 else x1
+    mk = _padded if aligned else (lambda t: t.to(DEV))
+    x1d, x2d, dzd = mk(x1), (mk(x2) if k2 else None), mk(dz)
+    Wd, bd = W.to(DEV), b.to(DEV)
+    z = ops.linear_fwd(x1d, x2d, Wd, bd)
+    exp = (X.double() @ W.double().t() + b.double())
+    assert z.shape == (n, fo)
+    if n:
+        assert rel_err(z, exp) < 2e-6
+    # input gradient, per column block, with row scaling and accumulation
+    rs = torch.rand(n)
+    dx1 = ops.linear_bwd_data(dzd, Wd, 0, k1)
+    if n:
+        assert rel_err(dx1, dz.double() @ W.double()[:, :k1]) < 2e-6
+    if k2:
+        dx2 = ops.linear_bwd_data(dzd, Wd, k1, k2, row_scale=rs.to(DEV))
+        if n:
+            assert rel_err(dx2, (dz.double() @ W.double()[:, k1:]) * rs.double().unsqueeze(1)) < 2e-6
+        if k1 == k2 and n:
+            ops.linear_bwd_data(dzd, Wd, k1, k2, out=dx1, accumulate=True)
+            assert rel_err(dx1, dz.double() @ (W.double()[:, :k1] + W.double()[:, k1:])) < 2e-6
+    # weight / bias gradient (deterministic split reduction)
+    dW = torch.full((fo, k1 + k2), 7.0, device=DEV)
+    db = torch.full((fo,), 7.0, device=DEV)
+    ops.linear_bwd_weight(dzd, x1d, x2d, dW, db)
+    expW = dz.double().t() @ X.double()
+    assert rel_err(dW, expW) < 2e-6 if n else torch.all(dW == 0)
+    assert rel_err(db, dz.double().sum(0)) < 2e-6 if n else torch.all(db == 0)
+    dW2 = dW.clone()
+    ops.linear_bwd_weight(dzd, x1d, x2d, dW2, db, accumulate=True)
+    if n:
+        assert rel_err(dW2, 2 * expW) < 2e-6
+    dW3 = torch.empty_like(dW)
+    ops.linear_bwd_weight(dzd, x1d, x2d, dW3, None)
+    assert torch.equal(dW3, dW)  # run-to-run bit-identical
+
+
+def test_linear_column_offset_views():
+    """project-then-aggregate uses the two column blocks of W separately."""
+    n, k, fo = 400, 218, 9
+    x = torch.randn(n, k)
+    W = torch.randn(fo, 2 * k) * 0.1
+    b = torch.randn(fo)
+    xd, Wd = _padded(x), W.to(DEV)
+    s = ops.linear_fwd(xd, None, Wd, b.to(DEV), w_col0=0)
+    p = ops.linear_fwd(xd, None, Wd, None, w_col0=k)
+    assert rel_err(s, x.double() @ W.double()[:, :k].t() + b.double()) < 2e-6
+    assert rel_err(p, x.double() @ W.double()[:, k:].t()) < 2e-6
+    dz = torch.randn(n, fo)
+    dW = torch.zeros(fo, 2 * k, device=DEV)
+    ops.linear_bwd_weight(_padded(dz), xd, None, dW, None, w_col0=k)
+    assert torch.all(dW[:, :k] == 0)
+    assert rel_err(dW[:, k:], dz.double().t() @ x.double()) < 2e-6
+
+
+# ----------------------------------------------------------- row ops --------
+@pytest.mark.parametrize("n,f", [(1000, 218), (33, 9), (257, 32), (100, 1000), (64, 300), (1, 5)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_layernorm_act(n, f, relu):
+    gen = torch.Generator().manual_seed(f)
+    z = (torch.randn(n, f, generator=gen) * 3 + 1).requires_grad_(True)
+    gamma = (torch.rand(f, generator=gen) + 0.5).requires_grad_(True)
+    beta = (torch.randn(f, generator=gen) * 0.1).requires_grad_(True)
+    up = torch.randn(n, f, generator=gen)
+    y = F.layer_norm(z, (f,), gamma, beta, 1e-5)
+    if relu:
+        y = F.relu(y)
+    (y * up).sum().backward()
+    zd = _padded(z.detach())
+    yd, mean, rstd = ops.layernorm_act_fwd(zd, gamma.detach().to(DEV), beta.detach().to(DEV), 1e-5, relu)
+    assert rel_err(yd, y) < 2e-6
+    dg = torch.empty(f, device=DEV)
+    dbt = torch.empty(f, device=DEV)
+    dz = ops.layernorm_act_bwd(_padded(up), zd, mean, rstd, gamma.detach().to(DEV), beta.detach().to(DEV), relu, dg, dbt)
+    assert rel_err(dz, z.grad) < 5e-6
+    assert rel_err(dg, gamma.grad) < 5e-6 and rel_err(dbt, beta.grad) < 5e-6
+    dg2 = torch.empty(f, device=DEV)
+    dz2 = ops.layernorm_act_bwd(_padded(up), zd, mean, rstd, gamma.detach().to(DEV), beta.detach().to(DEV), relu, dg2,
+                                torch.empty(f, device=DEV))
+    assert torch.equal(dg2, dg) and torch.equal(dz2, dz)  # deterministic
+
+
+@pytest.mark.parametrize("n,f", [(500, 20), (100, 218), (7, 3)])
+def test_relu_l2norm_and_relu(n, f):
+    z = torch.randn(n, f)
+    z[0] = -1.0  # a row that relu zeroes completely (norm clamps at eps)
+    z = z.requires_grad_(True)
+    up = torch.randn(n, f)
+    y = F.normalize(F.relu(z))
+    (y * up).sum().backward()
+    zd = _padded(z.detach())
+    assert rel_err(ops.relu_l2norm_fwd(zd), y) < 2e-6
+    assert rel_err(ops.relu_l2norm_bwd(_padded(up), zd), z.grad) < 5e-6
+    assert torch.equal(ops.relu_fwd(zd).cpu(), F.relu(z.detach()))
+    assert torch.equal(ops.relu_bwd(_padded(up), zd).cpu(), up * (z.detach() > 0))
+
+
+@pytest.mark.parametrize("n,c,weighted,ldt", [(1000, 9, False, torch.float32), (333, 9, True, torch.int64),
+                                              (50, 5, True, torch.int32), (1, 3, False, torch.float32)])
+def test_cross_entropy(n, c, weighted, ldt):
+    gen = torch.Generator().manual_seed(n)
+    logits = (torch.randn(n, c, generator=gen) * 3).requires_grad_(True)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    cw = (torch.rand(c, generator=gen) + 0.5) if weighted else None
+    loss = F.cross_entropy(logits, labels, weight=cw)
+    loss.backward()
+    ld = _padded(logits.detach())
+    lab = labels.to(ldt).to(DEV)
+    cwd = cw.to(DEV) if weighted else None
+    stats = ops.cross_entropy_fwd(ld, lab, cwd)
+    s = stats.cpu()
+    assert abs(s[0] / s[1] - loss.item()) < 2e-6 * max(1.0, abs(loss.item()))
+    assert s[2].item() == (logits.argmax(1) == labels).sum().item()
+    dl = ops.cross_entropy_bwd(ld, lab, cwd, stats[1:2])
+    assert rel_err(dl, logits.grad) < 2e-6
+
+
+def test_adam_matches_torch():
+    p0 = torch.randn(10007)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=0.01, weight_decay=5e-4)
+    p, m, v = p0.to(DEV), torch.zeros(10007, device=DEV), torch.zeros(10007, device=DEV)
+    step_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for t in range(1, 6):
+        g = torch.randn(10007, generator=torch.Generator().manual_seed(t))
+        ref.grad = g.clone()
+        opt.step()
+        if t % 2:
+            ops.adam_step(p, g.to(DEV), m, v, lr=0.01, weight_decay=5e-4, step_dev=step_dev)
+        else:
+            ops.adam_step(p, g.to(DEV), m, v, lr=0.01, weight_decay=5e-4, step=t)
+            step_dev += 1
+        assert rel_err(p, ref.data) < 2e-6, t
+    assert step_dev.item() == 5

@@ -1,0 +1,235 @@
+"""GPU parity tests of the drop-in modules and the train-step engine against
+(a) the golden vectors produced by the reference's own models.py and (b) the
+CPU oracle on seeded synthetic page batches.  Tolerance: 1e-5 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gnn_tableextraction_b200 as gte
+from conftest import TOL, load_golden, rel_err, sub
+from helpers import cuda_graph_from_arrays, oracle_graph_from_golden, oracle_graph_from_pages
+from gnn_tableextraction_b200 import synth
+from gnn_tableextraction_b200.graph import batch_pages_host
+from oracle import dgl_shim
+from oracle import sage_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cuda_graph(d):
+    return cuda_graph_from_arrays(d["src"], d["dst"], int(d["num_nodes"]), d["weight"], d["feat"], d.get("label"))
+
+
+# ------------------------------------------------------------ golden --------
+@pytest.mark.parametrize("name", ["gcnsage_default_knn", "gcnsage_bidir_classw", "gcnsage_multigraph"])
+def test_gcnsage_matches_reference_golden(name):
+    d = load_golden(name)
+    inf, hid, ncls, nl = (int(v) for v in d["config"])
+    model = gte.GcnSAGE(inf, hid, ncls, nl, F.relu, 0)
+    model.load_state_dict(sub(d, "state"))  # reference checkpoint loads unchanged
+    model = model.to(DEV)
+    g = _cuda_graph(d)
+    logits = model(g)
+    assert logits.shape == d["logits"].shape
+    assert rel_err(logits, d["logits"]) < TOL
+    cw = torch.from_numpy(d["class_w"]).to(DEV) if "class_w" in d else None
+    loss = gte.CrossEntropyLoss(weight=cw)(logits, g.ndata["label"])
+    assert abs(loss.item() - float(d["loss"])) < TOL * max(1.0, abs(float(d["loss"])))
+    loss.backward()
+    grads = sub(d, "grad")
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, grads[k]) < TOL, k
+    # the caller's graph is not mutated (models.py:47 local_var)
+    assert set(g.ndata.keys()) <= {"feat", "label"} and set(g.edata.keys()) == {"feat"}
+
+
+def test_layer_variants_match_reference_golden():
+    d = load_golden("gcnsage_layers")
+    g = _cuda_graph(d)
+    cfg = {"ln_relu": (32, F.relu, True, True), "plain": (10, None, True, False), "nobias_relu": (16, F.relu, False, False)}
+    for vn, (fo, act, bias, ln) in cfg.items():
+        layer = gte.GcnSAGELayer(13, fo, act, 0.0, bias=bias, use_lynorm=ln)
+        layer.load_state_dict(sub(d, f"{vn}.state"))
+        layer = layer.to(DEV)
+        h = torch.from_numpy(d["feat"]).to(DEV).requires_grad_(True)
+        y = layer(g, h)
+        (y * torch.from_numpy(d[f"{vn}.upstream"]).to(DEV)).sum().backward()
+        assert rel_err(y, d[f"{vn}.out"]) < TOL, vn
+        assert rel_err(h.grad, d[f"{vn}.dh"]) < TOL, vn
+        for k, p in layer.named_parameters():
+            assert rel_err(p.grad, d[f"{vn}.grad.{k}"]) < TOL, (vn, k)
+    layer = gte.GcnSAGELayer(13, 12, F.relu, 0.0, use_pp=True)
+    layer.load_state_dict(sub(d, "pp.state"))
+    layer = layer.to(DEV)
+    assert rel_err(layer(g, torch.from_numpy(d["pp.in"]).to(DEV)), d["pp.out"]) < TOL
+    norm = layer.get_norm(g)
+    assert norm.shape == (61, 1)
+
+
+def test_meansage_matches_reference_golden():
+    d = load_golden("meansage")
+    inf, hid, ncls, nl = (int(v) for v in d["config"])
+    model = gte.MeanSAGE(inf, hid, ncls, nl)
+    model.load_state_dict(sub(d, "state"))
+    model = model.to(DEV)
+    g = _cuda_graph(d)
+    h = torch.from_numpy(d["feat"]).to(DEV).requires_grad_(True)
+    y = model(g, h, torch.from_numpy(d["weight"]).to(DEV))
+    (y * torch.from_numpy(d["upstream"]).to(DEV)).sum().backward()
+    assert rel_err(y, d["out"]) < TOL
+    assert rel_err(h.grad, d["dh"]) < TOL
+    grads = sub(d, "grad")
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, grads[k]) < TOL, k
+
+
+# ------------------------------------------------------ oracle, synthetic ---
+def _oracle_and_cuda_models(seed, cfg=(13, 218, 9, 3)):
+    torch.manual_seed(seed)
+    om = so.OracleGcnSAGE(*cfg, F.relu, 0)
+    cm = gte.GcnSAGE(*cfg, F.relu, 0)
+    cm.load_state_dict(om.state_dict())
+    return om, cm.to(DEV)
+
+
+@pytest.mark.parametrize("pages_kw", [dict(num_pages=8), dict(num_pages=6, ragged=True), dict(num_pages=5, k=5, bidirectional=True),
+                                      dict(num_pages=1, n=77)])
+def test_gcnsage_default_vs_oracle_on_pages(pages_kw):
+    """Raw (un-normalised) BBOX features up to ~5e3 in magnitude: the stress case for fp32."""
+    pages = synth.make_pages(**pages_kw)
+    og = oracle_graph_from_pages(pages)
+    om, cm = _oracle_and_cuda_models(0)
+    g = gte.PageGraphBatch.from_pages(pages, DEV)
+    logits = cm(g)
+    ref = om(og)
+    ref64 = so.gcn_sage_forward_fp64(om, *og.edges(), og.edata["feat"], og.ndata["feat"])
+    # both fp32 implementations sit within tolerance of the fp64 dense-adjacency result, and of each other
+    assert rel_err(ref, ref64) < TOL
+    assert rel_err(logits, ref64) < TOL
+    assert rel_err(logits, ref) < TOL
+    loss = gte.cross_entropy(logits, g.ndata["label"])
+    loss.backward()
+    oloss = torch.nn.CrossEntropyLoss()(ref, og.ndata["label"].long())
+    oloss.backward()
+    assert abs(loss.item() - oloss.item()) < TOL * max(1.0, abs(oloss.item()))
+    for (k, p), (_, q) in zip(cm.named_parameters(), om.named_parameters()):
+        assert rel_err(p.grad, q.grad) < TOL, k
+
+
+def test_accepts_dgl_like_graph_on_cuda():
+    pages = synth.make_pages(3, n=50, k=4)
+    gs = []
+    for p in pages:
+        sg = dgl_shim.graph((torch.from_numpy(p.src), torch.from_numpy(p.dst)), num_nodes=p.num_nodes)
+        sg.ndata["feat"] = torch.from_numpy(p.feat)
+        sg.edata["feat"] = torch.from_numpy(p.weight)
+        gs.append(sg)
+    bg = dgl_shim.batch(gs).to(DEV)  # a DGL-like object: edges()/num_nodes()/ndata/edata
+    om, cm = _oracle_and_cuda_models(1, (13, 32, 9, 3))
+    out = cm(bg)
+    assert rel_err(out, om(oracle_graph_from_pages(pages))) < TOL
+    assert "h" not in bg.ndata and hasattr(bg, "_gte_batch")  # converted once, caller untouched
+    with pytest.raises(KeyError):
+        bg2 = dgl_shim.batch(gs).to(DEV)
+        bg2.edata.pop("feat")
+        cm(bg2)  # the reference raises KeyError('feat') without edge weights too (models.py:53)
+
+
+def test_dropout_path_runs_and_eval_matches():
+    pages = synth.make_pages(2, n=60, k=4)
+    torch.manual_seed(0)
+    om = so.OracleGcnSAGE(13, 32, 9, 3, F.relu, 0.5)
+    cm = gte.GcnSAGE(13, 32, 9, 3, F.relu, 0.5)
+    cm.load_state_dict(om.state_dict())
+    cm = cm.to(DEV)
+    g = gte.PageGraphBatch.from_pages(pages, DEV)
+    cm.train()
+    y = cm(g)
+    y.sum().backward()
+    assert torch.isfinite(y).all() and all(torch.isfinite(p.grad).all() for p in cm.parameters())
+    cm.eval(), om.eval()
+    assert rel_err(cm(g), om(oracle_graph_from_pages(pages))) < TOL
+
+
+# --------------------------------------------------------- train engine -----
+def test_trainer_three_steps_match_oracle_adam():
+    pages = synth.make_pages(6, n=80, k=6)
+    og = oracle_graph_from_pages(pages)
+    om, cm = _oracle_and_cuda_models(3, (13, 48, 9, 3))
+    cw = torch.tensor([1.0] * 6 + [2.0] + [1.0] * 2)
+    opt = so.make_optimizer(om, lr=0.01, weight_decay=5e-4)
+    tr = gte.SageTrainer(cm, lr=0.01, weight_decay=5e-4, class_weights=cw.to(DEV))
+    g = gte.PageGraphBatch.from_pages(pages, DEV)
+    for step in range(3):
+        oloss, ologits, ograds = so.train_step(om, og, og.ndata["label"], opt, class_weights=cw)
+        stats = tr.train_step(g).cpu()
+        assert abs(stats[0] / stats[1] - oloss.item()) < TOL * max(1.0, abs(oloss.item())), step
+        assert stats[2].item() == (ologits.argmax(1) == og.ndata["label"].long()).sum().item()
+        for k, p in cm.named_parameters():
+            assert rel_err(p.grad, ograds[k]) < 5 * TOL, (step, k)  # gradients of step>0 see drifted params
+    for (k, p), (_, q) in zip(cm.named_parameters(), om.named_parameters()):
+        assert rel_err(p.data, q.data) < 1e-4, k  # Adam's 1/sqrt(v) amplifies 1e-6 gradient noise
+    # parameters are views of one flat buffer; state_dict round-trips
+    sd = cm.state_dict()
+    assert list(sd.keys()) == list(om.state_dict().keys())
+    assert rel_err(tr.predict(g), om(og)) < 1e-3
+
+
+def test_trainer_graph_capture_replay_equals_eager():
+    pages_a = synth.make_pages(4, base_seed=1, n=64, k=5)
+    pages_b = synth.make_pages(4, base_seed=100, n=64, k=5)
+    ha, hb = batch_pages_host(pages_a), batch_pages_host(pages_b)
+    _, m1 = _oracle_and_cuda_models(4, (13, 40, 9, 3))
+    _, m2 = _oracle_and_cuda_models(4, (13, 40, 9, 3))
+    t1, t2 = gte.SageTrainer(m1), gte.SageTrainer(m2)
+    t2.capture(ha)
+    for hbatch in (ha, hb, ha):
+        s1 = t1.train_step(gte.PageGraphBatch.from_host(hbatch, DEV)).clone()
+        t2.load_batch(hbatch)
+        s2 = t2.replay().clone()
+        assert torch.equal(s1, s2)
+    assert torch.equal(t1.flat_param, t2.flat_param)  # deterministic kernels: bit-identical trajectories
+    assert t2.step_dev.item() == 3
+
+
+def test_pool_batches_train_like_host_batches():
+    from gnn_tableextraction_b200.pool import PagePool
+
+    pages = synth.make_pages(10, ragged=True, k=5)
+    pool = PagePool(pages, DEV)
+    ids = [3, 9, 0, 4]
+    _, m1 = _oracle_and_cuda_models(5, (13, 32, 9, 3))
+    _, m2 = _oracle_and_cuda_models(5, (13, 32, 9, 3))
+    g1 = gte.PageGraphBatch.from_pages([pages[i] for i in ids], DEV)
+    g2 = pool.batch(ids)
+    s1 = gte.SageTrainer(m1).train_step(g1).clone()
+    s2 = gte.SageTrainer(m2).train_step(g2).clone()
+    assert torch.equal(s1, s2)
+    for p, q in zip(m1.parameters(), m2.parameters()):
+        assert torch.equal(p.data, q.data)
+
+
+def test_config2_scale_determinism_and_sanity():
+    """Full config-2 size (512 pages, N=153600): size-independent properties."""
+    pages = synth.make_pages(512, distinct=32)
+    hb = batch_pages_host(pages)
+    outs = []
+    for _ in range(2):
+        _, cm = _oracle_and_cuda_models(6)
+        tr = gte.SageTrainer(cm)
+        g = gte.PageGraphBatch.from_host(hb, DEV)
+        st = tr.train_step(g).clone()
+        outs.append((st, tr.flat_grad.clone(), tr.flat_param.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2])
+    st = outs[0][0].cpu()
+    assert st[1].item() == 153600 and np.isfinite(st[0].item()) and 0 <= st[2].item() <= 153600
+    # page-permutation equivariance: repeated pages (distinct=32) must get identical logits
+    _, cm = _oracle_and_cuda_models(6)
+    logits = gte.SageTrainer(cm).predict(gte.PageGraphBatch.from_host(hb, DEV))
+    assert torch.equal(logits[:300], logits[32 * 300:33 * 300])
+    # and the first 4 pages agree with the oracle run on those 4 pages alone (pages are independent)
+    om, _ = _oracle_and_cuda_models(6)
+    assert rel_err(logits[:1200], om(oracle_graph_from_pages(pages[:4]))) < TOL
