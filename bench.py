@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""Headline benchmark: page-graphs/sec of the GNN train step (fwd + CE + bwd + Adam)
+on synthetic PubLayNet-shaped page-graph batches, B200-native path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): repo-default GcnSAGE 13->218->218->9, fp32,
+512 page graphs per GPU per step (300 nodes, directed k-NN k=10 => N=153600,
+E=1536000), weak scaling over GPUs (pages are independent; one gradient
+all-reduce per step).  One "step" = one pass of the hot path over one batch:
+CSC/CSR build from the batched COO, 3 conv layers forward, weighted-CE,
+backward, Adam.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "page-graphs/sec (fwd+bwd train step)"
+UNIT = "graphs/s"
+NODES_PER_PAGE, KNN = 300, 10
+MODEL_CFG = (13, 218, 9, 3)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pages", type=int, default=512, help="page graphs per GPU per step (config 2: 512)")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--cpu-pages", type=int, default=32, help="pages per step of the CPU baseline sample (config 1)")
+    ap.add_argument("--ref-pages", type=int, default=64, help="pages per step of --impl reference (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-op-profile", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained":
+                d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------ clocks -------
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (pynvml, 100 ms)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------ per-op profile -----
+class OpTimer:
+    """Wraps the tensor-level ops with CUDA events on the launching stream."""
+
+    NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "linear_fwd", "linear_bwd_data",
+             "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
+             "cross_entropy_bwd", "adam_step"]
+
+    def __init__(self, ops, torch):
+        self.ops, self.torch, self.rec, self.orig = ops, torch, [], {}
+
+    def _key(self, name, a, kw):
+        if name == "spmm":
+            x = a[3]
+            return (name, int(a[0].numel() - 1), int(x.shape[1]), int(a[1].numel()), kw.get("addend") is not None)
+        if name == "linear_fwd":
+            k = a[0].shape[1] + (a[1].shape[1] if a[1] is not None else 0)
+            return (name, int(a[0].shape[0]), int(k), int(a[2].shape[0]))
+        if name == "linear_bwd_data":
+            return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(a[3]))
+        if name == "linear_bwd_weight":
+            k = a[1].shape[1] + (a[2].shape[1] if a[2] is not None else 0)
+            return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(k))
+        if name in ("layernorm_act_fwd", "layernorm_act_bwd"):
+            return (name, int(a[0].shape[0]), int(a[0].shape[1]))
+        return (name,)
+
+    def __enter__(self):
+        for n in self.NAMES:
+            f = getattr(self.ops, n)
+            self.orig[n] = f
+
+            def wrap(*a, _f=f, _n=n, **kw):
+                e0 = self.torch.cuda.Event(enable_timing=True)
+                e1 = self.torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = _f(*a, **kw)
+                e1.record()
+                self.rec.append((self._key(_n, a, kw), e0, e1))
+                return out
+
+            setattr(self.ops, n, wrap)
+        return self
+
+    def __exit__(self, *a):
+        for n, f in self.orig.items():
+            setattr(self.ops, n, f)
+
+    def table(self, steps):
+        self.torch.cuda.synchronize()
+        agg = {}
+        for key, e0, e1 in self.rec:
+            ms = e0.elapsed_time(e1)
+            t = agg.setdefault(key, [0.0, 0])
+            t[0] += ms
+            t[1] += 1
+        return {k: (v[0] / v[1], v[1] / steps) for k, v in agg.items()}  # avg ms per launch, launches per step
+
+
+def op_cost(key):
+    """(algorithmic bytes, flops) per launch -- DESIGN.md section 4."""
+    n = key[0]
+    if n == "spmm":
+        _, N, F, E, add = key
+        return 8 * N * F + 8 * E + 4 * N + (4 * N * F if add else 0), 2 * E * F + N * F
+    if n == "linear_fwd":
+        _, N, K, Fo = key
+        return 4 * N * K + 4 * N * Fo + 4 * K * Fo, 2 * N * K * Fo
+    if n == "linear_bwd_data":
+        _, N, Fo, K = key
+        return 4 * N * Fo + 4 * N * K + 4 * K * Fo, 2 * N * K * Fo
+    if n == "linear_bwd_weight":
+        _, N, Fo, K = key
+        return 4 * N * Fo + 4 * N * K + 4 * K * Fo, 2 * N * K * Fo
+    if n == "layernorm_act_fwd":
+        return 8 * key[1] * key[2], 10 * key[1] * key[2]
+    if n == "layernorm_act_bwd":
+        return 12 * key[1] * key[2], 16 * key[1] * key[2]
+    return 0, 0
+
+
+# ------------------------------------------------------------- CPU arm -----
+def cpu_oracle_run(pages_per_step: int, steps: int, warmup: int, budget_s: float):
+    """Times the oracle port (torch-only restatement of the reference's DGL CPU path:
+    index_add aggregation + MKL sgemm + autograd + Adam) on the host cores."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+
+    from gnn_tableextraction_b200 import synth
+    from oracle import sage_oracle as so
+    from oracle.csx import OracleGraph, batch_coo
+
+    pages = synth.make_pages(pages_per_step, base_seed=42, n=NODES_PER_PAGE, k=KNN, distinct=min(pages_per_step, 32))
+    src, dst, w, noff, _ = batch_coo(pages)
+    g = OracleGraph(src, dst, int(noff[-1]), w, np.concatenate([p.feat for p in pages]))
+    labels = torch.from_numpy(np.concatenate([p.label for p in pages]))
+    torch.manual_seed(0)
+    model = so.OracleGcnSAGE(*MODEL_CFG[:3], MODEL_CFG[3], F.relu, 0)
+    opt = so.make_optimizer(model)
+    for _ in range(warmup):
+        so.train_step(model, g, labels, opt)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        so.train_step(model, g, labels, opt)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    total = sum(times)
+    return {"value": pages_per_step * len(times) / total, "ms_per_step": 1e3 * total / len(times),
+            "steps": len(times), "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(),
+            "torch": torch.__version__}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_oracle_run(args.ref_pages, args.steps, max(args.warmup, 1), budget_s=150.0)
+    sample = (f"{args.ref_pages} pages/step x {r['steps']} steps of the {args.pages}-page workload, fwd+CE+bwd+Adam, "
+              f"oracle port (DGL not installable: torch-only restatement of the reference CPU path), torch {r['torch']}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"configs[1]: GcnSAGE 13-218-218-9 train step, {args.pages} synthetic PubLayNet-shaped page graphs "
+                    f"per GPU (300 nodes, directed kNN k=10, edge weights), fp32",
+        "pages_per_gpu": args.pages, "global_pages": args.pages * world, "nodes_per_page": NODES_PER_PAGE, "knn": KNN,
+        "parallelism": f"dp{world} by graph", "step": "CSC+CSR build, fwd, weighted CE, bwd, Adam",
+        "l2": "working set per step > 1 GB (activations of 153600 x 218 fp32 = 134 MB each) exceeds the 126 MB L2; "
+              "input batches rotate",
+    }
+
+
+# ------------------------------------------------------------- our arm -----
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+
+    import gnn_tableextraction_b200 as gte
+    from gnn_tableextraction_b200 import ops, synth
+    from gnn_tableextraction_b200.graph import batch_pages_host
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = torch.distributed
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gte.lib()
+    pk = peaks()
+
+    # synthetic batches (host, pinned); 3 different page orders to rotate through
+    base = synth.make_pages(args.pages, base_seed=42 + 1000 * rank, n=NODES_PER_PAGE, k=KNN, distinct=min(args.pages, 64))
+    rng = np.random.default_rng(rank)
+    host_batches = []
+    for i in range(3):
+        order = np.arange(args.pages) if i == 0 else rng.permutation(args.pages)
+        host_batches.append(batch_pages_host([base[j] for j in order], pin=True))
+    n_nodes, n_edges = int(host_batches[0]["num_nodes"]), int(host_batches[0]["src"].numel())
+
+    torch.manual_seed(0)
+    model = gte.GcnSAGE(*MODEL_CFG[:3], MODEL_CFG[3], F.relu, 0).to(dev)
+    trainer = gte.SageTrainer(model, lr=0.01, weight_decay=5e-4)
+    use_graph = (not args.no_graph) and world == 1
+    lib = gte.lib()
+
+    dev_batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host_batches]
+
+    def eager_step(db):
+        g = gte.PageGraphBatch(db["src"], db["dst"], n_nodes, db["batch_num_nodes"], db["batch_num_edges"])
+        g.edata["feat"] = db["weight"]
+        g.ndata["feat"] = db["feat"]
+        return trainer.train_step(g, db["label"])
+
+    c0 = lib.gte_launch_count()
+    eager_step(dev_batches[0])
+    launches_per_step = lib.gte_launch_count() - c0
+    if use_graph:
+        trainer.capture(host_batches[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms[0].item(), ms[1].item()
+
+    stats_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    # --- leg 1: inputs resident in HBM ---------------------------------------------------------
+    if use_graph:
+        def resident(i):
+            # device->device refresh of the captured static inputs, then the whole step from one graph
+            db = dev_batches[i % 3]
+            for k in ("src", "dst", "weight", "feat", "label"):
+                trainer._static[k].copy_(db[k], non_blocking=True)
+            trainer.replay()
+    else:
+        def resident(i):
+            eager_step(dev_batches[i % 3])
+
+    # --- leg 2: end to end through the public API with HOST buffers ---------------------------------
+    if use_graph:
+        def e2e(i):
+            trainer.load_batch(host_batches[i % 3])  # H2D from pinned memory
+            trainer.replay()
+            stats_host.copy_(trainer.stats, non_blocking=True)  # D2H of [sum w*nll, sum w, #correct]
+            stream.synchronize()  # the caller reads the loss every step (model_train.py:328 .item())
+    else:
+        def e2e(i):
+            g = gte.PageGraphBatch.from_host(host_batches[i % 3], dev)
+            stats_host.copy_(trainer.train_step(g), non_blocking=True)
+            stream.synchronize()
+
+    with ClockSampler(local) as clk:
+        ms_res, _ = timed(resident, args.steps, args.warmup)
+        ms_e2e, wall_e2e = timed(e2e, args.steps, max(3, args.warmup // 2))
+    loss = float(stats_host[0] / stats_host[1])
+    hb = host_batches[0]
+    h2d = sum(int(hb[k].numel() * hb[k].element_size()) for k in ("src", "dst", "weight", "feat", "label"))
+    d2h = 12
+
+    total_pages = args.pages * world
+    value = total_pages * args.steps / (ms_res / 1e3)
+    e2e_value = total_pages * args.steps / (max(ms_e2e, wall_e2e) / 1e3)
+
+    # --- per-op device times (eager, events on the launching stream) --------------------------------
+    roofline, conv, ops_table = None, None, None
+    if not args.no_op_profile:
+        prof_steps = max(3, min(args.steps, 10))
+        for i in range(2):
+            eager_step(dev_batches[i % 3])
+        with OpTimer(ops, torch) as ot:
+            for i in range(prof_steps):
+                eager_step(dev_batches[i % 3])
+            tab = ot.table(prof_steps)
+        step_ms = sum(ms * cnt for ms, cnt in tab.values())
+        rows = []
+        for key, (ms, cnt) in sorted(tab.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+            b, fl = op_cost(key)
+            rows.append({"op": "/".join(str(x) for x in key), "ms": round(ms, 4), "per_step": cnt,
+                         "share": round(ms * cnt / step_ms, 4),
+                         "GBs": round(b / ms / 1e6, 1) if b else None, "TFLOPs": round(fl / ms / 1e9, 2) if fl else None})
+        ops_table = rows[:14]
+        # dominant kernel
+        dkey, (dms, dcnt) = max(tab.items(), key=lambda kv: kv[1][0] * kv[1][1])
+        b, fl = op_cost(dkey)
+        hbm_t, tensor_peak = b / (pk["hbm_gbs"] * 1e9), pk["bf16_tflops_sustained"] / 2.0  # TF32 dense = bf16/2
+        if dkey[0].startswith("linear") and fl / (tensor_peak * 1e12) > hbm_t:
+            roofline = {"kernel": "/".join(str(x) for x in dkey), "bound": "tensor", "achieved": fl / dms / 1e9,
+                        "peak": tensor_peak, "unit": "TFLOP/s", "frac": fl / dms / 1e9 / tensor_peak, "traffic": None,
+                        "peak_source": pk["source"] + " bf16 sustained / 2 (TF32 rate); fp32-exact FFMA or 3xTF32 "
+                                                      "needs >= 3x the flops counted here"}
+        else:
+            roofline = {"kernel": "/".join(str(x) for x in dkey), "bound": "hbm", "achieved": b / dms / 1e6,
+                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": b / dms / 1e6 / pk["hbm_gbs"], "traffic": None,
+                        "peak_source": pk["source"]}
+        roofline["share_of_step"] = round(dms * dcnt / step_ms, 4)
+        # the conv (aggregation) kernel of the hidden layer: the HBM-roofline number north_star asks for
+        sp = [(k, v) for k, v in tab.items() if k[0] == "spmm" and k[2] == MODEL_CFG[1]]
+        if sp:
+            k, (ms, cnt) = max(sp, key=lambda kv: kv[1][0])
+            b, _ = op_cost(k)
+            conv = {"kernel": "/".join(str(x) for x in k), "bound": "hbm", "achieved": b / ms / 1e6, "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "frac": b / ms / 1e6 / pk["hbm_gbs"], "frac_of_8TBs_nominal": b / ms / 1e6 / 8000.0,
+                    "ms": ms, "alg_bytes": b, "traffic": None}
+
+    # --- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_oracle_run(args.cpu_pages, 10, 2, budget_s=20.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"configs[0]: {args.cpu_pages} pages/step x {r['steps']} steps, fwd+CE+bwd+Adam, oracle port "
+                         f"(DGL absent: torch-only restatement of the reference CPU path), {r['ms_per_step']:.1f} ms/step, "
+                         f"host_cpus={r['host_cpus']}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": max(ms_e2e, wall_e2e) / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+            "cuda_graph": bool(use_graph), "clocks": clk.summary(), "roofline": roofline, "conv_roofline": conv,
+            "cpu_baseline": cpu, "ops": ops_table, "loss": loss, "nodes_per_step_per_gpu": n_nodes,
+            "edges_per_step_per_gpu": n_edges, "lib": os.path.relpath(gte.LIB_PATH, ROOT),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
