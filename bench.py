@@ -121,7 +121,7 @@ class OpTimer:
 
     NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
-             "cross_entropy_bwd", "adam_step"]
+             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data"]
 
     def __init__(self, ops, torch):
         self.ops, self.torch, self.rec, self.orig = ops, torch, [], {}
@@ -140,6 +140,10 @@ class OpTimer:
             return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(k))
         if name in ("layernorm_act_fwd", "layernorm_act_bwd"):
             return (name, int(a[0].shape[0]), int(a[0].shape[1]))
+        if name == "umma_linear_fwd":
+            return (name, int(a[0].shape[0]), int(a[2]) * (2 if a[1] is not None else 1), int(a[5]))
+        if name == "umma_linear_bwd_data":
+            return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(a[2]) * int(a[3]))
         return (name,)
 
     def __enter__(self):
@@ -183,7 +187,10 @@ def op_cost(key):
     if n == "linear_fwd":
         _, N, K, Fo = key
         return 4 * N * K + 4 * N * Fo + 4 * K * Fo, 2 * N * K * Fo
-    if n == "linear_bwd_data":
+    if n == "umma_linear_fwd":  # reads [h | ah], writes z and y
+        _, N, K, Fo = key
+        return 4 * N * K + 8 * N * Fo + 4 * K * Fo, 2 * N * K * Fo
+    if n in ("linear_bwd_data", "umma_linear_bwd_data"):
         _, N, Fo, K = key
         return 4 * N * Fo + 4 * N * K + 4 * K * Fo, 2 * N * K * Fo
     if n == "linear_bwd_weight":
@@ -397,7 +404,7 @@ def run_ours(args):
         dkey, (dms, dcnt) = max(tab.items(), key=lambda kv: kv[1][0] * kv[1][1])
         b, fl = op_cost(dkey)
         hbm_t, tensor_peak = b / (pk["hbm_gbs"] * 1e9), pk["bf16_tflops_sustained"] / 2.0  # TF32 dense = bf16/2
-        if dkey[0].startswith("linear") and fl / (tensor_peak * 1e12) > hbm_t:
+        if "linear" in dkey[0] and fl / (tensor_peak * 1e12) > hbm_t:
             roofline = {"kernel": "/".join(str(x) for x in dkey), "bound": "tensor", "achieved": fl / dms / 1e9,
                         "peak": tensor_peak, "unit": "TFLOP/s", "frac": fl / dms / 1e9 / tensor_peak, "traffic": None,
                         "peak_source": pk["source"] + " bf16 sustained / 2 (TF32 rate); fp32-exact FFMA or 3xTF32 "

@@ -20,5 +20,5 @@ for s in "${srcs[@]}"; do
   fi
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$out" "${objs[@]}" -lcudart -lcuda
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$out" "${objs[@]}" -lcudart
 echo "built $out"

@@ -1,0 +1,641 @@
+// Tensor-core route for the wide hidden layers (Fin, Fout ~ 218): tcgen05.mma
+// kind::tf32 with fp32 accumulators in TMEM, operands staged by TMA, and the
+// error-compensated 3xTF32 split so that the result stays within fp32 parity
+// (1e-5 rel) of the reference's `nn.Linear` (models.py:63):
+//
+//     a = a_hi + a_lo,  b = b_hi + b_lo   (hi = top 19 bits, lo = remainder)
+//     a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (drops a_lo*b_lo ~ 2^-22)
+//
+// One persistent CTA per SM, 12 warps, warp-specialised:
+//   warp 0      TMA producer: raw A tile [128 x 32] + packed W_hi/W_lo tiles [BN x 32]
+//               (SWIZZLE_128B, K-major) into a 2-stage smem ring
+//   warps 4-7   split A in place (hi) + side buffer (lo) -- position preserving, so
+//               the swizzle does not matter -- then fence.proxy.async + arrive
+//   warp 1      elected lane issues 12 tcgen05.mma (M=128, N=BN, K=8) per 32-wide k block
+//               into one of two TMEM accumulator stages; tcgen05.commit frees smem / signals
+//   warps 8-11  epilogue: tcgen05.ld (thread = row), + bias, optional fused
+//               LayerNorm + ReLU (row statistics are thread-local), smem transpose,
+//               coalesced stores of z (saved for backward) and y
+//
+// Used for   z = [h | ah] W^T + b  (+ LayerNorm + ReLU)      -> gte_umma_linear_fwd
+//            [dh_self | d_ah] = dz W                         -> gte_umma_linear_bwd_data
+// Weights are re-packed (split, zero padded, transposed for the backward) by
+// gte_umma_pack_weights every step: 95k elements, negligible.
+//
+// Roofline: tensor pipe (3 * 2*M*N*K flops at the TF32 rate) vs. L2->SM operand
+// traffic (W tiles are re-read per 128-row tile); HBM traffic is compulsory
+// (read A once, write z and y once).
+#include "gte_common.cuh"
+
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace gte {
+
+constexpr int UM_THREADS = 384;
+constexpr int UM_BM = 128;
+constexpr int UM_BK = 32;               // floats per k block = one 128-byte swizzle row
+constexpr int UM_STAGES = 2;
+constexpr int UM_A_BYTES = UM_BM * 128;  // 16 KB
+constexpr int UM_MAX_BN = 256;
+constexpr int UM_ACC_STRIDE = 256;       // TMEM columns per accumulator stage
+constexpr int UM_STAGE_LD = 33;          // padded row of the epilogue transpose buffer
+
+struct UmmaArgs {
+  CUtensorMap tmA[2];       // per K segment: activations [M, K_s], box 32 x 128
+  CUtensorMap tmBhi[2][2];  // [group][segment]: packed weights hi [BN, Kpad], box 32 x BN
+  CUtensorMap tmBlo[2][2];
+  int32_t nseg, ngroups;
+  int32_t kblocks[2];
+  int32_t M, N, BN;
+  float* out[2];            // per group: pre-activation output (z / dx)
+  int64_t ldo[2];
+  float* y;                 // LayerNorm/ReLU output (forward only), may be null
+  int64_t ldy;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float* mean;
+  float* rstd;
+  float eps;
+  int32_t fuse_ln, relu;
+  int32_t variant;  // bit0: round-to-nearest hi/lo split, bit1: cross terms in their own accumulator
+};
+
+// ------------------------------------------------------------ PTX helpers --
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row atoms 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units, bits [0,14)
+  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset = 1024 B, bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version, bits [46,48)
+  d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------ the kernel ---
+__global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_constant__ UmmaArgs P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up (all operand tiles 1024-byte aligned)
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = P.BN * 128;
+  const int stage_bytes = 2 * UM_A_BYTES + 2 * b_bytes;
+  uint8_t* const tiles = base;
+  auto sA_hi_p = [&](int s) { return tiles + s * stage_bytes; };
+  auto sA_lo_p = [&](int s) { return tiles + s * stage_bytes + UM_A_BYTES; };
+  auto sB_hi_p = [&](int s) { return tiles + s * stage_bytes + 2 * UM_A_BYTES; };
+  auto sB_lo_p = [&](int s) { return tiles + s * stage_bytes + 2 * UM_A_BYTES + b_bytes; };
+  base = tiles + UM_STAGES * stage_bytes;
+  float* s_stage = reinterpret_cast<float*>(base);                 // [4 warps][32][33]
+  float* s_bias = s_stage + 4 * 32 * UM_STAGE_LD;                  // [256]
+  float* s_gamma = s_bias + UM_MAX_BN;
+  float* s_beta = s_gamma + UM_MAX_BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + UM_MAX_BN);  // 8-byte aligned by construction
+  uint64_t* bar_full = bars;                  // [STAGES] TMA landed
+  uint64_t* bar_ready = bars + UM_STAGES;     // [STAGES] A split done
+  uint64_t* bar_empty = bars + 2 * UM_STAGES; // [STAGES] MMAs finished reading the stage
+  uint64_t* bar_tfull = bars + 3 * UM_STAGES; // [2] accumulator complete
+  uint64_t* bar_tempty = bar_tfull + 2;       // [2] accumulator drained
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (P.M + UM_BM - 1) / UM_BM;
+  const int total_tiles = m_tiles * P.ngroups;
+  const int kb_total = P.kblocks[0] + (P.nseg > 1 ? P.kblocks[1] : 0);
+
+  for (int i = threadIdx.x; i < UM_MAX_BN; i += UM_THREADS) {
+    s_bias[i] = (P.bias && i < P.N) ? P.bias[i] : 0.f;
+    s_gamma[i] = (P.gamma && i < P.N) ? P.gamma[i] : 1.f;
+    s_beta[i] = (P.beta && i < P.N) ? P.beta[i] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < UM_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_ready[s]), 128);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bar_tfull[a]), 1);
+      mbar_init(smem_u32(&bar_tempty[a]), 128);
+    }
+    fence_barrier_init();
+    for (int s = 0; s < P.nseg; ++s) tma_prefetch_desc(&P.tmA[s]);
+    for (int gq = 0; gq < P.ngroups; ++gq)
+      for (int s = 0; s < P.nseg; ++s) {
+        tma_prefetch_desc(&P.tmBhi[gq][s]);
+        tma_prefetch_desc(&P.tmBlo[gq][s]);
+      }
+  }
+  if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / P.ngroups, grp = tile % P.ngroups;
+        for (int seg = 0; seg < P.nseg; ++seg) {
+          for (int kb = 0; kb < P.kblocks[seg]; ++kb) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&bar_full[stage]);
+            mbar_expect_tx(fb, (uint32_t)(UM_A_BYTES + 2 * b_bytes));
+            tma_load_2d(smem_u32(sA_hi_p(stage)), &P.tmA[seg], fb, kb * UM_BK, mt * UM_BM);
+            tma_load_2d(smem_u32(sB_hi_p(stage)), &P.tmBhi[grp][seg], fb, kb * UM_BK, 0);
+            tma_load_2d(smem_u32(sB_lo_p(stage)), &P.tmBlo[grp][seg], fb, kb * UM_BK, 0);
+            if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const bool split_acc = (P.variant & 2) != 0;
+      const int nacc = split_acc ? 1 : 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * UM_ACC_STRIDE);
+        const uint32_t d_cross = split_acc ? tmem_base + UM_ACC_STRIDE : d_tmem;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          mbar_wait(smem_u32(&bar_ready[stage]), phase);
+          tc_fence_after();
+          const uint64_t dah = make_desc_k_sw128(smem_u32(sA_hi_p(stage)));
+          const uint64_t dal = make_desc_k_sw128(smem_u32(sA_lo_p(stage)));
+          const uint64_t dbh = make_desc_k_sw128(smem_u32(sB_hi_p(stage)));
+          const uint64_t dbl = make_desc_k_sw128(smem_u32(sB_lo_p(stage)));
+#pragma unroll
+          for (int k = 0; k < UM_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 step inside the 128 B swizzle row
+            umma_tf32(d_cross, dal + adv, dbh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(d_cross, dah + adv, dbl + adv, idesc, 1u);
+            umma_tf32(d_tmem, dah + adv, dbh + adv, idesc, (split_acc && (kb | k) == 0) ? 0u : 1u);
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&bar_tfull[acc]));
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================ operand split ===============================
+    const int t = threadIdx.x - 128;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        float4* hi = reinterpret_cast<float4*>(sA_hi_p(stage));
+        float4* lo = reinterpret_cast<float4*>(sA_lo_p(stage));
+#pragma unroll
+        for (int i = 0; i < UM_A_BYTES / 16 / 128; ++i) {
+          const int idx = t + 128 * i;
+          const float4 v = hi[idx];
+          float4 h, l;
+          if (P.variant & 1) {
+            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          } else {
+            h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          }
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(smem_u32(&bar_ready[stage]));
+        if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may touch
+    float* st = s_stage + q * 32 * UM_STAGE_LD;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool split_acc = (P.variant & 2) != 0;
+    const int nacc = split_acc ? 1 : 2;
+    const int nchunks = (P.N + 31) / 32;
+    const float inv_n = 1.0f / (float)P.N;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / P.ngroups, grp = tile % P.ngroups;
+      mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * UM_ACC_STRIDE);
+      const int64_t row0 = (int64_t)mt * UM_BM + q * 32;  // first global row of this warp
+      float* outp = P.out[grp];
+      const int64_t ldo = P.ldo[grp];
+      uint32_t v[32];
+      auto load_chunk = [&](int c) {
+        tmem_ld_32x32b_x32(t_base + c * 32, v);
+        if (split_acc) {
+          uint32_t v2[32];
+          tmem_ld_32x32b_x32(t_base + UM_ACC_STRIDE + c * 32, v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
+      };
+      float mean = 0.f, rstd = 1.f;
+      if (P.fuse_ln) {
+        float s = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          load_chunk(c);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * 32 + j;
+            if (col < P.N) s += __uint_as_float(v[j]) + s_bias[col];
+          }
+        }
+        mean = s * inv_n;
+        float qv = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          load_chunk(c);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * 32 + j;
+            if (col < P.N) {
+              const float d = __uint_as_float(v[j]) + s_bias[col] - mean;
+              qv = fmaf(d, d, qv);
+            }
+          }
+        }
+        rstd = 1.0f / sqrtf(qv * inv_n + P.eps);
+        const int64_t grow = row0 + lane;
+        if (grow < P.M) {
+          P.mean[grow] = mean;
+          P.rstd[grow] = rstd;
+        }
+      }
+      for (int c = 0; c < nchunks; ++c) {
+        load_chunk(c);
+        // z chunk -> transpose buffer -> coalesced rows
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[lane * UM_STAGE_LD + j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+        __syncwarp();
+        const int col = c * 32 + lane;
+        if (col < P.N) {
+          for (int rr = 0; rr < 32; ++rr) {
+            const int64_t grow = row0 + rr;
+            if (grow < P.M) outp[grow * ldo + col] = st[rr * UM_STAGE_LD + lane];
+          }
+        }
+        if (P.y != nullptr) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int cj = c * 32 + j;
+            float o = __uint_as_float(v[j]) + s_bias[cj];
+            if (P.fuse_ln) o = (o - mean) * rstd * s_gamma[cj] + s_beta[cj];
+            if (P.relu) o = fmaxf(o, 0.f);
+            st[lane * UM_STAGE_LD + j] = o;
+          }
+          __syncwarp();
+          if (col < P.N) {
+            for (int rr = 0; rr < 32; ++rr) {
+              const int64_t grow = row0 + rr;
+              if (grow < P.M) P.y[grow * P.ldy + col] = st[rr * UM_STAGE_LD + lane];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_tempty[acc]));
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------- weight packing ----
+// fwd pack:  Pf[seg][half][BN][Kp]   Pf[seg][.][o][k] = W[o, seg*fin + k]          (K-major B of z = x W^T)
+// bwd pack:  Pb[grp][half][BNb][Kpb] Pb[grp][.][j][o] = W[o, grp*fin + j]          (K-major B of dx = dz W)
+// half 0 = tf32 hi, half 1 = tf32(lo); zero padded.
+__global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
+                            float* __restrict__ Pf, int32_t BN, int32_t Kp, float* __restrict__ Pb, int32_t BNb,
+                            int32_t Kpb, int32_t variant) {
+  const int64_t per_f = (int64_t)BN * Kp, per_b = (int64_t)BNb * Kpb;
+  const int64_t total_f = (int64_t)nseg * per_f, total_b = (int64_t)nseg * per_b;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total_f + total_b; i += stride) {
+    float w = 0.f;
+    float* dst;
+    int64_t half_stride;
+    if (i < total_f) {
+      const int seg = (int)(i / per_f);
+      const int64_t r = i % per_f;
+      const int o = (int)(r / Kp), k = (int)(r % Kp);
+      if (o < fo && k < fin) w = W[(int64_t)o * ldw + (int64_t)seg * fin + k];
+      dst = Pf + (int64_t)seg * 2 * per_f + r;
+      half_stride = per_f;
+    } else {
+      const int64_t ib = i - total_f;
+      const int grp = (int)(ib / per_b);
+      const int64_t r = ib % per_b;
+      const int j = (int)(r / Kpb), o = (int)(r % Kpb);
+      if (o < fo && j < fin) w = W[(int64_t)o * ldw + (int64_t)grp * fin + j];
+      dst = Pb + (int64_t)grp * 2 * per_b + r;
+      half_stride = per_b;
+    }
+    const float h = (variant & 1) ? tf32_rna(w) : tf32_hi(w);
+    dst[0] = h;
+    dst[half_stride] = (variant & 1) ? tf32_rna(w - h) : tf32_hi(w - h);
+  }
+}
+
+// ------------------------------------------------------------ host side ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with leading dimension ld (floats); box = 32 cols x box_rows, SWIZZLE_128B
+static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(GTE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)UM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GTE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return GTE_OK;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// experiment switch (GTE_UMMA_VARIANT): bit0 = round-to-nearest split, bit1 = separate cross-term accumulator
+static int umma_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GTE_UMMA_VARIANT");
+    v = e ? atoi(e) : 3;
+  }
+  return v;
+}
+
+struct PackDims {
+  int BN, Kp, BNb, Kpb;
+  size_t fwd_floats, bwd_floats;
+};
+static PackDims pack_dims(int fo, int fin, int nseg) {
+  PackDims d;
+  d.BN = round_up(fo, 16);
+  d.Kp = round_up(fin, UM_BK);
+  d.BNb = round_up(fin, 16);
+  d.Kpb = round_up(fo, UM_BK);
+  d.fwd_floats = (size_t)nseg * 2 * d.BN * d.Kp;
+  d.bwd_floats = (size_t)nseg * 2 * d.BNb * d.Kpb;
+  return d;
+}
+
+static size_t umma_smem_bytes(int BN) {
+  return 1024 + (size_t)UM_STAGES * (2 * UM_A_BYTES + 2 * (size_t)BN * 128) + 4 * 32 * UM_STAGE_LD * 4 + 3 * UM_MAX_BN * 4 +
+         (3 * UM_STAGES + 4) * 8 + 16;
+}
+
+static int launch_umma(UmmaArgs& a, cudaStream_t st) {
+  const size_t smem = umma_smem_bytes(a.BN);
+  static size_t configured = 0;
+  if (smem > configured) {
+    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "k_umma_gemm(smem attr)");
+    configured = smem;
+  }
+  a.variant = umma_variant();
+  const int tiles = ((a.M + UM_BM - 1) / UM_BM) * a.ngroups;
+  int grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) return GTE_OK;
+  k_umma_gemm<<<grid, UM_THREADS, smem, st>>>(a);
+  GTE_CHECK_LAUNCH("k_umma_gemm");
+  return GTE_OK;
+}
+
+}  // namespace gte
+
+using namespace gte;
+
+extern "C" {
+
+int gte_umma_supported(int32_t fo, int32_t fin) {
+  return (fo >= 16 && fo <= UM_MAX_BN && fin >= 16 && fin <= UM_MAX_BN) ? 1 : 0;
+}
+
+size_t gte_umma_pack_bytes(int32_t fo, int32_t fin, int32_t nseg) {
+  if (!gte_umma_supported(fo, fin) || nseg < 1 || nseg > 2) return 0;
+  PackDims d = pack_dims(fo, fin, nseg);
+  return (d.fwd_floats + d.bwd_floats) * 4;
+}
+
+int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg, float* pack,
+                          gte_stream_t stream) {
+  GTE_CHECK_ARG(W && pack, "gte_umma_pack_weights: null argument");
+  GTE_CHECK_ARG(nseg >= 1 && nseg <= 2 && ldw >= (int64_t)nseg * fin, "gte_umma_pack_weights: bad nseg/ldw");
+  if (!gte_umma_supported(fo, fin)) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_pack_weights: fo=%d fin=%d unsupported", fo, fin);
+  GTE_CHECK_ARG(aligned16(pack), "gte_umma_pack_weights: pack buffer must be 16-byte aligned");
+  PackDims d = pack_dims(fo, fin, nseg);
+  const int64_t total = (int64_t)nseg * ((int64_t)d.BN * d.Kp + (int64_t)d.BNb * d.Kpb);
+  k_umma_pack<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(W, ldw, fo, fin, nseg, pack, d.BN, d.Kp,
+                                                                              pack + d.fwd_floats, d.BNb, d.Kpb, umma_variant());
+  GTE_CHECK_LAUNCH("k_umma_pack");
+  return GTE_OK;
+}
+
+int gte_umma_linear_fwd(const float* x1, int64_t ldx1, const float* x2, int64_t ldx2, int32_t fin, const float* pack,
+                        const float* bias, const float* gamma, const float* beta, float eps, int relu, int fuse_ln,
+                        float* z, int64_t ldz, float* y, int64_t ldy, float* mean, float* rstd, int32_t n, int32_t fo,
+                        gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0, "gte_umma_linear_fwd: negative n");
+  if (!gte_umma_supported(fo, fin)) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_fwd: fo=%d fin=%d unsupported", fo, fin);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(x1 && pack && z, "gte_umma_linear_fwd: null argument");
+  GTE_CHECK_ARG(!fuse_ln || (gamma && beta && mean && rstd && y), "gte_umma_linear_fwd: fused LayerNorm needs gamma/beta/mean/rstd/y");
+  GTE_CHECK_ARG(aligned16(x1) && ldx1 % 4 == 0 && ldx1 >= fin, "gte_umma_linear_fwd: x1 must be 16-byte aligned with ld %% 4 == 0");
+  GTE_CHECK_ARG(!x2 || (aligned16(x2) && ldx2 % 4 == 0 && ldx2 >= fin), "gte_umma_linear_fwd: x2 must be 16-byte aligned with ld %% 4 == 0");
+  GTE_CHECK_ARG(ldz >= fo && (!y || ldy >= fo), "gte_umma_linear_fwd: output leading dimension < fo");
+  const int nseg = x2 ? 2 : 1;
+  PackDims d = pack_dims(fo, fin, nseg);
+  UmmaArgs a{};
+  a.nseg = nseg;
+  a.ngroups = 1;
+  a.M = n;
+  a.N = fo;
+  a.BN = d.BN;
+  const float* xs[2] = {x1, x2};
+  const int64_t lds[2] = {ldx1, ldx2};
+  const size_t per = (size_t)d.BN * d.Kp;
+  for (int s = 0; s < nseg; ++s) {
+    a.kblocks[s] = d.Kp / UM_BK;
+    int rc = make_map(&a.tmA[s], xs[s], n, fin, lds[s], UM_BM);
+    if (rc) return rc;
+    rc = make_map(&a.tmBhi[0][s], pack + (size_t)s * 2 * per, d.BN, d.Kp, d.Kp, d.BN);
+    if (rc) return rc;
+    rc = make_map(&a.tmBlo[0][s], pack + (size_t)s * 2 * per + per, d.BN, d.Kp, d.Kp, d.BN);
+    if (rc) return rc;
+  }
+  a.out[0] = z;
+  a.ldo[0] = ldz;
+  a.y = y;
+  a.ldy = ldy;
+  a.bias = bias;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.mean = mean;
+  a.rstd = rstd;
+  a.eps = eps;
+  a.fuse_ln = fuse_ln ? 1 : 0;
+  a.relu = relu ? 1 : 0;
+  return launch_umma(a, as_stream(stream));
+}
+
+int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const float* pack, int32_t nseg, float* dx1,
+                             int64_t lddx1, float* dx2, int64_t lddx2, int32_t n, int32_t fin, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0, "gte_umma_linear_bwd_data: negative n");
+  if (!gte_umma_supported(fo, fin)) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_data: fo=%d fin=%d unsupported", fo, fin);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(dz && pack && dx1 && nseg >= 1 && nseg <= 2 && (nseg == 1 || dx2), "gte_umma_linear_bwd_data: null argument");
+  GTE_CHECK_ARG(aligned16(dz) && lddz % 4 == 0 && lddz >= fo, "gte_umma_linear_bwd_data: dz must be 16-byte aligned with ld %% 4 == 0");
+  GTE_CHECK_ARG(lddx1 >= fin && (nseg == 1 || lddx2 >= fin), "gte_umma_linear_bwd_data: output leading dimension < fin");
+  PackDims d = pack_dims(fo, fin, nseg);
+  const float* pb = pack + d.fwd_floats;
+  UmmaArgs a{};
+  a.nseg = 1;
+  a.ngroups = nseg;
+  a.M = n;
+  a.N = fin;
+  a.BN = d.BNb;
+  a.kblocks[0] = d.Kpb / UM_BK;
+  int rc = make_map(&a.tmA[0], dz, n, fo, lddz, UM_BM);
+  if (rc) return rc;
+  const size_t per = (size_t)d.BNb * d.Kpb;
+  for (int gq = 0; gq < nseg; ++gq) {
+    rc = make_map(&a.tmBhi[gq][0], pb + (size_t)gq * 2 * per, d.BNb, d.Kpb, d.Kpb, d.BNb);
+    if (rc) return rc;
+    rc = make_map(&a.tmBlo[gq][0], pb + (size_t)gq * 2 * per + per, d.BNb, d.Kpb, d.Kpb, d.BNb);
+    if (rc) return rc;
+  }
+  a.out[0] = dx1;
+  a.ldo[0] = lddx1;
+  a.out[1] = dx2;
+  a.ldo[1] = lddx2;
+  return launch_umma(a, as_stream(stream));
+}
+
+}  // extern "C"

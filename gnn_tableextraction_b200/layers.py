@@ -17,6 +17,7 @@ SpMM on the CSR (deterministic, no atomics).  Nothing here runs on the CPU.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -24,6 +25,13 @@ import torch
 
 from . import _lib, ops
 from .graph import PageGraphBatch
+
+# Dense-contraction route: "auto" sends wide hidden layers (a real dense contraction)
+# to the tcgen05 3xTF32 kernels and everything else to the exact-fp32 FFMA kernels;
+# "ffma" forces the CUDA-core path everywhere, "umma" forces tensor cores wherever supported.
+GEMM_MODE = os.environ.get("GTE_GEMM", "auto")
+UMMA_MIN_ROWS = 1024
+UMMA_MIN_WIDTH = 64
 
 GCN = "gcn"    # sum, then * 1/in_deg (0 for isolated nodes)  -- GcnSAGELayer
 MEAN = "mean"  # sum / max(in_deg, 1)                          -- WeightedMeanSAGELayer (DGL fn.mean)
@@ -39,6 +47,7 @@ class LayerCtx:
     mean: Optional[torch.Tensor] = None
     rstd: Optional[torch.Tensor] = None
     w_edge: Optional[torch.Tensor] = None
+    pack: Optional[torch.Tensor] = None  # tf32 hi/lo weight tiles when the layer ran on tensor cores
     ln: bool = False
     relu: bool = False
     fin: int = 0
@@ -49,6 +58,16 @@ def pick_strategy(fin: int, fout: int, use_pp: bool) -> str:
     if use_pp:
         return "pp"
     return "proj" if fout < fin else "agg"
+
+
+def use_umma(n: int, fin: int, fout: int, *mats) -> bool:
+    if GEMM_MODE == "ffma" or not ops.umma_supported(fout, fin):
+        return False
+    if not all(ops._aligned_mat(m) for m in mats if m is not None):
+        return False
+    if GEMM_MODE == "umma":
+        return True
+    return n >= UMMA_MIN_ROWS and fin >= UMMA_MIN_WIDTH and fout >= UMMA_MIN_WIDTH
 
 
 def _agg_mode(agg: str) -> int:
@@ -87,6 +106,13 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
     elif st == "agg":
         ah = aggregate_forward(g, h, w_edge, agg)
         ctx.ah = ah
+        if use_umma(h.shape[0], fin, fout, h, ah):
+            # tensor cores: projection + bias + LayerNorm + ReLU in one kernel
+            ctx.pack = ops.umma_pack_weights(W, fin, 2)
+            z, y, ctx.mean, ctx.rstd = ops.umma_linear_fwd(h, ah, fin, ctx.pack, b, fout, gamma=gamma, beta=beta,
+                                                           eps=eps, relu=relu, fuse_ln=ln)
+            ctx.z = z
+            return (y if y is not None else z), ctx
         z = ops.linear_fwd(h, ah, W, b)
     elif st == "proj":
         s = ops.linear_fwd(h, None, W, b, w_col0=0)
@@ -123,8 +149,11 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
         ops.linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
         if not need_dh:
             return None
-        d_self = ops.linear_bwd_data(dz, W, 0, fin)
-        d_ah = ops.linear_bwd_data(dz, W, fin, fin)
+        if ctx.pack is not None and ops._aligned_mat(dz):
+            d_self, d_ah = ops.umma_linear_bwd_data(dz, ctx.pack, fin, 2)
+        else:
+            d_self = ops.linear_bwd_data(dz, W, 0, fin)
+            d_ah = ops.linear_bwd_data(dz, W, fin, fin)
         return aggregate_backward(g, d_ah, ctx.w_edge, addend=d_self)
     # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
     #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn

@@ -231,6 +231,73 @@ def linear_bwd_weight(dz, x1, x2, dW, db, accumulate=False, w_col0: int = 0):
     )
 
 
+# ------------------------------------------------ tensor-core route --------
+def umma_supported(fo: int, fin: int) -> bool:
+    return bool(lib().gte_umma_supported(fo, fin))
+
+
+def _aligned_mat(t: torch.Tensor) -> bool:
+    return t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.data_ptr() % 16 == 0 and (
+        t.shape[0] <= 1 or t.stride(0) % 4 == 0) and (t.shape[1] <= 1 or t.stride(1) == 1)
+
+
+def umma_pack_weights(W: torch.Tensor, fin: int, nseg: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Split W [fo, nseg*fin] into tf32 hi/lo tiles (forward + transposed backward layouts)."""
+    Wp, ldw, kw = _mat(W, "umma_pack.W")
+    fo = W.shape[0]
+    l = lib()
+    nbytes = l.gte_umma_pack_bytes(fo, fin, nseg)
+    if nbytes == 0 or kw < nseg * fin:
+        raise GteError(f"umma_pack_weights: unsupported shape fo={fo} fin={fin} nseg={nseg}")
+    if out is None:
+        out = torch.empty(nbytes // 4, dtype=torch.float32, device=W.device)
+    check(l.gte_umma_pack_weights(Wp, ldw, fo, fin, nseg, _vec(out, "pack", n=nbytes // 4), _stream()),
+          "gte_umma_pack_weights")
+    return out
+
+
+def umma_linear_fwd(x1, x2, fin: int, pack, bias, fo: int, *, gamma=None, beta=None, eps: float = 1e-5,
+                    relu: bool = False, fuse_ln: bool = False, want_y: bool = False):
+    """(z, y, mean, rstd): z = [x1 | x2] W^T + b ; y = act(LN(z)) / act(z) (None unless requested)."""
+    x1p, ld1, k1 = _mat(x1, "umma.x1")
+    n = x1.shape[0]
+    x2p, ld2 = None, 0
+    if x2 is not None:
+        x2p, ld2, k2 = _mat(x2, "umma.x2")
+        if k2 != fin or x2.shape[0] != n:
+            raise GteError("umma_linear_fwd: x2 shape mismatch")
+    if k1 != fin:
+        raise GteError("umma_linear_fwd: x1 shape mismatch")
+    dev = x1.device
+    z = empty_padded(n, fo, dev)
+    zp, ldz, _ = _mat(z, "umma.z")
+    need_y = fuse_ln or want_y or relu
+    y = empty_padded(n, fo, dev) if need_y else None
+    yp, ldy = (None, 0) if y is None else _mat(y, "umma.y")[:2]
+    mean = torch.empty(n, dtype=torch.float32, device=dev) if fuse_ln else None
+    rstd = torch.empty(n, dtype=torch.float32, device=dev) if fuse_ln else None
+    check(
+        lib().gte_umma_linear_fwd(x1p, ld1, x2p, ld2, fin, _vec(pack, "pack"), _vec(bias, "bias", n=fo),
+                                  _vec(gamma, "gamma", n=fo), _vec(beta, "beta", n=fo), float(eps), 1 if relu else 0,
+                                  1 if fuse_ln else 0, zp, ldz, yp, ldy, _ptr(mean), _ptr(rstd), n, fo, _stream()),
+        "gte_umma_linear_fwd",
+    )
+    return z, y, mean, rstd
+
+
+def umma_linear_bwd_data(dz, pack, fin: int, nseg: int):
+    """(dx1, dx2) = dz W[:, :fin], dz W[:, fin:2 fin]."""
+    dzp, lddz, fo = _mat(dz, "umma_bwd.dz")
+    n = dz.shape[0]
+    dx1 = empty_padded(n, fin, dz.device)
+    dx2 = empty_padded(n, fin, dz.device) if nseg == 2 else None
+    d1p, ld1, _ = _mat(dx1, "umma_bwd.dx1")
+    d2p, ld2 = (None, 0) if dx2 is None else _mat(dx2, "umma_bwd.dx2")[:2]
+    check(lib().gte_umma_linear_bwd_data(dzp, lddz, fo, _vec(pack, "pack"), nseg, d1p, ld1, d2p, ld2, n, fin, _stream()),
+          "gte_umma_linear_bwd_data")
+    return dx1, dx2
+
+
 # ---------------------------------------------------------------- row ops ---
 def layernorm_act_fwd(z, gamma, beta, eps: float, relu: bool, out=None):
     zp, ldz, f = _mat(z, "ln.z")

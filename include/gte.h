@@ -163,6 +163,37 @@ int gte_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo,
                           float* dW, int64_t lddw, float* db, int accumulate, int32_t n,
                           void* ws, size_t ws_bytes, gte_stream_t stream);
 
+/* ------------------------------------ tensor-core route (tcgen05, 3xTF32) -- */
+/*
+ * Same contractions as gte_linear_fwd / gte_linear_bwd_data for the wide hidden
+ * layers (16 <= fin, fo <= 256), on tcgen05.mma kind::tf32 with the
+ * error-compensated 3xTF32 operand split (fp32-level accuracy: a_lo*b_hi +
+ * a_hi*b_lo + a_hi*b_hi accumulated in fp32 TMEM), TMA-staged operands and the
+ * bias / LayerNorm / ReLU epilogue of models.py:63-66 fused.  Activations must be
+ * 16-byte aligned with leading dimensions that are multiples of 4 floats.
+ *
+ * gte_umma_pack_weights splits W [fo, nseg*fin] into tf32 hi/lo halves, zero pads
+ * them to the tile shape and stores both the forward (W) and the backward (W^T)
+ * operand layouts into `pack` (gte_umma_pack_bytes bytes, 16-byte aligned).
+ * It must be re-run whenever W changes.
+ */
+int gte_umma_supported(int32_t fo, int32_t fin);
+size_t gte_umma_pack_bytes(int32_t fo, int32_t fin, int32_t nseg);
+int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
+                          float* pack, gte_stream_t stream);
+/*
+ * z = x1 W[:, :fin]^T (+ x2 W[:, fin:]^T) + bias ; y = act(LayerNorm(z)) when
+ * fuse_ln (mean/rstd [n] saved), else y = act(z) when y != NULL.  x2 may be NULL.
+ */
+int gte_umma_linear_fwd(const float* x1, int64_t ldx1, const float* x2, int64_t ldx2, int32_t fin,
+                        const float* pack, const float* bias, const float* gamma, const float* beta,
+                        float eps, int relu, int fuse_ln, float* z, int64_t ldz, float* y, int64_t ldy,
+                        float* mean, float* rstd, int32_t n, int32_t fo, gte_stream_t stream);
+/* dx1 = dz W[:, :fin] and (nseg == 2) dx2 = dz W[:, fin:2*fin]. */
+int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const float* pack, int32_t nseg,
+                             float* dx1, int64_t lddx1, float* dx2, int64_t lddx2, int32_t n, int32_t fin,
+                             gte_stream_t stream);
+
 /* ------------------------------------------- row normalisation + act ---- */
 /*
  * y = act(LayerNorm(z; gamma, beta, eps)) per row over the first f columns

@@ -80,7 +80,12 @@ class OracleGcnSAGELayer(nn.Module):
     def concat(self, h, ah, norm):  # models.py:69-72 -- self block first
         return torch.cat((h, ah * norm), dim=1)
 
-    def forward(self, g, h):  # models.py:46-67
+    def forward(self, g, h, relu_mask=None):  # models.py:46-67
+        """``relu_mask`` (test-only): evaluate the activation with a GIVEN on/off pattern
+        (h * mask) instead of ``activation(h)``.  ReLU's derivative is discontinuous at 0, so
+        two fp32 implementations can legitimately disagree on elements whose pre-activation is
+        within rounding noise of 0; the parity tests compare gradients under the same pattern
+        and separately check that the patterns differ only at such elements."""
         if not self.use_pp:
             src, dst, n = _graph_parts(g)
             norm = self.get_norm(g)
@@ -90,8 +95,9 @@ class OracleGcnSAGELayer(nn.Module):
             h = self.dropout(h)
         h = self.linear(h)
         h = self.lynorm(h)
+        self.last_preact = h.detach()
         if self.activation:
-            h = self.activation(h)
+            h = self.activation(h) if relu_mask is None else h * relu_mask.to(h.dtype)
         return h
 
 
@@ -111,11 +117,11 @@ class OracleGcnSAGE(nn.Module):
             OracleGcnSAGELayer(n_hidden, n_classes, activation=None, dropout=False, use_pp=False, use_lynorm=False)
         )
 
-    def forward(self, g):  # models.py:105-116
+    def forward(self, g, relu_masks=None):  # models.py:105-116
         h = g.ndata["feat"]
         h = self.dropout(h)
-        for layer in self.layers:
-            h = layer(g, h)
+        for i, layer in enumerate(self.layers):
+            h = layer(g, h) if relu_masks is None else layer(g, h, relu_masks[i])
         return h
 
 

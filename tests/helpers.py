@@ -39,3 +39,32 @@ def copy_state(dst_model, src_state, device=None):
     sd = {k: (v.to(device) if device else v) for k, v in src_state.items()}
     dst_model.load_state_dict(sd)
     return dst_model
+
+
+def cuda_forward_with_masks(cuda_model, g):
+    """logits + the ReLU on/off pattern of every layer of the CUDA model (None where no activation)."""
+    masks = [None] * len(cuda_model.layers)
+    hooks = []
+    for i, layer in enumerate(cuda_model.layers):
+        if layer.activation is not None:
+            hooks.append(layer.register_forward_hook(
+                lambda m, inp, out, i=i: masks.__setitem__(i, (out.detach() > 0).cpu())))
+    logits = cuda_model(g)
+    for h in hooks:
+        h.remove()
+    return logits, masks
+
+
+def check_relu_patterns(oracle_model, masks, tol=1e-5):
+    """The CUDA and oracle activation patterns may differ only where the oracle's pre-activation is
+    within `tol` (relative to the layer's largest pre-activation) of the ReLU kink.  Returns #flips."""
+    flips = 0
+    for layer, m in zip(oracle_model.layers, masks):
+        if m is None:
+            continue
+        pre = layer.last_preact
+        diff = (pre > 0) != m
+        flips += int(diff.sum())
+        if diff.any():
+            assert pre[diff].abs().max().item() <= tol * pre.abs().max().item(), "activation pattern differs away from 0"
+    return flips

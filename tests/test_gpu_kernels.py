@@ -310,3 +310,55 @@ def test_adam_matches_torch():
             step_dev += 1
         assert rel_err(p, ref.data) < 2e-6, t
     assert step_dev.item() == 5
+
+
+# ------------------------------------------------- tensor-core route --------
+def _log_err(tag, err):
+    import os
+
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/umma_err.txt", "a") as fh:
+        fh.write(f"{tag} {err:.3e}\n")
+
+
+@pytest.mark.parametrize("n,fin,fo,ln,relu,two", [(1000, 218, 218, True, True, True), (129, 64, 64, False, False, True),
+                                                  (5000, 100, 130, True, False, True), (128, 32, 16, False, True, False),
+                                                  (3001, 256, 256, True, True, True), (40000, 218, 218, True, True, True)])
+def test_umma_linear_fwd_3xtf32(n, fin, fo, ln, relu, two):
+    gen = torch.Generator().manual_seed(n)
+    x1 = torch.randn(n, fin, generator=gen)
+    x2 = torch.randn(n, fin, generator=gen) * 3 if two else None
+    nseg = 2 if two else 1
+    W = (torch.rand(fo, nseg * fin, generator=gen) - 0.5) * (2.0 / (nseg * fin) ** 0.5)
+    b = torch.randn(fo, generator=gen) * 0.1
+    gamma = torch.rand(fo, generator=gen) + 0.5
+    beta = torch.randn(fo, generator=gen) * 0.1
+    X = torch.cat([x1, x2], 1) if two else x1
+    z64 = X.double() @ W.double().t() + b.double()
+    y64 = F.layer_norm(z64, (fo,), gamma.double(), beta.double(), 1e-5) if ln else z64
+    if relu:
+        y64 = F.relu(y64)
+    pack = ops.umma_pack_weights(W.to(DEV), fin, nseg)
+    z, y, mean, rstd = ops.umma_linear_fwd(_padded(x1), _padded(x2) if two else None, fin, pack, b.to(DEV), fo,
+                                           gamma=gamma.to(DEV), beta=beta.to(DEV), relu=relu, fuse_ln=ln, want_y=True)
+    ez, ey = rel_err(z, z64), rel_err(y, y64)
+    # the same product in plain fp32 (FFMA path) for comparison of the error level
+    zf = ops.linear_fwd(_padded(x1), _padded(x2) if two else None, W.to(DEV), b.to(DEV))
+    _log_err(f"fwd n={n} fin={fin} fo={fo} ln={ln}: umma_z={ez:.2e} umma_y={ey:.2e} ffma_z", rel_err(zf, z64))
+    assert ez < 3e-6 and ey < 5e-6
+    if ln:
+        assert rel_err(mean, z64.mean(1)) < 3e-6
+        assert rel_err(rstd, 1.0 / torch.sqrt(z64.var(1, unbiased=False) + 1e-5)) < 3e-6
+
+
+@pytest.mark.parametrize("n,fin,fo", [(1000, 218, 218), (4097, 64, 96), (257, 256, 16)])
+def test_umma_linear_bwd_data_3xtf32(n, fin, fo):
+    gen = torch.Generator().manual_seed(n + 1)
+    dz = torch.randn(n, fo, generator=gen)
+    W = (torch.rand(fo, 2 * fin, generator=gen) - 0.5) * 0.2
+    pack = ops.umma_pack_weights(W.to(DEV), fin, 2)
+    d1, d2 = ops.umma_linear_bwd_data(_padded(dz), pack, fin, 2)
+    e1 = rel_err(d1, dz.double() @ W.double()[:, :fin])
+    e2 = rel_err(d2, dz.double() @ W.double()[:, fin:])
+    _log_err(f"bwd_data n={n} fin={fin} fo={fo}: d1={e1:.2e} d2", e2)
+    assert e1 < 3e-6 and e2 < 3e-6
