@@ -121,7 +121,7 @@ class OpTimer:
 
     NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
-             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data"]
+             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2"]
 
     def __init__(self, ops, torch):
         self.ops, self.torch, self.rec, self.orig = ops, torch, [], {}
@@ -140,6 +140,10 @@ class OpTimer:
             return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(k))
         if name in ("layernorm_act_fwd", "layernorm_act_bwd"):
             return (name, int(a[0].shape[0]), int(a[0].shape[1]))
+        if name == "linear_bwd_data2":  # (dz1, col1, dz2, col2, W, k)
+            return (name, int(a[0].shape[0]), 2 * int(a[0].shape[1]), int(a[5]))
+        if name == "linear_bwd_weight2":  # (dz1, dz2, x, ...)
+            return (name, int(a[0].shape[0]), 2 * int(a[0].shape[1]), int(a[2].shape[1]))
         if name == "umma_linear_fwd":
             return (name, int(a[0].shape[0]), int(a[2]) * (2 if a[1] is not None else 1), int(a[5]))
         if name == "umma_linear_bwd_data":
@@ -190,7 +194,7 @@ def op_cost(key):
     if n == "umma_linear_fwd":  # reads [h | ah], writes z and y
         _, N, K, Fo = key
         return 4 * N * K + 8 * N * Fo + 4 * K * Fo, 2 * N * K * Fo
-    if n in ("linear_bwd_data", "umma_linear_bwd_data"):
+    if n in ("linear_bwd_data", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2"):
         _, N, Fo, K = key
         return 4 * N * Fo + 4 * N * K + 4 * K * Fo, 2 * N * K * Fo
     if n == "linear_bwd_weight":

@@ -30,10 +30,13 @@ SIGNATURES = {
     "gte_gather_f32": (ci, [vp, vp, vp, i64, vp]),
     "gte_degree_norm": (ci, [vp, i32, ci, vp, vp]),
     "gte_spmm": (ci, [vp, vp, vp, vp, vp, ci, vp, i64, vp, i64, vp, i64, i32, i32, vp]),
+    "gte_spmm_paged": (ci, [vp, vp, vp, vp, vp, ci, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
     "gte_linear_fwd": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, vp, vp, i64, i32, i32, vp]),
     "gte_linear_bwd_data": (ci, [vp, i64, i32, vp, i64, i32, i32, vp, vp, i64, i32, ci, vp]),
+    "gte_linear_bwd_data2": (ci, [vp, i64, i32, vp, i64, i32, i32, vp, i64, i32, vp, vp, i64, i32, ci, vp]),
     "gte_linear_bwd_weight_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "gte_linear_bwd_weight": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, ci, i32, vp, sz, vp]),
+    "gte_linear_bwd_weight2": (ci, [vp, i64, vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, vp, ci, i32, vp, sz, vp]),
     "gte_umma_supported": (ci, [i32, i32]),
     "gte_umma_pack_bytes": (sz, [i32, i32, i32]),
     "gte_umma_pack_weights": (ci, [vp, i64, i32, i32, i32, vp, vp]),

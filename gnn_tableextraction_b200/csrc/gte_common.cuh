@@ -54,6 +54,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// Fixed-order reduction of `nb` partial vectors: result(i) = sum_b partial[b*stride + i].
+// Block = 32 outputs (threadIdx.x & 31) x RED_SLICES slices (threadIdx.x >> 5): slice s adds
+// partials s, s+SLICES, ... in ascending order, then slice 0 adds the slice sums in ascending
+// order.  The order depends only on nb, so results are reproducible; unlike one thread walking
+// all nb partials, the loads of a block are independent and coalesced.  Valid in threads with
+// (threadIdx.x >> 5) == 0.  `smem` holds RED_SLICES*32 floats.  All threads must call it.
+constexpr int RED_SLICES = 32;
+constexpr int RED_THREADS = RED_SLICES * 32;
+__device__ __forceinline__ float reduce_partials_block(const float* __restrict__ partial, int nb, int64_t stride,
+                                                       int64_t i, bool valid, float* smem) {
+  const int ox = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  float s = 0.f;
+  if (valid)
+    for (int b = sy; b < nb; b += RED_SLICES) s += partial[(int64_t)b * stride + i];
+  smem[sy * 32 + ox] = s;
+  __syncthreads();
+  float t = 0.f;
+  if (sy == 0)
+    for (int k = 0; k < RED_SLICES; ++k) t += smem[k * 32 + ox];
+  return t;
+}
 #endif
 
 }  // namespace gte

@@ -41,6 +41,7 @@ struct GemmArgs {
   const float* bias;               // per n, may be null
   const float* row_scale;          // per m, may be null
   int32_t accumulate;              // C += result
+  int32_t vecC;                    // 128-bit stores allowed (c_stride_n == 1, 16-byte aligned rows)
   int32_t k_chunk;                 // split-K: rows of segment 0 per grid.z slice (multiple of 16); 0 = no split
   int64_t split_stride;            // floats between consecutive split partials
 };
@@ -274,16 +275,44 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_ffma(const GemmArgs g) {
     const int64_t m = m0 + ml;
     if (m >= g.M) continue;
     const float rs = g.row_scale ? __ldg(g.row_scale + m) : 1.0f;
+    if constexpr (TN >= 4) {
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int nl = (TN == 8) ? ((j < 4) ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4)) : ((TN == 4) ? tx * 4 + j : tx);
-      const int n = n0 + nl;
-      if (n >= g.N) continue;
-      float v = acc[i][j] * rs;
-      if (g.bias) v += __ldg(g.bias + n);
-      float* p = Cout + m * g.c_stride_m + (int64_t)n * g.c_stride_n;
-      if (g.accumulate) v += *p;
-      *p = v;
+      for (int jq = 0; jq < TN / 4; ++jq) {
+        const int nl = (jq == 0) ? tx * 4 : BN / 2 + tx * 4;
+        const int n = n0 + nl;
+        if (n >= g.N) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = acc[i][jq * 4 + j] * rs;
+          if (g.bias && n + j < g.N) v[j] += __ldg(g.bias + n + j);
+        }
+        float* p = Cout + m * g.c_stride_m + (int64_t)n * g.c_stride_n;
+        if (g.vecC && n + 3 < g.N) {
+          float4 o = make_float4(v[0], v[1], v[2], v[3]);
+          if (g.accumulate) {
+            const float4 c = *reinterpret_cast<const float4*>(p);
+            o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+          }
+          *reinterpret_cast<float4*>(p) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n + j >= g.N) continue;
+            float* pj = p + (int64_t)j * g.c_stride_n;
+            *pj = g.accumulate ? v[j] + *pj : v[j];
+          }
+        }
+      }
+    } else {
+      const int n = n0 + tx;
+      if (n < g.N) {
+        float v = acc[i][0] * rs;
+        if (g.bias) v += __ldg(g.bias + n);
+        float* p = Cout + m * g.c_stride_m + (int64_t)n * g.c_stride_n;
+        if (g.accumulate) v += *p;
+        *p = v;
+      }
     }
   }
 }

@@ -126,13 +126,119 @@ __global__ void __launch_bounds__(ROW_THREADS)
   }
 }
 
-// out[i] (+)= sum_b partial[b*stride + i], b ascending
-__global__ void k_reduce_partials(const float* __restrict__ partial, int nb, int64_t stride, int32_t count,
-                                  float* __restrict__ out, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  float s = 0.f;
-  for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * stride + i];
+// 128-bit variant: lane owns float4 chunks lane, lane+32, ... of the row; two rows in flight per warp.
+// Same arithmetic and the same fixed reduction order as the scalar kernel above.
+template <int MAXV>
+__global__ void __launch_bounds__(ROW_THREADS)
+    k_layernorm_act_bwd_v4(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z, int64_t ldz,
+                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                           float* __restrict__ dz, int64_t lddz, float* __restrict__ partial, int32_t n, int32_t f) {
+  extern __shared__ float sm[];  // [ROW_WARPS][2][f]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float gam[MAXV][4], bet[MAXV][4], dg[MAXV][4], db[MAXV][4];
+#pragma unroll
+  for (int c = 0; c < MAXV; ++c)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = 4 * (lane + 32 * c) + e;
+      gam[c][e] = col < f ? __ldg(gamma + col) : 0.f;
+      bet[c][e] = col < f ? __ldg(beta + col) : 0.f;
+      dg[c][e] = 0.f;
+      db[c][e] = 0.f;
+    }
+  const float inv_f = 1.0f / (float)f;
+  const int64_t stride = (int64_t)gridDim.x * ROW_WARPS;
+  for (int64_t row0 = (int64_t)blockIdx.x * ROW_WARPS + warp; row0 < n; row0 += 2 * stride) {
+    float4 zv[2][MAXV], gv[2][MAXV];
+    float mu[2], rs[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t row = row0 + u * stride;
+      live[u] = row < n;
+      mu[u] = live[u] ? mean[row] : 0.f;
+      rs[u] = live[u] ? rstd[row] : 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXV; ++c) {
+        const int col = 4 * (lane + 32 * c);
+        const bool ok = live[u] && col < f;  // padding columns [f, ld) are readable, never interpreted
+        zv[u][c] = ok ? *reinterpret_cast<const float4*>(z + row * ldz + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gv[u][c] = ok ? *reinterpret_cast<const float4*>(dy + row * lddy + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!live[u]) continue;  // warp-uniform
+      const int64_t row = row0 + u * stride;
+      float xh[MAXV][4], a[MAXV][4];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXV; ++c) {
+        const float zz[4] = {zv[u][c].x, zv[u][c].y, zv[u][c].z, zv[u][c].w};
+        const float gg[4] = {gv[u][c].x, gv[u][c].y, gv[u][c].z, gv[u][c].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = 4 * (lane + 32 * c) + e;
+          float g = 0.f;
+          xh[c][e] = 0.f;
+          if (col < f) {
+            xh[c][e] = (zz[e] - mu[u]) * rs[u];
+            g = gg[e];
+            if (relu && !(xh[c][e] * gam[c][e] + bet[c][e] > 0.f)) g = 0.f;
+          }
+          db[c][e] += g;
+          dg[c][e] = fmaf(g, xh[c][e], dg[c][e]);
+          a[c][e] = g * gam[c][e];
+          s1 += a[c][e];
+          s2 = fmaf(a[c][e], xh[c][e], s2);
+        }
+      }
+      const float c1 = warp_sum(s1) * inv_f;
+      const float c2 = warp_sum(s2) * inv_f;
+#pragma unroll
+      for (int c = 0; c < MAXV; ++c) {
+        const int col = 4 * (lane + 32 * c);
+        if (col < f) {
+          float4 o;
+          o.x = rs[u] * (a[c][0] - c1 - xh[c][0] * c2);
+          o.y = rs[u] * (a[c][1] - c1 - xh[c][1] * c2);
+          o.z = rs[u] * (a[c][2] - c1 - xh[c][2] * c2);
+          o.w = rs[u] * (a[c][3] - c1 - xh[c][3] * c2);
+          *reinterpret_cast<float4*>(dz + row * lddz + col) = o;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXV; ++c)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = 4 * (lane + 32 * c) + e;
+      if (col < f) {
+        sm[(warp * 2 + 0) * f + col] = dg[c][e];
+        sm[(warp * 2 + 1) * f + col] = db[c][e];
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * f; i += ROW_THREADS) {
+    const int which = i / f, col = i % f;
+    float s = 0.f;
+    for (int w = 0; w < ROW_WARPS; ++w) s += sm[(w * 2 + which) * f + col];
+    partial[(int64_t)blockIdx.x * 2 * f + i] = s;
+  }
+}
+
+// out[i] (+)= sum_b partial[b*stride + i] in a fixed order; 32 outputs per block
+__global__ void __launch_bounds__(RED_THREADS)
+    k_reduce_partials(const float* __restrict__ partial, int nb, int64_t stride, int32_t count, float* __restrict__ out,
+                      int accumulate) {
+  __shared__ float red[RED_THREADS];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool valid = i < count;
+  float s = reduce_partials_block(partial, nb, stride, i, valid, red);
+  if ((threadIdx.x >> 5) != 0 || !valid) return;
   if (accumulate) s += out[i];
   out[i] = s;
 }
@@ -390,7 +496,18 @@ int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t
   cudaStream_t st = as_stream(stream);
   float* partial = static_cast<float*>(ws);
   const int grid = ln_bwd_grid(n);
-  if (n > 0) {
+  const bool vec4 = aligned16(dy) && aligned16(z) && aligned16(dz) && lddy % 4 == 0 && ldz % 4 == 0 && lddz % 4 == 0 && f <= 512;
+  if (n > 0 && vec4) {
+    const size_t smem = (size_t)ROW_WARPS * 2 * f * 4;
+    const int nv = (f + 3) / 4;
+    if (nv <= 32)
+      k_layernorm_act_bwd_v4<1><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, beta, relu, dz, lddz, partial, n, f);
+    else if (nv <= 64)
+      k_layernorm_act_bwd_v4<2><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, beta, relu, dz, lddz, partial, n, f);
+    else
+      k_layernorm_act_bwd_v4<4><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, beta, relu, dz, lddz, partial, n, f);
+    GTE_CHECK_LAUNCH("k_layernorm_act_bwd_v4");
+  } else if (n > 0) {
     const size_t smem = (size_t)ROW_WARPS * 2 * f * 4;
     if (smem > 48 * 1024)
       GTE_CHECK_CUDA(cudaFuncSetAttribute(k_layernorm_act_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -402,9 +519,9 @@ int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t
     GTE_CHECK_LAUNCH("k_layernorm_act_bwd");
   }
   const int nb = n > 0 ? grid : 0;
-  k_reduce_partials<<<(unsigned)ceil_div64(f, 256), 256, 0, st>>>(partial, nb, 2 * (int64_t)f, f, dgamma, accumulate);
+  k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial, nb, 2 * (int64_t)f, f, dgamma, accumulate);
   GTE_CHECK_LAUNCH("k_reduce_partials");
-  k_reduce_partials<<<(unsigned)ceil_div64(f, 256), 256, 0, st>>>(partial + f, nb, 2 * (int64_t)f, f, dbeta,
+  k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial + f, nb, 2 * (int64_t)f, f, dbeta,
                                                                  accumulate);
   GTE_CHECK_LAUNCH("k_reduce_partials");
   return GTE_OK;
@@ -484,7 +601,7 @@ int gte_cross_entropy_fwd(const float* logits, int64_t ld, const void* labels, i
     k_ce_fwd<<<grid, CE_THREADS, 0, st>>>(logits, ld, labels, label_dtype, class_w, n, c, partial);
     GTE_CHECK_LAUNCH("k_ce_fwd");
   }
-  k_reduce_partials<<<1, 32, 0, st>>>(partial, n > 0 ? grid : 0, 3, 3, stats, 0);
+  k_reduce_partials<<<1, RED_THREADS, 0, st>>>(partial, n > 0 ? grid : 0, 3, 3, stats, 0);
   GTE_CHECK_LAUNCH("k_reduce_partials(ce)");
   return GTE_OK;
 }

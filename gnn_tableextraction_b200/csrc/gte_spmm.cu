@@ -168,6 +168,139 @@ static int launch_spmm(const int32_t* indptr, const int32_t* indices, const floa
   return GTE_OK;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Block-diagonal (page-batched) variant: one CTA per (page, column slice).  A batch of page graphs has
+// no edge between pages, so every source row a page's rows can touch lies in that page's own node
+// range.  The CTA stages, once and coalesced, everything the page needs in shared memory:
+//   x[page rows, slice] (cp.async), the page's row pointers, its column indices (made page-local) and
+//   its edge weights (with the source-side scale folded in),
+// after which the whole aggregation of the page runs out of shared memory: no dependent global
+// load is left in the per-row loop, and the L2->SM gather traffic (4*E*F bytes, ~10x the compulsory
+// bytes at degree 10) disappears -- the kernel streams x in / y out at HBM rate.  Indices outside
+// the page window (not block diagonal) fall back to a global load, so the result is always correct.
+template <int G>
+__global__ void __launch_bounds__(SPMM_THREADS)
+    k_spmm_paged(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ w,
+                 const float* __restrict__ pre_scale, const float* __restrict__ row_norm, int mode,
+                 const float* __restrict__ x, int64_t ldx, const float* __restrict__ addend, int64_t ldadd,
+                 float* __restrict__ y, int64_t ldy, const int32_t* __restrict__ page_off, int32_t f,
+                 int32_t np_cap, int32_t ne_cap) {
+  extern __shared__ __align__(16) float smem_f[];
+  constexpr int CS = G * 4;
+  constexpr int ROWS_PER_ITER = SPMM_THREADS / G;
+  float* sx = smem_f;                                                   // [np_cap][CS]
+  int32_t* s_idx = reinterpret_cast<int32_t*>(sx + (size_t)np_cap * CS);  // [ne_cap] page-local column ids
+  float* s_w = reinterpret_cast<float*>(s_idx + ne_cap);                // [ne_cap]
+  int32_t* s_ptr = reinterpret_cast<int32_t*>(s_w + ne_cap);            // [np_cap + 1] page-local row pointers
+  const int page = blockIdx.x;
+  const int c0 = blockIdx.y * CS;
+  const int32_t n0 = page_off[page], n1 = page_off[page + 1];
+  const int32_t np = n1 - n0;
+  const int32_t e0 = indptr[n0];
+  const int32_t ne = indptr[n1] - e0;
+  const bool staged_edges = ne <= ne_cap;  // always true when the caller's max_page_edges is right
+  // x slice: 16-byte chunks; chunks entirely beyond f are zero-filled
+  for (int i = threadIdx.x; i < np * G; i += SPMM_THREADS) {
+    const int r = i / G, ch = i % G;
+    const int col = c0 + ch * 4;
+    float* dst = sx + (size_t)r * CS + ch * 4;
+    if (col < f) {
+      const float* src = x + (int64_t)(n0 + r) * ldx + col;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                   : "memory");
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = threadIdx.x; i <= np; i += SPMM_THREADS) s_ptr[i] = indptr[n0 + i] - e0;
+  if (staged_edges) {
+    for (int i = threadIdx.x; i < ne; i += SPMM_THREADS) {
+      const int32_t c = __ldg(indices + e0 + i);
+      float wv = w ? __ldg(w + e0 + i) : 1.0f;
+      if (pre_scale) wv *= __ldg(pre_scale + c);
+      s_idx[i] = c - n0;
+      s_w[i] = wv;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int lane = threadIdx.x % G;
+  const int grp = threadIdx.x / G;
+  const int col = c0 + lane * 4;
+  const bool on = col < f;
+  for (int32_t rl = grp; rl < np; rl += ROWS_PER_ITER) {
+    const int64_t row = n0 + rl;
+    const int32_t beg = s_ptr[rl], end = s_ptr[rl + 1];
+    // issue the row-end operands early so their latency overlaps the neighbour loop
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (addend && on) av = __ldg(reinterpret_cast<const float4*>(addend + row * ldadd + col));
+    const float nrm = (mode == GTE_AGG_SUM_NORM) ? __ldg(row_norm + row) : 1.0f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int32_t j = beg; j < end; ++j) {
+      int32_t sl;
+      float wt;
+      if (staged_edges) {
+        sl = s_idx[j];  // shared-memory broadcasts
+        wt = s_w[j];
+      } else {
+        const int32_t c = __ldg(indices + e0 + j);
+        wt = w ? __ldg(w + e0 + j) : 1.0f;
+        if (pre_scale) wt *= __ldg(pre_scale + c);
+        sl = c - n0;
+      }
+      float4 xv;
+      if (sl >= 0 && sl < np) {
+        xv = *reinterpret_cast<const float4*>(sx + (size_t)sl * CS + lane * 4);
+      } else {
+        xv = on ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)(sl + n0) * ldx + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      acc.x = fmaf(wt, xv.x, acc.x);
+      acc.y = fmaf(wt, xv.y, acc.y);
+      acc.z = fmaf(wt, xv.z, acc.z);
+      acc.w = fmaf(wt, xv.w, acc.w);
+    }
+    if (!on) continue;
+    if (mode == GTE_AGG_MEAN) {
+      const int32_t deg = end - beg;
+      const float d = (float)(deg > 1 ? deg : 1);
+      acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d;
+    } else if (mode == GTE_AGG_SUM_NORM) {
+      acc.x *= nrm; acc.y *= nrm; acc.z *= nrm; acc.w *= nrm;
+    }
+    if (addend) {
+      acc.x += av.x; acc.y += av.y; acc.z += av.z; acc.w += av.w;
+    }
+    *reinterpret_cast<float4*>(y + row * ldy + col) = acc;
+  }
+}
+
+static size_t paged_smem_bytes(int G, int32_t np_cap, int32_t ne_cap) {
+  return (size_t)np_cap * G * 16 + (size_t)ne_cap * 8 + ((size_t)np_cap + 1) * 4 + 16;
+}
+
+template <int G>
+static int launch_spmm_paged(const int32_t* indptr, const int32_t* indices, const float* w, const float* pre_scale,
+                             const float* row_norm, int mode, const float* x, int64_t ldx, const float* addend,
+                             int64_t ldadd, float* y, int64_t ldy, const int32_t* page_off, int32_t num_pages,
+                             int32_t np_cap, int32_t ne_cap, int32_t f, cudaStream_t st) {
+  constexpr int CS = G * 4;
+  const size_t smem = paged_smem_bytes(G, np_cap, ne_cap);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_paged<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "k_spmm_paged(smem attr)");
+    configured = smem;
+  }
+  dim3 grid((unsigned)num_pages, (unsigned)ceil_div64(f, CS));
+  k_spmm_paged<G><<<grid, SPMM_THREADS, smem, st>>>(indptr, indices, w, pre_scale, row_norm, mode, x, ldx, addend, ldadd, y,
+                                                    ldy, page_off, f, np_cap, ne_cap);
+  GTE_CHECK_LAUNCH("k_spmm_paged");
+  return GTE_OK;
+}
+
 }  // namespace gte
 
 using namespace gte;
@@ -205,4 +338,42 @@ extern "C" int gte_spmm(const int32_t* indptr, const int32_t* indices, const flo
     GTE_SPMM_GO(1, 32, 4);  // blocks of 128 columns over grid.y
   }
 #undef GTE_SPMM_GO
+}
+
+extern "C" int gte_spmm_paged(const int32_t* indptr, const int32_t* indices, const float* w, const float* pre_scale,
+                              const float* row_norm, int mode, const float* x, int64_t ldx, const float* addend,
+                              int64_t ldadd, float* y, int64_t ldy, const int32_t* page_off, int32_t num_pages,
+                              int32_t max_page_nodes, int32_t max_page_edges, int32_t n_rows, int32_t f,
+                              gte_stream_t stream) {
+  GTE_CHECK_ARG(n_rows >= 0 && f >= 0 && num_pages >= 0 && max_page_nodes >= 0 && max_page_edges >= 0,
+                "gte_spmm_paged: negative size");
+  GTE_CHECK_ARG(mode == GTE_AGG_SUM || mode == GTE_AGG_SUM_NORM || mode == GTE_AGG_MEAN, "gte_spmm_paged: bad mode %d", mode);
+  if (n_rows == 0 || f == 0 || num_pages == 0) return GTE_OK;
+  GTE_CHECK_ARG(indptr && indices && x && y && page_off, "gte_spmm_paged: null argument");
+  GTE_CHECK_ARG(mode != GTE_AGG_SUM_NORM || row_norm, "gte_spmm_paged: SUM_NORM needs row_norm");
+  GTE_CHECK_ARG(ldx >= f && ldy >= f && (!addend || ldadd >= f), "gte_spmm_paged: leading dimension < f");
+  GTE_CHECK_ARG(x != y, "gte_spmm_paged: x and y must not alias");
+  const bool vec = aligned16(x) && aligned16(y) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
+                   (!addend || (aligned16(addend) && ldadd % 4 == 0));
+  // widest column slice whose page working set fits ~110 KB of shared memory (2 CTAs per SM)
+  const size_t budget = 110 * 1024;
+  int G = 0;
+  const int fv = (f + 3) / 4;  // 16-byte chunks per row
+  for (int g : {32, 16, 8}) {
+    if (paged_smem_bytes(g, max_page_nodes, max_page_edges) <= budget) {
+      G = g;
+      break;
+    }
+  }
+  while (G > 8 && G / 2 >= fv) G /= 2;  // narrow rows: do not stage padding
+  if (!vec || G == 0)  // unaligned operands or pages too large to stage: generic L2-gather kernel
+    return gte_spmm(indptr, indices, w, pre_scale, row_norm, mode, x, ldx, addend, ldadd, y, ldy, n_rows, f, stream);
+  cudaStream_t st = as_stream(stream);
+#define GTE_PAGED_GO(GG)                                                                                               \
+  return launch_spmm_paged<GG>(indptr, indices, w, pre_scale, row_norm, mode, x, ldx, addend, ldadd, y, ldy, page_off, \
+                               num_pages, max_page_nodes, max_page_edges, f, st)
+  if (G == 32) GTE_PAGED_GO(32);
+  if (G == 16) GTE_PAGED_GO(16);
+  GTE_PAGED_GO(8);
+#undef GTE_PAGED_GO
 }

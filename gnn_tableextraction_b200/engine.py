@@ -28,7 +28,7 @@ import torch.nn as nn
 from . import layers as L
 from . import ops
 from ._lib import GteError
-from .graph import PageGraphBatch
+from .graph import PageGraphBatch, page_table
 from .nn import GcnSAGE, _is_relu
 
 
@@ -160,8 +160,13 @@ class SageTrainer:
         self._static_meta = (n, e, host_batch["batch_num_nodes"], host_batch["batch_num_edges"])
         self.load_batch(host_batch)
 
+        # host->device copy must happen outside the capture, and the tensor must outlive it (the graph
+        # replays read it): keep a reference on the trainer
+        pages = self._static_pages = page_table(self._static_meta[2], self._static_meta[3], n, dev)
+
         def body():
             g = PageGraphBatch(st["src"], st["dst"], n, self._static_meta[2], self._static_meta[3])
+            g._cache["pages"] = pages
             g.edata["feat"] = st["weight"]
             g.ndata["feat"] = st["feat"]
             self._step_impl(g, st["label"])

@@ -169,6 +169,15 @@ class PageGraphBatch:
             self._cache[k] = v
         return v
 
+    def pages(self):
+        """(page_off int32 [P+1] on device, P, max page nodes, max page edges) for the staged SpMM, or None
+        when the batch has no page structure worth staging (a single huge graph)."""
+        v = self._cache.get("pages", 0)
+        if v == 0:
+            v = page_table(self._bn, self._be, self._n, self.device)
+            self._cache["pages"] = v
+        return v
+
     def _weights(self, which: str, w: torch.Tensor) -> torch.Tensor:
         if w.dtype != torch.float32:
             w = w.float()
@@ -195,6 +204,19 @@ class PageGraphBatch:
 
     def weights_csr(self, w: torch.Tensor) -> torch.Tensor:
         return self._weights("w_csr", w)
+
+
+def page_table(batch_num_nodes, batch_num_edges, num_nodes: int, device):
+    """(page_off int32 [P+1] device tensor, P, max page nodes, max page edges) or None (no useful page
+    structure).  Pages are closed under edges, so the per-page edge counts hold for the CSC and the CSR."""
+    bn = list(batch_num_nodes) if batch_num_nodes is not None else []
+    be = list(batch_num_edges) if batch_num_edges is not None else []
+    mx = max(bn) if bn else 0
+    if not bn or len(be) != len(bn) or sum(bn) != num_nodes or mx > 1600:
+        return None
+    off = np.zeros(len(bn) + 1, dtype=np.int32)
+    np.cumsum(np.asarray(bn, dtype=np.int64), out=off[1:])
+    return (torch.from_numpy(off).to(device), len(bn), int(mx), int(max(be)))
 
 
 def batch_pages_host(pages, pin: bool = True) -> Dict[str, torch.Tensor]:

@@ -79,7 +79,7 @@ def aggregate_forward(g: PageGraphBatch, h: torch.Tensor, w_edge: torch.Tensor, 
     """``update_all(u_mul_e, sum|mean)`` (+ ``* norm``): models.py:53-54,69-71,149."""
     indptr, indices, _ = g.csc()
     return ops.spmm(indptr, indices, g.weights_csc(w_edge), h, mode=_agg_mode(agg),
-                    row_norm=g.norm() if agg == GCN else None, addend=addend)
+                    row_norm=g.norm() if agg == GCN else None, addend=addend, pages=g.pages())
 
 
 def aggregate_backward(g: PageGraphBatch, d_out: torch.Tensor, w_edge: torch.Tensor,
@@ -87,7 +87,7 @@ def aggregate_backward(g: PageGraphBatch, d_out: torch.Tensor, w_edge: torch.Ten
     """d h[u] = sum_{u->v} w_e * norm[v] * d_out[v] (+ addend[u]) on the CSR (reverse graph)."""
     indptr, indices, _ = g.csr()
     return ops.spmm(indptr, indices, g.weights_csr(w_edge), d_out, mode=_lib.GTE_AGG_SUM, pre_scale=g.norm(),
-                    addend=addend)
+                    addend=addend, pages=g.pages())
 
 
 def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Optional[torch.Tensor],
@@ -158,13 +158,10 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
     # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
     #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn
     gq = aggregate_backward(g, dz, ctx.w_edge)
-    ops.linear_bwd_weight(dz, ctx.h, None, dW, db, accumulate, w_col0=0)
-    ops.linear_bwd_weight(gq, ctx.h, None, dW, None, accumulate, w_col0=fin)
+    ops.linear_bwd_weight2(dz, gq, ctx.h, dW, 0, fin, db, accumulate)
     if not need_dh:
         return None
-    dh = ops.linear_bwd_data(dz, W, 0, fin)
-    ops.linear_bwd_data(gq, W, fin, fin, out=dh, accumulate=True)
-    return dh
+    return ops.linear_bwd_data2(dz, 0, gq, fin, W, fin)
 
 
 # ------------------------------------------------------------- autograd ----

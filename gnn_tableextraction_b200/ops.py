@@ -139,8 +139,11 @@ def degree_norm(indptr: torch.Tensor, mode: int = _lib.GTE_NORM_INV_DEG_ZERO) ->
 
 
 # ------------------------------------------------------------ aggregation ---
-def spmm(indptr, indices, w, x, *, mode=_lib.GTE_AGG_SUM, row_norm=None, pre_scale=None, addend=None, out=None):
-    """y[r] = post(r) * sum_j w[j] * pre[c_j] * x[c_j] (+ addend[r]); see gte.h."""
+def spmm(indptr, indices, w, x, *, mode=_lib.GTE_AGG_SUM, row_norm=None, pre_scale=None, addend=None, out=None,
+         pages=None):
+    """y[r] = post(r) * sum_j w[j] * pre[c_j] * x[c_j] (+ addend[r]); see gte.h.
+    ``pages`` = (page_off int32 [P+1] device tensor, P, max_page_nodes, max_page_edges) selects the
+    shared-memory staged kernel for block-diagonal page batches."""
     xp, ldx, f = _mat(x, "spmm.x")
     n_rows = indptr.numel() - 1
     if out is None:
@@ -153,6 +156,17 @@ def spmm(indptr, indices, w, x, *, mode=_lib.GTE_AGG_SUM, row_norm=None, pre_sca
         ap, lda, fa = _mat(addend, "spmm.addend")
         if fa != f or addend.shape[0] != n_rows:
             raise GteError("spmm: addend shape mismatch")
+    if pages is not None and pages[1] > 0:
+        page_off, num_pages, max_nodes, max_edges = pages
+        check(
+            lib().gte_spmm_paged(_vec(indptr, "indptr", torch.int32), _vec(indices, "indices", torch.int32),
+                                 _vec(w, "w", n=indices.numel()), _vec(pre_scale, "pre_scale"),
+                                 _vec(row_norm, "row_norm", n=n_rows), mode, xp, ldx, ap, lda, yp, ldy,
+                                 _vec(page_off, "page_off", torch.int32, num_pages + 1), num_pages, max_nodes, max_edges, n_rows, f,
+                                 _stream()),
+            "gte_spmm_paged",
+        )
+        return out
     check(
         lib().gte_spmm(_vec(indptr, "indptr", torch.int32), _vec(indices, "indices", torch.int32),
                        _vec(w, "w", n=indices.numel()), _vec(pre_scale, "pre_scale"), _vec(row_norm, "row_norm", n=n_rows),
@@ -210,6 +224,29 @@ def linear_bwd_data(dz, W, col0: int, k: int, row_scale=None, out=None, accumula
     return out
 
 
+def linear_bwd_data2(dz1, col1: int, dz2, col2: int, W, k: int, row_scale=None, out=None, accumulate=False):
+    """dx (+)= (dz1 W[:, col1:col1+k] + dz2 W[:, col2:col2+k]) * row_scale -- one launch."""
+    d1p, ld1, fo = _mat(dz1, "bwd_data2.dz1")
+    d2p, ld2, fo2 = _mat(dz2, "bwd_data2.dz2")
+    Wp, ldw, kw = _mat(W, "bwd_data2.W")
+    if fo2 != fo or W.shape[0] != fo or max(col1, col2) + k > kw or dz2.shape[0] != dz1.shape[0]:
+        raise GteError("linear_bwd_data2: shape mismatch")
+    n = dz1.shape[0]
+    if out is None:
+        if accumulate:
+            raise GteError("linear_bwd_data2: accumulate needs an output")
+        out = empty_padded(n, k, dz1.device)
+    dxp, lddx, kx = _mat(out, "bwd_data2.dx")
+    if kx != k or out.shape[0] != n:
+        raise GteError("linear_bwd_data2: output shape mismatch")
+    check(
+        lib().gte_linear_bwd_data2(d1p, ld1, col1, d2p, ld2, col2, fo, Wp, ldw, k, _vec(row_scale, "row_scale", n=n), dxp,
+                                   lddx, n, 1 if accumulate else 0, _stream()),
+        "gte_linear_bwd_data2",
+    )
+    return out
+
+
 def linear_bwd_weight(dz, x1, x2, dW, db, accumulate=False, w_col0: int = 0):
     """dW[:, c0:c0+k1+k2] (+)= dz^T [x1 | x2]; db (+)= colsum(dz) (db may be None)."""
     dzp, lddz, fo = _mat(dz, "bwd_weight.dz")
@@ -228,6 +265,24 @@ def linear_bwd_weight(dz, x1, x2, dW, db, accumulate=False, w_col0: int = 0):
         l.gte_linear_bwd_weight(dzp, lddz, fo, x1p, ld1, k1, x2p, ld2, k2, dWp + 4 * w_col0, lddw,
                                 _vec(db, "db", n=fo), 1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),
         "gte_linear_bwd_weight",
+    )
+
+
+def linear_bwd_weight2(dz1, dz2, x, dW, col1: int, col2: int, db, accumulate=False):
+    """dW[:, col1:col1+k] (+)= dz1^T x ; dW[:, col2:col2+k] (+)= dz2^T x ; db (+)= colsum(dz1) -- x is read once."""
+    d1p, ld1, fo = _mat(dz1, "bwd_weight2.dz1")
+    d2p, ld2, fo2 = _mat(dz2, "bwd_weight2.dz2")
+    xp, ldx, k = _mat(x, "bwd_weight2.x")
+    dWp, lddw, kw = _mat(dW, "bwd_weight2.dW")
+    n = dz1.shape[0]
+    if fo2 != fo or dW.shape[0] != fo or max(col1, col2) + k > kw or dz2.shape[0] != n or x.shape[0] != n:
+        raise GteError("linear_bwd_weight2: shape mismatch")
+    l = lib()
+    ws = workspace(l.gte_linear_bwd_weight_workspace_bytes(n, fo, k, k), dz1.device)
+    check(
+        l.gte_linear_bwd_weight2(d1p, ld1, d2p, ld2, fo, xp, ldx, k, dWp, lddw, col1, col2, _vec(db, "db", n=fo),
+                                 1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),
+        "gte_linear_bwd_weight2",
     )
 
 

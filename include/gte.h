@@ -128,6 +128,21 @@ int gte_spmm(const int32_t* indptr, const int32_t* indices, const float* w,
              const float* x, int64_t ldx, const float* addend, int64_t ldadd,
              float* y, int64_t ldy, int32_t n_rows, int32_t f, gte_stream_t stream);
 
+/*
+ * Same contract as gte_spmm for a batch of independent page graphs (block-diagonal adjacency):
+ * `page_off` [num_pages+1] (int32, device) are the node offsets of the pages
+ * (dgl.batch's batch_num_nodes prefix sums), `max_page_nodes` / `max_page_edges` the largest page.
+ * Each page's operand slice is staged in shared memory so gathers never leave the SM.
+ * Falls back to gte_spmm when pages are too large to stage or operands are unaligned;
+ * indices outside a page's own range are still handled correctly (slow path).
+ */
+int gte_spmm_paged(const int32_t* indptr, const int32_t* indices, const float* w,
+                   const float* pre_scale, const float* row_norm, int mode,
+                   const float* x, int64_t ldx, const float* addend, int64_t ldadd,
+                   float* y, int64_t ldy, const int32_t* page_off, int32_t num_pages,
+                   int32_t max_page_nodes, int32_t max_page_edges, int32_t n_rows, int32_t f,
+                   gte_stream_t stream);
+
 /* ------------------------------------------------- dense projection ----- */
 /*
  * z[n,fo] = x1[n,k1] W[:, 0:k1]^T + x2[n,k2] W[:, k1:k1+k2]^T + bias
@@ -149,6 +164,14 @@ int gte_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo,
                         const float* W, int64_t ldw, int32_t col0, int32_t k,
                         const float* row_scale, float* dx, int64_t lddx, int32_t n,
                         int accumulate, gte_stream_t stream);
+/*
+ * Two-term form used by the project-then-aggregate layers:
+ * dx (+)= (dz1 W[:, col1:col1+k] + dz2 W[:, col2:col2+k]) * row_scale[r]   (dz2 may be NULL).
+ */
+int gte_linear_bwd_data2(const float* dz1, int64_t lddz1, int32_t col1,
+                         const float* dz2, int64_t lddz2, int32_t col2, int32_t fo,
+                         const float* W, int64_t ldw, int32_t k, const float* row_scale,
+                         float* dx, int64_t lddx, int32_t n, int accumulate, gte_stream_t stream);
 
 /*
  * dW[fo, k1+k2] = dz^T [x1 | x2]  and  db[fo] = column sums of dz (db may be
@@ -162,6 +185,16 @@ int gte_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo,
                           const float* x2, int64_t ldx2, int32_t k2,
                           float* dW, int64_t lddw, float* db, int accumulate, int32_t n,
                           void* ws, size_t ws_bytes, gte_stream_t stream);
+
+/*
+ * Two gradient blocks against the SAME input in one pass (project-then-aggregate layers):
+ * dW[:, col1:col1+k] (+)= dz1^T x ; dW[:, col2:col2+k] (+)= dz2^T x ; db (+)= colsum(dz1).
+ * Workspace: gte_linear_bwd_weight_workspace_bytes(n, fo, k, k).
+ */
+int gte_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz2, int64_t lddz2, int32_t fo,
+                           const float* x, int64_t ldx, int32_t k, float* dW, int64_t lddw,
+                           int32_t col1, int32_t col2, float* db, int accumulate, int32_t n,
+                           void* ws, size_t ws_bytes, gte_stream_t stream);
 
 /* ------------------------------------ tensor-core route (tcgen05, 3xTF32) -- */
 /*

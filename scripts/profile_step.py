@@ -1,0 +1,17 @@
+"""Two eager train steps at config 2 (512 pages) for ncu; no timing here."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.nn.functional as F
+import gnn_tableextraction_b200 as gte
+from gnn_tableextraction_b200 import synth
+from gnn_tableextraction_b200.graph import batch_pages_host
+pages = synth.make_pages(int(os.environ.get("PAGES", "512")), distinct=64)
+hb = batch_pages_host(pages)
+torch.manual_seed(0)
+model = gte.GcnSAGE(13, 218, 9, 3, F.relu, 0).cuda()
+tr = gte.SageTrainer(model)
+for _ in range(int(os.environ.get("STEPS", "2"))):
+    g = gte.PageGraphBatch.from_host(hb, "cuda")
+    tr.train_step(g)
+torch.cuda.synchronize()
+print("launches", gte.lib().gte_launch_count())

@@ -362,3 +362,52 @@ def test_umma_linear_bwd_data_3xtf32(n, fin, fo):
     e2 = rel_err(d2, dz.double() @ W.double()[:, fin:])
     _log_err(f"bwd_data n={n} fin={fin} fo={fo}: d1={e1:.2e} d2", e2)
     assert e1 < 3e-6 and e2 < 3e-6
+
+
+@pytest.mark.parametrize("n,k,fo", [(2000, 218, 9), (300, 40, 16), (700, 64, 48), (0, 10, 4)])
+def test_linear_two_term_backward(n, k, fo):
+    """project-then-aggregate backward: dW blocks against one input, dx from two gradients."""
+    gen = torch.Generator().manual_seed(k)
+    x = torch.randn(n, k, generator=gen)
+    dz1, dz2 = torch.randn(n, fo, generator=gen), torch.randn(n, fo, generator=gen)
+    W = torch.randn(fo, 2 * k, generator=gen) * 0.1
+    dW = torch.full((fo, 2 * k), 3.0, device=DEV)
+    db = torch.full((fo,), 3.0, device=DEV)
+    ops.linear_bwd_weight2(_padded(dz1), _padded(dz2), _padded(x), dW, 0, k, db)
+    if n:
+        assert rel_err(dW[:, :k], dz1.double().t() @ x.double()) < 2e-6
+        assert rel_err(dW[:, k:], dz2.double().t() @ x.double()) < 2e-6
+        assert rel_err(db, dz1.double().sum(0)) < 2e-6
+    else:
+        assert torch.all(dW == 0) and torch.all(db == 0)
+    dx = ops.linear_bwd_data2(_padded(dz1), 0, _padded(dz2), k, W.to(DEV), k)
+    if n:
+        assert rel_err(dx, dz1.double() @ W.double()[:, :k] + dz2.double() @ W.double()[:, k:]) < 2e-6
+    dW2 = torch.empty_like(dW)
+    ops.linear_bwd_weight2(_padded(dz1), _padded(dz2), _padded(x), dW2, 0, k, None)
+    assert torch.equal(dW2, dW)
+
+
+@pytest.mark.parametrize("f", [9, 13, 64, 218, 300])
+def test_spmm_paged_equals_generic(f):
+    """shared-memory staged kernel (one CTA per page x column slice) == generic kernel, bit for bit"""
+    pages = synth.make_pages(9, ragged=True, k=7)
+    s, d, w, noff, _ = csx.batch_coo(pages)
+    n = int(noff[-1])
+    ip, ix, ei = ops.csx_from_coo(_i32(d), _i32(s), n)
+    w_row = ops.gather_f32(_f32(w), ei)
+    norm = ops.degree_norm(ip)
+    x = _padded(torch.randn(n, f))
+    add = _padded(torch.randn(n, f))
+    pre = torch.rand(n, device=DEV)
+    pg = (_i32(noff), len(pages), int(max(p.num_nodes for p in pages)), int(max(p.num_edges for p in pages)))
+    for kw in (dict(mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm), dict(mode=_lib.GTE_AGG_MEAN),
+               dict(mode=_lib.GTE_AGG_SUM, pre_scale=pre, addend=add)):
+        a = ops.spmm(ip, ix, w_row, x, **kw)
+        b = ops.spmm(ip, ix, w_row, x, pages=pg, **kw)
+        assert torch.equal(a, b)
+    # wrong page table (graph is NOT block diagonal w.r.t. it): the slow path keeps the result correct
+    fake = (_i32(np.array([0, n // 3, n])), 2, int(n - n // 3), 64)  # also under-sized edge capacity
+    if fake[2] <= 1600:
+        b = ops.spmm(ip, ix, w_row, x, pages=fake, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
+        assert torch.equal(ops.spmm(ip, ix, w_row, x, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm), b)
