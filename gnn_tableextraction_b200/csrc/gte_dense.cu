@@ -80,11 +80,11 @@ static int dw_block(const float* dz, int64_t lddz, int32_t fo, const float* x, i
   if (k == 0) return GTE_OK;
   if (gram_eligible(k + (db ? 1 : 0))) {  // narrow x (input layer): stream dz once, bias gradient for free
     *did_ones = db != nullptr;
-    return gram_tall(dz, lddz, fo, x, ldx, k, nullptr, 0, 0, db != nullptr, n, dWblk, lddw, 1, nullptr, 0, 0, db,
+    return gram_tall(dz, lddz, fo, x, ldx, k, nullptr, 0, 0, db != nullptr, n, dWblk, lddw, 1, nullptr, 0, 0, db, nullptr,
                      accumulate, part, st);
   }
   if (gram_eligible(fo))  // narrow dz (class layer): stream x once, write the transpose
-    return gram_tall(x, ldx, k, dz, lddz, fo, nullptr, 0, 0, false, n, dWblk, 1, lddw, nullptr, 0, 0, nullptr,
+    return gram_tall(x, ldx, k, dz, lddz, fo, nullptr, 0, 0, false, n, dWblk, 1, lddw, nullptr, 0, 0, nullptr, nullptr,
                      accumulate, part, st);
   const bool dz_is_A = fo >= k;  // put the wider side on the 128-row tile axis
   const int32_t M = dz_is_A ? fo : k, N = dz_is_A ? k : fo;
@@ -234,8 +234,8 @@ int gte_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const float
   cudaStream_t st = as_stream(stream);
   float* part = static_cast<float*>(ws);
   if (k1 > 0 && k2 > 0 && gram_eligible(k1 + k2 + (db ? 1 : 0)))  // both blocks narrow (input layer): ONE pass over dz
-    return gram_tall(dz, lddz, fo, x1, ldx1, k1, x2, ldx2, k2, db != nullptr, n, dW, lddw, 1, dW + k1, lddw, 1, db, accumulate,
-                     part, st);
+    return gram_tall(dz, lddz, fo, x1, ldx1, k1, x2, ldx2, k2, db != nullptr, n, dW, lddw, 1, dW + k1, lddw, 1, db, nullptr,
+                     accumulate, part, st);
   bool have_db = db == nullptr, did = false;
   int rc = dw_block(dz, lddz, fo, x1, ldx1, k1, dW, lddw, have_db ? nullptr : db, accumulate, n, part, st, &did);
   if (rc != GTE_OK) return rc;
@@ -267,10 +267,11 @@ int gte_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz2, in
   float* bpart = reinterpret_cast<float*>(static_cast<char*>(ws) + (need - 256 - colsum_ws_bytes(n, fo)));
   if (gram_eligible(2 * fo)) {
     // one pass over the wide operand x for both gradient blocks: Q = [dz1 | dz2]
+    const bool fuse_db = db && aligned16(x) && ldx % 4 == 0;  // bias gradient = column sums of dz1, from the same pass
     int rc = gram_tall(x, ldx, k, dz1, lddz1, fo, dz2, lddz2, fo, false, n, dW + col1, 1, lddw, dW + col2, 1, lddw, nullptr,
-                       accumulate, part, st);
+                       fuse_db ? db : nullptr, accumulate, part, st);
     if (rc != GTE_OK) return rc;
-    return db ? colsum(dz1, lddz1, n, fo, db, accumulate, bpart, st) : GTE_OK;
+    return (db && !fuse_db) ? colsum(dz1, lddz1, n, fo, db, accumulate, bpart, st) : GTE_OK;
   }
   bool did = false;
   int rc = dw_block(dz1, lddz1, fo, x, ldx, k, dW + col1, lddw, nullptr, accumulate, n, part, st, &did);

@@ -57,17 +57,17 @@ __global__ void __launch_bounds__(ROW_THREADS)
   }
 }
 
-// dz per row + per-block partial sums of dgamma / dbeta: partial[block][2][f]
+// dz per row + per-block partial sums of dgamma / dbeta / colsum(dz): partial[block][3][f]
 template <int MAXC>
 __global__ void __launch_bounds__(ROW_THREADS)
     k_layernorm_act_bwd(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ z, int64_t ldz,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                         float* __restrict__ dz, int64_t lddz, float* __restrict__ partial, int32_t n, int32_t f) {
-  extern __shared__ float sm[];  // [ROW_WARPS][2][f]
+  extern __shared__ float sm[];  // [ROW_WARPS][3][f]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float gam[MAXC], bet[MAXC], dg[MAXC], db[MAXC];
+  float gam[MAXC], bet[MAXC], dg[MAXC], db[MAXC], dl[MAXC];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     const int col = lane + 32 * c;
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
     bet[c] = col < f ? __ldg(beta + col) : 0.f;
     dg[c] = 0.f;
     db[c] = 0.f;
+    dl[c] = 0.f;
   }
   const float inv_f = 1.0f / (float)f;
   for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < n; row += (int64_t)gridDim.x * ROW_WARPS) {
@@ -105,7 +106,11 @@ __global__ void __launch_bounds__(ROW_THREADS)
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
       const int col = lane + 32 * c;
-      if (col < f) dr[col] = rs * (a[c] - c1 - xh[c] * c2);
+      if (col < f) {
+        const float o = rs * (a[c] - c1 - xh[c] * c2);
+        dr[col] = o;
+        dl[c] += o;
+      }
     }
   }
   // block combine, warps in fixed order
@@ -113,16 +118,17 @@ __global__ void __launch_bounds__(ROW_THREADS)
   for (int c = 0; c < MAXC; ++c) {
     const int col = lane + 32 * c;
     if (col < f) {
-      sm[(warp * 2 + 0) * f + col] = dg[c];
-      sm[(warp * 2 + 1) * f + col] = db[c];
+      sm[(warp * 3 + 0) * f + col] = dg[c];
+      sm[(warp * 3 + 1) * f + col] = db[c];
+      sm[(warp * 3 + 2) * f + col] = dl[c];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * f; i += ROW_THREADS) {
+  for (int i = threadIdx.x; i < 3 * f; i += ROW_THREADS) {
     const int which = i / f, col = i % f;
     float s = 0.f;
-    for (int w = 0; w < ROW_WARPS; ++w) s += sm[(w * 2 + which) * f + col];
-    partial[(int64_t)blockIdx.x * 2 * f + i] = s;
+    for (int w = 0; w < ROW_WARPS; ++w) s += sm[(w * 3 + which) * f + col];
+    partial[(int64_t)blockIdx.x * 3 * f + i] = s;
   }
 }
 
@@ -134,10 +140,10 @@ __global__ void __launch_bounds__(ROW_THREADS)
                            const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                            float* __restrict__ dz, int64_t lddz, float* __restrict__ partial, int32_t n, int32_t f) {
-  extern __shared__ float sm[];  // [ROW_WARPS][2][f]
+  extern __shared__ float sm[];  // [ROW_WARPS][3][f]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float gam[MAXV][4], bet[MAXV][4], dg[MAXV][4], db[MAXV][4];
+  float gam[MAXV][4], bet[MAXV][4], dg[MAXV][4], db[MAXV][4], dl[MAXV][4];
 #pragma unroll
   for (int c = 0; c < MAXV; ++c)
 #pragma unroll
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
       bet[c][e] = col < f ? __ldg(beta + col) : 0.f;
       dg[c][e] = 0.f;
       db[c][e] = 0.f;
+      dl[c][e] = 0.f;
     }
   const float inv_f = 1.0f / (float)f;
   const int64_t stride = (int64_t)gridDim.x * ROW_WARPS;
@@ -207,6 +214,10 @@ __global__ void __launch_bounds__(ROW_THREADS)
           o.z = rs[u] * (a[c][2] - c1 - xh[c][2] * c2);
           o.w = rs[u] * (a[c][3] - c1 - xh[c][3] * c2);
           *reinterpret_cast<float4*>(dz + row * lddz + col) = o;
+          dl[c][0] += o.x;  // columns >= f carry a = xh = 0, i.e. o = -rs*c1: never read back (col < f below)
+          dl[c][1] += o.y;
+          dl[c][2] += o.z;
+          dl[c][3] += o.w;
         }
       }
     }
@@ -217,16 +228,17 @@ __global__ void __launch_bounds__(ROW_THREADS)
     for (int e = 0; e < 4; ++e) {
       const int col = 4 * (lane + 32 * c) + e;
       if (col < f) {
-        sm[(warp * 2 + 0) * f + col] = dg[c][e];
-        sm[(warp * 2 + 1) * f + col] = db[c][e];
+        sm[(warp * 3 + 0) * f + col] = dg[c][e];
+        sm[(warp * 3 + 1) * f + col] = db[c][e];
+        sm[(warp * 3 + 2) * f + col] = dl[c][e];
       }
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * f; i += ROW_THREADS) {
+  for (int i = threadIdx.x; i < 3 * f; i += ROW_THREADS) {
     const int which = i / f, col = i % f;
     float s = 0.f;
-    for (int w = 0; w < ROW_WARPS; ++w) s += sm[(w * 2 + which) * f + col];
-    partial[(int64_t)blockIdx.x * 2 * f + i] = s;
+    for (int w = 0; w < ROW_WARPS; ++w) s += sm[(w * 3 + which) * f + col];
+    partial[(int64_t)blockIdx.x * 3 * f + i] = s;
   }
 }
 
@@ -478,13 +490,13 @@ int gte_layernorm_act_fwd(const float* z, int64_t ldz, const float* gamma, const
 
 size_t gte_layernorm_act_bwd_workspace_bytes(int32_t n, int32_t f) {
   if (n < 0 || f <= 0) return 0;
-  return (size_t)ln_bwd_grid(n) * 2 * (size_t)f * 4 + 256;
+  return (size_t)ln_bwd_grid(n) * 3 * (size_t)f * 4 + 256;
 }
 
 int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* mean,
                           const float* rstd, const float* gamma, const float* beta, int relu, float* dz,
-                          int64_t lddz, float* dgamma, float* dbeta, int accumulate, int32_t n, int32_t f, void* ws,
-                          size_t ws_bytes, gte_stream_t stream) {
+                          int64_t lddz, float* dgamma, float* dbeta, float* dz_colsum, int accumulate, int32_t n,
+                          int32_t f, void* ws, size_t ws_bytes, gte_stream_t stream) {
   GTE_CHECK_ARG(n >= 0 && f > 0, "gte_layernorm_act_bwd: bad size");
   if (f > 1024) return fail(GTE_ERR_UNSUPPORTED, "gte_layernorm_act_bwd: f=%d > 1024 not supported", f);
   GTE_CHECK_ARG(dgamma && dbeta, "gte_layernorm_act_bwd: null dgamma/dbeta");
@@ -496,9 +508,9 @@ int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t
   cudaStream_t st = as_stream(stream);
   float* partial = static_cast<float*>(ws);
   const int grid = ln_bwd_grid(n);
-  const bool vec4 = aligned16(dy) && aligned16(z) && aligned16(dz) && lddy % 4 == 0 && ldz % 4 == 0 && lddz % 4 == 0 && f <= 512;
+  const bool vec4 = aligned16(dy) && aligned16(z) && aligned16(dz) && lddy % 4 == 0 && ldz % 4 == 0 && lddz % 4 == 0 && f <= 480;  // 8 warps x 3 x f floats of shared memory stay under 48 KB
   if (n > 0 && vec4) {
-    const size_t smem = (size_t)ROW_WARPS * 2 * f * 4;
+    const size_t smem = (size_t)ROW_WARPS * 3 * f * 4;
     const int nv = (f + 3) / 4;
     if (nv <= 32)
       k_layernorm_act_bwd_v4<1><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, beta, relu, dz, lddz, partial, n, f);
@@ -508,7 +520,7 @@ int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t
       k_layernorm_act_bwd_v4<4><<<grid, ROW_THREADS, smem, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, beta, relu, dz, lddz, partial, n, f);
     GTE_CHECK_LAUNCH("k_layernorm_act_bwd_v4");
   } else if (n > 0) {
-    const size_t smem = (size_t)ROW_WARPS * 2 * f * 4;
+    const size_t smem = (size_t)ROW_WARPS * 3 * f * 4;
     if (smem > 48 * 1024)
       GTE_CHECK_CUDA(cudaFuncSetAttribute(k_layernorm_act_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem),
@@ -519,11 +531,16 @@ int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t
     GTE_CHECK_LAUNCH("k_layernorm_act_bwd");
   }
   const int nb = n > 0 ? grid : 0;
-  k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial, nb, 2 * (int64_t)f, f, dgamma, accumulate);
+  k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial, nb, 3 * (int64_t)f, f, dgamma, accumulate);
   GTE_CHECK_LAUNCH("k_reduce_partials");
-  k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial + f, nb, 2 * (int64_t)f, f, dbeta,
+  k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial + f, nb, 3 * (int64_t)f, f, dbeta,
                                                                  accumulate);
   GTE_CHECK_LAUNCH("k_reduce_partials");
+  if (dz_colsum) {
+    k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial + 2 * f, nb, 3 * (int64_t)f, f, dz_colsum,
+                                                                   accumulate);
+    GTE_CHECK_LAUNCH("k_reduce_partials");
+  }
   return GTE_OK;
 }
 

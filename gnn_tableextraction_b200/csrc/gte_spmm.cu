@@ -178,8 +178,10 @@ static int launch_spmm(const int32_t* indptr, const int32_t* indices, const floa
 // load is left in the per-row loop, and the L2->SM gather traffic (4*E*F bytes, ~10x the compulsory
 // bytes at degree 10) disappears -- the kernel streams x in / y out at HBM rate.  Indices outside
 // the page window (not block diagonal) fall back to a global load, so the result is always correct.
+constexpr int PAGED_THREADS = 512;
+
 template <int G>
-__global__ void __launch_bounds__(SPMM_THREADS)
+__global__ void __launch_bounds__(PAGED_THREADS)
     k_spmm_paged(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ w,
                  const float* __restrict__ pre_scale, const float* __restrict__ row_norm, int mode,
                  const float* __restrict__ x, int64_t ldx, const float* __restrict__ addend, int64_t ldadd,
@@ -187,24 +189,27 @@ __global__ void __launch_bounds__(SPMM_THREADS)
                  int32_t np_cap, int32_t ne_cap) {
   extern __shared__ __align__(16) float smem_f[];
   constexpr int CS = G * 4;
-  constexpr int ROWS_PER_ITER = SPMM_THREADS / G;
-  float* sx = smem_f;                                                   // [np_cap][CS]
-  int32_t* s_idx = reinterpret_cast<int32_t*>(sx + (size_t)np_cap * CS);  // [ne_cap] page-local column ids
-  float* s_w = reinterpret_cast<float*>(s_idx + ne_cap);                // [ne_cap]
-  int32_t* s_ptr = reinterpret_cast<int32_t*>(s_w + ne_cap);            // [np_cap + 1] page-local row pointers
-  const int page = blockIdx.x;
-  const int c0 = blockIdx.y * CS;
+  constexpr int ROWS_PER_ITER = PAGED_THREADS / G;
+  float* sx = smem_f;                                                     // [np_cap][CS]
+  uint32_t* s_off = reinterpret_cast<uint32_t*>(sx + (size_t)np_cap * CS);  // [ne_cap] byte offset of the source row in sx
+  float* s_w = reinterpret_cast<float*>(s_off + ne_cap);                  // [ne_cap] edge weight (* source-side scale)
+  int32_t* s_ptr = reinterpret_cast<int32_t*>(s_w + ne_cap);              // [np_cap + 1] page-local row pointers
+  int32_t* s_flag = s_ptr + np_cap + 1;                                   // some edge needs the global slow path
+  // the slices of one page are adjacent in launch order (blockIdx.x fastest) so that cache lines shared
+  // by neighbouring slices are fetched from DRAM once
+  const int page = blockIdx.y;
+  const int c0 = blockIdx.x * CS;
   const int32_t n0 = page_off[page], n1 = page_off[page + 1];
   const int32_t np = n1 - n0;
   const int32_t e0 = indptr[n0];
   const int32_t ne = indptr[n1] - e0;
   const bool staged_edges = ne <= ne_cap;  // always true when the caller's max_page_edges is right
-  // x slice: 16-byte chunks; chunks entirely beyond f are zero-filled
-  for (int i = threadIdx.x; i < np * G; i += SPMM_THREADS) {
+  if (threadIdx.x == 0) *s_flag = staged_edges ? 0 : 1;
+  for (int i = threadIdx.x; i < np * G; i += PAGED_THREADS) {
     const int r = i / G, ch = i % G;
     const int col = c0 + ch * 4;
     float* dst = sx + (size_t)r * CS + ch * 4;
-    if (col < f) {
+    if (col < f) {  // 16-byte chunks; chunks entirely beyond f are zero-filled
       const float* src = x + (int64_t)(n0 + r) * ldx + col;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
                    : "memory");
@@ -213,14 +218,18 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = threadIdx.x; i <= np; i += SPMM_THREADS) s_ptr[i] = indptr[n0 + i] - e0;
+  for (int i = threadIdx.x; i <= np; i += PAGED_THREADS) s_ptr[i] = indptr[n0 + i] - e0;
+  __syncthreads();  // s_flag initialised before anyone raises it
   if (staged_edges) {
-    for (int i = threadIdx.x; i < ne; i += SPMM_THREADS) {
+    for (int i = threadIdx.x; i < ne; i += PAGED_THREADS) {
       const int32_t c = __ldg(indices + e0 + i);
       float wv = w ? __ldg(w + e0 + i) : 1.0f;
       if (pre_scale) wv *= __ldg(pre_scale + c);
-      s_idx[i] = c - n0;
-      s_w[i] = wv;
+      const int32_t sl = c - n0;
+      const bool inside = sl >= 0 && sl < np;
+      s_off[i] = inside ? (uint32_t)sl * (CS * 4) : 0u;
+      s_w[i] = inside ? wv : 0.f;  // outside edges contribute through the slow path below
+      if (!inside) *s_flag = 1;
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -230,6 +239,8 @@ __global__ void __launch_bounds__(SPMM_THREADS)
   const int grp = threadIdx.x / G;
   const int col = c0 + lane * 4;
   const bool on = col < f;
+  const bool slow = *s_flag != 0;
+  const char* xb = reinterpret_cast<const char*>(sx) + lane * 16;
   for (int32_t rl = grp; rl < np; rl += ROWS_PER_ITER) {
     const int64_t row = n0 + rl;
     const int32_t beg = s_ptr[rl], end = s_ptr[rl + 1];
@@ -238,29 +249,36 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     if (addend && on) av = __ldg(reinterpret_cast<const float4*>(addend + row * ldadd + col));
     const float nrm = (mode == GTE_AGG_SUM_NORM) ? __ldg(row_norm + row) : 1.0f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int32_t j = beg; j < end; ++j) {
-      int32_t sl;
-      float wt;
-      if (staged_edges) {
-        sl = s_idx[j];  // shared-memory broadcasts
-        wt = s_w[j];
-      } else {
+    if (staged_edges) {
+      int32_t j = beg;
+      for (; j + 4 <= end; j += 4) {  // edge order preserved: deterministic, same sums as the generic kernel
+        const uint32_t o0 = s_off[j], o1 = s_off[j + 1], o2 = s_off[j + 2], o3 = s_off[j + 3];
+        const float w0 = s_w[j], w1 = s_w[j + 1], w2 = s_w[j + 2], w3 = s_w[j + 3];
+        const float4 x0 = *reinterpret_cast<const float4*>(xb + o0);
+        const float4 x1 = *reinterpret_cast<const float4*>(xb + o1);
+        const float4 x2 = *reinterpret_cast<const float4*>(xb + o2);
+        const float4 x3 = *reinterpret_cast<const float4*>(xb + o3);
+        acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y); acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
+        acc.x = fmaf(w1, x1.x, acc.x); acc.y = fmaf(w1, x1.y, acc.y); acc.z = fmaf(w1, x1.z, acc.z); acc.w = fmaf(w1, x1.w, acc.w);
+        acc.x = fmaf(w2, x2.x, acc.x); acc.y = fmaf(w2, x2.y, acc.y); acc.z = fmaf(w2, x2.z, acc.z); acc.w = fmaf(w2, x2.w, acc.w);
+        acc.x = fmaf(w3, x3.x, acc.x); acc.y = fmaf(w3, x3.y, acc.y); acc.z = fmaf(w3, x3.z, acc.z); acc.w = fmaf(w3, x3.w, acc.w);
+      }
+      for (; j < end; ++j) {
+        const float wt = s_w[j];
+        const float4 xv = *reinterpret_cast<const float4*>(xb + s_off[j]);
+        acc.x = fmaf(wt, xv.x, acc.x); acc.y = fmaf(wt, xv.y, acc.y); acc.z = fmaf(wt, xv.z, acc.z); acc.w = fmaf(wt, xv.w, acc.w);
+      }
+    }
+    if (slow && on) {  // rare: the page table does not describe a block-diagonal graph (or edge capacity too small)
+      for (int32_t j = beg; j < end; ++j) {
         const int32_t c = __ldg(indices + e0 + j);
-        wt = w ? __ldg(w + e0 + j) : 1.0f;
+        const int32_t sl = c - n0;
+        if (staged_edges && sl >= 0 && sl < np) continue;  // already accumulated from shared memory
+        float wt = w ? __ldg(w + e0 + j) : 1.0f;
         if (pre_scale) wt *= __ldg(pre_scale + c);
-        sl = c - n0;
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c * ldx + col));
+        acc.x = fmaf(wt, xv.x, acc.x); acc.y = fmaf(wt, xv.y, acc.y); acc.z = fmaf(wt, xv.z, acc.z); acc.w = fmaf(wt, xv.w, acc.w);
       }
-      float4 xv;
-      if (sl >= 0 && sl < np) {
-        xv = *reinterpret_cast<const float4*>(sx + (size_t)sl * CS + lane * 4);
-      } else {
-        xv = on ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)(sl + n0) * ldx + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      acc.x = fmaf(wt, xv.x, acc.x);
-      acc.y = fmaf(wt, xv.y, acc.y);
-      acc.z = fmaf(wt, xv.z, acc.z);
-      acc.w = fmaf(wt, xv.w, acc.w);
     }
     if (!on) continue;
     if (mode == GTE_AGG_MEAN) {
@@ -278,7 +296,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 }
 
 static size_t paged_smem_bytes(int G, int32_t np_cap, int32_t ne_cap) {
-  return (size_t)np_cap * G * 16 + (size_t)ne_cap * 8 + ((size_t)np_cap + 1) * 4 + 16;
+  return (size_t)np_cap * G * 16 + (size_t)ne_cap * 8 + ((size_t)np_cap + 2) * 4 + 16;
 }
 
 template <int G>
@@ -294,8 +312,8 @@ static int launch_spmm_paged(const int32_t* indptr, const int32_t* indices, cons
                    "k_spmm_paged(smem attr)");
     configured = smem;
   }
-  dim3 grid((unsigned)num_pages, (unsigned)ceil_div64(f, CS));
-  k_spmm_paged<G><<<grid, SPMM_THREADS, smem, st>>>(indptr, indices, w, pre_scale, row_norm, mode, x, ldx, addend, ldadd, y,
+  dim3 grid((unsigned)ceil_div64(f, CS), (unsigned)num_pages);
+  k_spmm_paged<G><<<grid, PAGED_THREADS, smem, st>>>(indptr, indices, w, pre_scale, row_norm, mode, x, ldx, addend, ldadd, y,
                                                     ldy, page_off, f, np_cap, ne_cap);
   GTE_CHECK_LAUNCH("k_spmm_paged");
   return GTE_OK;

@@ -137,7 +137,10 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
     """Writes dW/db/dgamma/dbeta (overwrite or accumulate) and returns dh (or None)."""
     fin, fout = ctx.fin, ctx.fout
     if ctx.ln:
-        dz = ops.layernorm_act_bwd(dy, ctx.z, ctx.mean, ctx.rstd, gamma, beta, ctx.relu, dgamma, dbeta, accumulate)
+        # the linear-bias gradient (column sums of dz) falls out of the same pass
+        dz = ops.layernorm_act_bwd(dy, ctx.z, ctx.mean, ctx.rstd, gamma, beta, ctx.relu, dgamma, dbeta, accumulate,
+                                   dz_colsum=db)
+        db = None
     elif ctx.relu:
         dz = ops.relu_bwd(dy, ctx.z)
     else:

@@ -370,7 +370,8 @@ def layernorm_act_fwd(z, gamma, beta, eps: float, relu: bool, out=None):
     return out, mean, rstd
 
 
-def layernorm_act_bwd(dy, z, mean, rstd, gamma, beta, relu: bool, dgamma, dbeta, accumulate=False, out=None):
+def layernorm_act_bwd(dy, z, mean, rstd, gamma, beta, relu: bool, dgamma, dbeta, accumulate=False, out=None,
+                      dz_colsum=None):
     dyp, lddy, f = _mat(dy, "ln_bwd.dy")
     zp, ldz, _ = _mat(z, "ln_bwd.z")
     n = dy.shape[0]
@@ -383,7 +384,8 @@ def layernorm_act_bwd(dy, z, mean, rstd, gamma, beta, relu: bool, dgamma, dbeta,
     check(
         l.gte_layernorm_act_bwd(dyp, lddy, zp, ldz, _vec(mean, "mean", n=n), _vec(rstd, "rstd", n=n),
                                 _vec(gamma, "gamma", n=f), _vec(beta, "beta", n=f), 1 if relu else 0, dzp, lddz,
-                                _vec(dgamma, "dgamma", n=f), _vec(dbeta, "dbeta", n=f), 1 if accumulate else 0, n, f,
+                                _vec(dgamma, "dgamma", n=f), _vec(dbeta, "dbeta", n=f), _vec(dz_colsum, "dz_colsum", n=f),
+                                1 if accumulate else 0, n, f,
                                 ws.data_ptr(), ws.numel(), _stream()),
         "gte_layernorm_act_bwd",
     )

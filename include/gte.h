@@ -237,12 +237,13 @@ int gte_layernorm_act_fwd(const float* z, int64_t ldz, const float* gamma, const
                           float eps, int relu, float* y, int64_t ldy, float* mean, float* rstd,
                           int32_t n, int32_t f, gte_stream_t stream);
 size_t gte_layernorm_act_bwd_workspace_bytes(int32_t n, int32_t f);
-/* dz may alias dy.  dgamma/dbeta [f]: deterministic two-stage reduction. */
+/* dz may alias dy.  dgamma/dbeta [f]: deterministic two-stage reduction.  dz_colsum [f]
+ * (may be NULL) receives the column sums of dz = the gradient of the preceding nn.Linear's bias. */
 int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz,
                           const float* mean, const float* rstd, const float* gamma,
                           const float* beta, int relu, float* dz, int64_t lddz,
-                          float* dgamma, float* dbeta, int accumulate, int32_t n, int32_t f,
-                          void* ws, size_t ws_bytes, gte_stream_t stream);
+                          float* dgamma, float* dbeta, float* dz_colsum, int accumulate,
+                          int32_t n, int32_t f, void* ws, size_t ws_bytes, gte_stream_t stream);
 
 /* y = normalize(relu(z)) : F.relu + F.normalize(p=2, dim=1, eps) (models.py:168-169) */
 int gte_relu_l2norm_fwd(const float* z, int64_t ldz, float eps, float* y, int64_t ldy,

@@ -249,8 +249,11 @@ def test_layernorm_act(n, f, relu):
     assert rel_err(yd, y) < 2e-6
     dg = torch.empty(f, device=DEV)
     dbt = torch.empty(f, device=DEV)
-    dz = ops.layernorm_act_bwd(_padded(up), zd, mean, rstd, gamma.detach().to(DEV), beta.detach().to(DEV), relu, dg, dbt)
+    dcs = torch.empty(f, device=DEV)
+    dz = ops.layernorm_act_bwd(_padded(up), zd, mean, rstd, gamma.detach().to(DEV), beta.detach().to(DEV), relu, dg, dbt,
+                               dz_colsum=dcs)
     assert rel_err(dz, z.grad) < 5e-6
+    assert (dcs.double().cpu() - z.grad.double().sum(0)).abs().max() < 5e-6 * max(1.0, z.grad.abs().sum(0).max().item())
     assert rel_err(dg, gamma.grad) < 5e-6 and rel_err(dbt, beta.grad) < 5e-6
     dg2 = torch.empty(f, device=DEV)
     dz2 = ops.layernorm_act_bwd(_padded(up), zd, mean, rstd, gamma.detach().to(DEV), beta.detach().to(DEV), relu, dg2,
