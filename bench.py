@@ -121,7 +121,7 @@ class OpTimer:
 
     NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
-             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2"]
+             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2"]
 
     def __init__(self, ops, torch):
         self.ops, self.torch, self.rec, self.orig = ops, torch, [], {}
@@ -135,7 +135,9 @@ class OpTimer:
             return (name, int(a[0].shape[0]), int(k), int(a[2].shape[0]))
         if name == "linear_bwd_data":
             return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(a[3]))
-        if name == "linear_bwd_weight":
+        if name == "umma_linear_bwd_weight2":
+            return (name, int(a[0].shape[0]), 2 * int(a[0].shape[1]), int(a[2].shape[1]))
+        if name in ("linear_bwd_weight", "umma_linear_bwd_weight"):
             k = a[1].shape[1] + (a[2].shape[1] if a[2] is not None else 0)
             return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(k))
         if name in ("layernorm_act_fwd", "layernorm_act_bwd"):
@@ -197,7 +199,7 @@ def op_cost(key):
     if n in ("linear_bwd_data", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2"):
         _, N, Fo, K = key
         return 4 * N * Fo + 4 * N * K + 4 * K * Fo, 2 * N * K * Fo
-    if n == "linear_bwd_weight":
+    if n in ("linear_bwd_weight", "umma_linear_bwd_weight", "umma_linear_bwd_weight2"):
         _, N, Fo, K = key
         return 4 * N * Fo + 4 * N * K + 4 * K * Fo, 2 * N * K * Fo
     if n == "layernorm_act_fwd":

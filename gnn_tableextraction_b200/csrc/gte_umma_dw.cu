@@ -1,0 +1,519 @@
+// Weight gradients on the tensor cores: dW = dz^T [x1 | x2] (and the transposed, narrow-dz form of
+// the class layer), the reduction over all N nodes of the batch.
+//
+//     out[m, j] = sum_r A[r, m] * B[r, j]          A: [n, M<=256]   B: boxes of 32 columns from up to 3 tensors
+//
+// Both operands are activations stored row-major [node, feature], i.e. "MN-major" for the MMA
+// (the contraction index r is the slow axis), which tcgen05.mma kind::tf32 consumes directly through
+// MN-major SWIZZLE_128B_BASE32B shared-memory descriptors -- no transposes are materialised.  TMA loads
+// [32 rows x 32 floats] boxes; a 128-row A tile is 4 boxes, a B tile up to 8 boxes (N <= 256).
+// 3xTF32 split as in gte_umma.cu (both operands are split in shared memory by the transform warps:
+// hi = rna(x), lo = rna(x - hi)); the small cross terms (a_lo*b_hi + a_hi*b_lo) accumulate in
+// their own TMEM accumulator so that the long main chain sees as few round-toward-zero steps as possible.
+//
+// Rows are processed in chunks (512 rows = 64 MMA K-steps per accumulator) whose fp32 partial
+// tiles are written to a workspace and summed afterwards in a fixed order -- deterministic, no
+// atomics, and the in-TMEM chain stays short (tensor-core accumulation truncates).
+// An all-ones column (B side) or row (A side) can be injected to obtain column sums (bias gradient)
+// from the same pass.
+//
+// Roofline: HBM (each activation byte is read once per use) -- the MMA work is 3*2*n*M*N flops.
+#include "gte_common.cuh"
+#include "gte_umma_ptx.cuh"
+
+#include <stdlib.h>
+
+namespace gte {
+
+constexpr int DW_THREADS = 384;
+constexpr int DW_KB = 32;                      // contraction rows per pipeline stage
+constexpr int DW_BOX_BYTES = DW_KB * 128;      // one TMA box: 32 rows x 32 floats
+constexpr int DW_STAGES = 2;
+constexpr int DW_MAX_BOXES = 8;
+constexpr int DW_STAGE_LD = 33;
+
+struct DwBox {
+  int32_t map;  // index into tmB
+  int32_t col;  // first column of the box in that tensor
+};
+struct DwGroup {
+  int32_t a;       // index into tmA
+  int32_t nboxes;  // N = 32 * nboxes
+  DwBox box[DW_MAX_BOXES];
+  int32_t pcol0;   // first column of this group's tile in the partial matrix
+  int32_t ones_b_col;  // >= 0: tile column of B forced to 1 (column sums of A); -1: none
+  int32_t ones_a_col;  // >= 0: column of A forced to 1 (column sums of B); -1: none
+};
+struct DwArgs {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[3];
+  DwGroup grp[2];
+  int32_t item_g[4], item_mt[4];  // (group, m-tile) pairs processed per row chunk
+  int32_t items_per_chunk;
+  int32_t n, chunk_rows, nchunks;
+  int32_t max_boxes;
+  float* partial;
+  int64_t ldp, chunk_stride;
+  int32_t dbg_lbo, dbg_sbo;  // descriptor experiment (GTE_DW_DESC)
+  int32_t dbg_mode;
+};
+
+__global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant__ DwArgs P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = 4 * DW_BOX_BYTES;
+  const int b_bytes = P.max_boxes * DW_BOX_BYTES;
+  const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint8_t* const tiles = base;
+  auto sA_hi = [&](int s) { return tiles + s * stage_bytes; };
+  auto sA_lo = [&](int s) { return tiles + s * stage_bytes + a_bytes; };
+  auto sB_hi = [&](int s) { return tiles + s * stage_bytes + 2 * a_bytes; };
+  auto sB_lo = [&](int s) { return tiles + s * stage_bytes + 2 * a_bytes + b_bytes; };
+  float* s_stage = reinterpret_cast<float*>(tiles + DW_STAGES * stage_bytes);  // [4][32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * 32 * DW_STAGE_LD);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_ready = bars + DW_STAGES;
+  uint64_t* bar_empty = bars + 2 * DW_STAGES;
+  uint64_t* bar_tfull = bars + 3 * DW_STAGES;
+  uint64_t* bar_tempty = bar_tfull + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_items = P.nchunks * P.items_per_chunk;
+  const int kb_per_chunk = P.chunk_rows / DW_KB;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < DW_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_ready[s]), 128);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(bar_tfull), 1);
+    mbar_init(smem_u32(bar_tempty), 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&P.tmA[0]);
+    tma_prefetch_desc(&P.tmB[0]);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  // number of K blocks of a chunk that contain at least one real row
+  auto chunk_kblocks = [&](int chunk) {
+    const int r0 = chunk * P.chunk_rows;
+    const int rows = min(P.chunk_rows, P.n - r0);
+    const int kb = (rows + DW_KB - 1) / DW_KB;
+    return kb < 1 ? 1 : (kb > kb_per_chunk ? kb_per_chunk : kb);
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
+        const DwGroup& G = P.grp[P.item_g[sub]];
+        const int mt = P.item_mt[sub];
+        const int r0 = chunk * P.chunk_rows;
+        const int nkb = chunk_kblocks(chunk);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&bar_full[stage]);
+          mbar_expect_tx(fb, (uint32_t)((4 + G.nboxes) * DW_BOX_BYTES));
+          const int row = r0 + kb * DW_KB;
+          for (int b = 0; b < 4; ++b)
+            tma_load_2d(smem_u32(sA_hi(stage) + b * DW_BOX_BYTES), &P.tmA[G.a], fb, mt * 128 + b * 32, row);
+          for (int b = 0; b < G.nboxes; ++b)
+            tma_load_2d(smem_u32(sB_hi(stage) + b * DW_BOX_BYTES), &P.tmB[G.box[b].map], fb, G.box[b].col, row);
+          if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
+        const DwGroup& G = P.grp[P.item_g[sub]];
+        const int BN = G.nboxes * 32;
+        // D=f32, A=B=tf32, both MN-major, N=BN, M=128
+        uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        if (P.dbg_mode == 13) idesc &= ~((1u << 15) | (1u << 16));
+        mbar_wait(smem_u32(bar_tempty), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base, d_cross = tmem_base + 256;
+        const int nkb = chunk_kblocks(chunk);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          mbar_wait(smem_u32(&bar_ready[stage]), phase);
+          tc_fence_after();
+          const uint64_t dah = make_desc_mn_sw128_32b(smem_u32(sA_hi(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
+          const uint64_t dal = make_desc_mn_sw128_32b(smem_u32(sA_lo(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
+          const uint64_t dbh = make_desc_mn_sw128_32b(smem_u32(sB_hi(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
+          const uint64_t dbl = make_desc_mn_sw128_32b(smem_u32(sB_lo(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
+#pragma unroll
+          for (int k = 0; k < DW_KB / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 1024) >> 4);  // next 8-row atom inside every box
+            const uint32_t first = (kb | k) == 0 ? 0u : 1u;
+            umma_tf32(d_cross, dal + adv, dbh + adv, idesc, first);
+            umma_tf32(d_cross, dah + adv, dbl + adv, idesc, 1u);
+            umma_tf32(d_main, dah + adv, dbh + adv, idesc, first);
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(bar_tfull));
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================ operand split ===============================
+    const int t = threadIdx.x - 128;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
+      const DwGroup& G = P.grp[P.item_g[sub]];
+      const int mt = P.item_mt[sub];
+      const int r0 = chunk * P.chunk_rows;
+      const int nkb = chunk_kblocks(chunk);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        auto split = [&](uint8_t* hi_p, uint8_t* lo_p, int nf4) {
+          float4* hi = reinterpret_cast<float4*>(hi_p);
+          float4* lo = reinterpret_cast<float4*>(lo_p);
+          for (int idx = t; idx < nf4; idx += 128) {
+            const float4 v = hi[idx];
+            float4 h, l;
+            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+            hi[idx] = h;
+            lo[idx] = l;
+          }
+        };
+        split(sA_hi(stage), sA_lo(stage), 4 * DW_BOX_BYTES / 16);
+        split(sB_hi(stage), sB_lo(stage), G.nboxes * DW_BOX_BYTES / 16);
+        // all-ones column: element (row kk, tile column c) of an MN-major SW128 box tile
+        const int ones_col = G.ones_b_col >= 0 ? G.ones_b_col : ((G.ones_a_col >= 0 && G.ones_a_col / 128 == mt) ? G.ones_a_col % 128 : -1);
+        if (ones_col >= 0) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // the splits above wrote the same words
+          if (t < DW_KB) {
+            const int kk = t;
+            if (r0 + kb * DW_KB + kk < P.n) {
+              uint8_t* tile = G.ones_b_col >= 0 ? sB_hi(stage) : sA_hi(stage);
+              const int box = ones_col / 32, cin = ones_col % 32;
+              const int off = box * DW_BOX_BYTES + kk * 128 + (((cin >> 3) ^ (kk & 3)) << 5) + (cin & 7) * 4;  // 32-byte chunk swizzle
+              *reinterpret_cast<float*>(tile + off) = 1.0f;
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&bar_ready[stage]));
+        if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;
+    float* st = s_stage + q * 32 * DW_STAGE_LD;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
+      const DwGroup& G = P.grp[P.item_g[sub]];
+      const int mt = P.item_mt[sub];
+      mbar_wait(smem_u32(bar_tfull), acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      float* outp = P.partial + (int64_t)chunk * P.chunk_stride + (int64_t)(mt * 128 + q * 32) * P.ldp + G.pcol0;
+      for (int c = 0; c < G.nboxes; ++c) {
+        uint32_t v[32], v2[32];
+        tmem_ld_32x32b_x32(t_base + c * 32, v);
+        tmem_ld_32x32b_x32(t_base + 256 + c * 32, v2);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float val = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+          if (P.dbg_mode == 10) val = 1.0f;
+          if (P.dbg_mode == 11) val = __uint_as_float(v[j]);
+          if (P.dbg_mode == 12) val = __uint_as_float(v2[j]);
+          st[lane * DW_STAGE_LD + j] = val;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) outp[(int64_t)rr * P.ldp + c * 32 + lane] = st[rr * DW_STAGE_LD + lane];
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(bar_tempty));
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- fixed-order reduction of the chunk partials into up to four rectangular destinations -------------------
+struct DwSeg {
+  int32_t prow0, nrows, pcol0, ncols;  // rectangle of the partial matrix
+  float* dst;
+  int64_t stride_row, stride_col;      // dst[row*stride_row + col*stride_col]
+};
+struct DwReduceArgs {
+  DwSeg seg[4];
+  int32_t nseg;
+  const float* partial;
+  int64_t ldp, chunk_stride;
+  int32_t nchunks, accumulate;
+};
+
+__global__ void __launch_bounds__(RED_THREADS) k_umma_dw_reduce(const DwReduceArgs R) {
+  __shared__ float red[RED_THREADS];
+  int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  int s = 0;
+  bool valid = false;
+  for (; s < R.nseg; ++s) {
+    const int64_t cnt = (int64_t)R.seg[s].nrows * R.seg[s].ncols;
+    if (i < cnt) {
+      valid = true;
+      break;
+    }
+    i -= cnt;
+  }
+  int row = 0, col = 0;
+  int64_t pidx = 0;
+  if (valid) {
+    row = (int)(i / R.seg[s].ncols);
+    col = (int)(i % R.seg[s].ncols);
+    pidx = (int64_t)(R.seg[s].prow0 + row) * R.ldp + R.seg[s].pcol0 + col;
+  }
+  float v = reduce_partials_block(R.partial, R.nchunks, R.chunk_stride, pidx, valid, red);
+  if ((threadIdx.x >> 5) != 0 || !valid) return;
+  float* p = R.seg[s].dst + row * R.seg[s].stride_row + col * R.seg[s].stride_col;
+  if (R.accumulate) v += *p;
+  *p = v;
+}
+
+constexpr int DW_CHUNK_ROWS = 512;
+
+static size_t dw_smem_bytes(int max_boxes) {
+  return 1024 + (size_t)DW_STAGES * (2 * 4 * DW_BOX_BYTES + 2 * (size_t)max_boxes * DW_BOX_BYTES) + 4 * 32 * DW_STAGE_LD * 4 +
+         (3 * DW_STAGES + 2) * 8 + 16;
+}
+
+static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
+  const size_t smem = dw_smem_bytes(a.max_boxes);
+  static size_t configured = 0;
+  if (smem > configured) {
+    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "k_umma_dw(smem attr)");
+    configured = smem;
+  }
+  a.dbg_lbo = DW_BOX_BYTES;
+  a.dbg_sbo = 512;
+  a.dbg_mode = 0;
+  if (const char* e = getenv("GTE_DW_MODE")) a.dbg_mode = atoi(e);
+  if (const char* e = getenv("GTE_DW_DESC")) {
+    if (atoi(e) == 1) { a.dbg_lbo = 512; a.dbg_sbo = DW_BOX_BYTES; }
+    if (atoi(e) == 2) { a.dbg_lbo = DW_BOX_BYTES; a.dbg_sbo = DW_BOX_BYTES; }
+    if (atoi(e) == 3) { a.dbg_lbo = DW_BOX_BYTES; a.dbg_sbo = 1024; }
+  }
+  const int items = a.nchunks * a.items_per_chunk;
+  int grid = sm_count();
+  if (grid > items) grid = items;
+  if (grid >= 1) {
+    k_umma_dw<<<grid, DW_THREADS, smem, st>>>(a);
+    GTE_CHECK_LAUNCH("k_umma_dw");
+  }
+  int64_t total = 0;
+  for (int s = 0; s < r.nseg; ++s) total += (int64_t)r.seg[s].nrows * r.seg[s].ncols;
+  if (total > 0) {
+    k_umma_dw_reduce<<<(unsigned)ceil_div64(total, 32), RED_THREADS, 0, st>>>(r);
+    GTE_CHECK_LAUNCH("k_umma_dw_reduce");
+  }
+  return GTE_OK;
+}
+
+static int boxes_of(int k) { return (k + 31) / 32; }
+
+static bool tma_ok(const float* p, int64_t ld) { return p == nullptr || (aligned16(p) && ld % 4 == 0); }
+
+}  // namespace gte
+
+using namespace gte;
+
+extern "C" {
+
+// dW[:, 0:k1] (+)= dz^T x1 ; dW[:, k1:k1+k2] (+)= dz^T x2 ; db (+)= colsum(dz) when a padding column is free.
+int gte_umma_bwd_weight_supported(int32_t fo, int32_t k1, int32_t k2) {
+  return (fo >= 1 && fo <= 256 && k1 >= 1 && k1 <= 256 && k2 >= 0 && k2 <= 256) ? 1 : 0;
+}
+
+size_t gte_umma_bwd_weight_workspace_bytes(int32_t n, int32_t fo, int32_t k1, int32_t k2) {
+  if (!gte_umma_bwd_weight_supported(fo, k1, k2) || n < 0) return 0;
+  const int64_t nchunks = ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS);
+  const int64_t rows = ceil_div64(fo, 128) * 128;
+  const int64_t ldp = 32 * (boxes_of(k1) + boxes_of(k2));
+  return (size_t)(nchunks * rows * ldp * 4 + 256);
+}
+
+int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const float* x1, int64_t ldx1, int32_t k1,
+                               const float* x2, int64_t ldx2, int32_t k2, float* dW, int64_t lddw, float* db,
+                               int accumulate, int32_t n, void* ws, size_t ws_bytes, gte_stream_t stream) {
+  if (!gte_umma_bwd_weight_supported(fo, k1, k2))
+    return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight: fo=%d k1=%d k2=%d unsupported", fo, k1, k2);
+  GTE_CHECK_ARG(n >= 0 && dW && (n == 0 || (dz && x1 && (k2 == 0 || x2))), "gte_umma_linear_bwd_weight: bad argument");
+  GTE_CHECK_ARG(tma_ok(dz, lddz) && tma_ok(x1, ldx1) && (k2 == 0 || tma_ok(x2, ldx2)),
+                "gte_umma_linear_bwd_weight: operands must be 16-byte aligned with ld %% 4 == 0");
+  GTE_CHECK_ARG(lddz >= fo && ldx1 >= k1 && (k2 == 0 || ldx2 >= k2) && lddw >= (int64_t)k1 + k2,
+                "gte_umma_linear_bwd_weight: leading dimension too small");
+  const size_t need = gte_umma_bwd_weight_workspace_bytes(n, fo, k1, k2);
+  if (ws == nullptr || ws_bytes < need)
+    return fail(GTE_ERR_WORKSPACE, "gte_umma_linear_bwd_weight: workspace %zu < required %zu", ws_bytes, need);
+  const int nb1 = boxes_of(k1), nb2 = boxes_of(k2);
+  DwArgs a{};
+  DwReduceArgs r{};
+  a.n = n;
+  a.chunk_rows = DW_CHUNK_ROWS;
+  a.nchunks = (int)ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS);
+  const int mtiles = (fo + 127) / 128;
+  a.ldp = 32 * (nb1 + nb2);
+  a.chunk_stride = (int64_t)mtiles * 128 * a.ldp;
+  a.partial = static_cast<float*>(ws);
+  if (n > 0) {
+    int rc = make_tmap_2d(&a.tmA[0], dz, n, fo, lddz, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_tmap_2d(&a.tmB[0], x1, n, k1, ldx1, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    if (k2 > 0) {
+      rc = make_tmap_2d(&a.tmB[1], x2, n, k2, ldx2, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      if (rc) return rc;
+    }
+  }
+  // one group when all boxes fit one accumulator (N <= 256), otherwise one group per input segment
+  const bool one_group = nb1 + nb2 <= DW_MAX_BOXES;
+  int ngroups = 0;
+  auto add_boxes = [&](DwGroup& G, int map, int nb) {
+    for (int b = 0; b < nb; ++b) G.box[G.nboxes++] = DwBox{map, b * 32};
+  };
+  DwGroup& G0 = a.grp[0];
+  G0.a = 0; G0.nboxes = 0; G0.pcol0 = 0; G0.ones_b_col = -1; G0.ones_a_col = -1;
+  add_boxes(G0, 0, nb1);
+  ngroups = 1;
+  if (k2 > 0) {
+    if (one_group) {
+      add_boxes(G0, 1, nb2);
+    } else {
+      DwGroup& G1 = a.grp[1];
+      G1.a = 0; G1.nboxes = 0; G1.pcol0 = 32 * nb1; G1.ones_b_col = -1; G1.ones_a_col = -1;
+      add_boxes(G1, 1, nb2);
+      ngroups = 2;
+    }
+  }
+  // bias gradient: a free padding column of the first segment carries the all-ones column
+  bool db_fused = false;
+  if (db && k1 % 32 != 0) {
+    G0.ones_b_col = k1;
+    db_fused = true;
+  }
+  a.max_boxes = 0;
+  a.items_per_chunk = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    if (a.grp[g].nboxes > a.max_boxes) a.max_boxes = a.grp[g].nboxes;
+    for (int mt = 0; mt < mtiles; ++mt) {
+      a.item_g[a.items_per_chunk] = g;
+      a.item_mt[a.items_per_chunk] = mt;
+      ++a.items_per_chunk;
+    }
+  }
+  r.partial = a.partial;
+  r.ldp = a.ldp;
+  r.chunk_stride = a.chunk_stride;
+  r.nchunks = n > 0 ? a.nchunks : 0;
+  r.accumulate = accumulate;
+  r.nseg = 0;
+  r.seg[r.nseg++] = DwSeg{0, fo, 0, k1, dW, lddw, 1};
+  if (k2 > 0) r.seg[r.nseg++] = DwSeg{0, fo, 32 * nb1, k2, dW + k1, lddw, 1};
+  if (db_fused) r.seg[r.nseg++] = DwSeg{0, fo, k1, 1, db, 1, 0};
+  if (n == 0) a.nchunks = 0;
+  int rc = dw_launch(a, r, as_stream(stream));
+  if (rc) return rc;
+  if (db && !db_fused) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight: db needs k1 %% 32 != 0 (no free padding column)");
+  return GTE_OK;
+}
+
+// Narrow-dz form (class layer, project-then-aggregate): A = x [n, k<=256], B = [dz1 | dz2] (fo <= 32 each)
+//   dW[:, col1:col1+k] (+)= dz1^T x ; dW[:, col2:col2+k] (+)= dz2^T x ; db (+)= colsum(dz1)
+size_t gte_umma_bwd_weight2_workspace_bytes(int32_t n, int32_t fo, int32_t k) {
+  if (n < 0 || fo < 1 || fo > 32 || k < 1 || k > 256) return 0;
+  const int64_t nchunks = ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS);
+  const int64_t rows = ceil_div64(k + 1, 128) * 128;
+  return (size_t)(nchunks * rows * 64 * 4 + 256);
+}
+
+int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz2, int64_t lddz2, int32_t fo,
+                                const float* x, int64_t ldx, int32_t k, float* dW, int64_t lddw, int32_t col1,
+                                int32_t col2, float* db, int accumulate, int32_t n, void* ws, size_t ws_bytes,
+                                gte_stream_t stream) {
+  if (fo < 1 || fo > 32 || k < 1 || k > 256)
+    return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight2: fo=%d k=%d unsupported", fo, k);
+  GTE_CHECK_ARG(n >= 0 && dW && (n == 0 || (dz1 && dz2 && x)), "gte_umma_linear_bwd_weight2: bad argument");
+  GTE_CHECK_ARG(tma_ok(dz1, lddz1) && tma_ok(dz2, lddz2) && tma_ok(x, ldx),
+                "gte_umma_linear_bwd_weight2: operands must be 16-byte aligned with ld %% 4 == 0");
+  GTE_CHECK_ARG(lddz1 >= fo && lddz2 >= fo && ldx >= k && lddw >= (int64_t)col1 + k && lddw >= (int64_t)col2 + k,
+                "gte_umma_linear_bwd_weight2: leading dimension too small");
+  const size_t need = gte_umma_bwd_weight2_workspace_bytes(n, fo, k);
+  if (ws == nullptr || ws_bytes < need)
+    return fail(GTE_ERR_WORKSPACE, "gte_umma_linear_bwd_weight2: workspace %zu < required %zu", ws_bytes, need);
+  const bool db_fused = db != nullptr && (k % 128 != 0);
+  if (db && !db_fused) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight2: db needs k %% 128 != 0");
+  DwArgs a{};
+  DwReduceArgs r{};
+  a.n = n;
+  a.chunk_rows = DW_CHUNK_ROWS;
+  a.nchunks = (int)ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS);
+  const int mtiles = (k + (db_fused ? 1 : 0) + 127) / 128;
+  a.ldp = 64;
+  a.chunk_stride = (int64_t)mtiles * 128 * a.ldp;
+  a.partial = static_cast<float*>(ws);
+  if (n > 0) {
+    int rc = make_tmap_2d(&a.tmA[0], x, n, k, ldx, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_tmap_2d(&a.tmB[0], dz1, n, fo, lddz1, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_tmap_2d(&a.tmB[1], dz2, n, fo, lddz2, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  DwGroup& G = a.grp[0];
+  G.a = 0; G.nboxes = 2; G.pcol0 = 0; G.ones_b_col = -1; G.ones_a_col = db_fused ? k : -1;
+  G.box[0] = DwBox{0, 0};
+  G.box[1] = DwBox{1, 0};
+  a.max_boxes = 2;
+  a.items_per_chunk = 0;
+  for (int mt = 0; mt < mtiles; ++mt) {
+    a.item_g[a.items_per_chunk] = 0;
+    a.item_mt[a.items_per_chunk] = mt;
+    ++a.items_per_chunk;
+  }
+  r.partial = a.partial;
+  r.ldp = a.ldp;
+  r.chunk_stride = a.chunk_stride;
+  r.nchunks = n > 0 ? a.nchunks : 0;
+  r.accumulate = accumulate;
+  r.nseg = 0;
+  r.seg[r.nseg++] = DwSeg{0, k, 0, fo, dW + col1, 1, lddw};   // out[j][o] -> dW[o][col1 + j]
+  r.seg[r.nseg++] = DwSeg{0, k, 32, fo, dW + col2, 1, lddw};
+  if (db_fused) r.seg[r.nseg++] = DwSeg{k, 1, 0, fo, db, 0, 1};  // ones row: column sums of dz1
+  if (n == 0) a.nchunks = 0;
+  return dw_launch(a, r, as_stream(stream));
+}
+
+}  // extern "C"

@@ -70,6 +70,17 @@ def use_umma(n: int, fin: int, fout: int, *mats) -> bool:
     return n >= UMMA_MIN_ROWS and fin >= UMMA_MIN_WIDTH and fout >= UMMA_MIN_WIDTH
 
 
+def use_umma_dw(n: int, fo: int, k1: int, k2: int, db_needed: bool, *mats) -> bool:
+    """Tensor-core weight gradient: any width up to 256 (the reduction over all nodes is the long axis)."""
+    if GEMM_MODE == "ffma" or not ops.umma_bwd_weight_supported(fo, k1, k2):
+        return False
+    if not all(ops._aligned_mat(m) for m in mats if m is not None):
+        return False
+    if db_needed and k1 % 32 == 0:
+        return False
+    return GEMM_MODE == "umma" or n >= UMMA_MIN_ROWS
+
+
 def _agg_mode(agg: str) -> int:
     return _lib.GTE_AGG_SUM_NORM if agg == GCN else _lib.GTE_AGG_MEAN
 
@@ -100,6 +111,11 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
     if h.shape[1] != (W.shape[1] if use_pp else fin):
         raise _lib.GteError(f"layer expects {W.shape[1] if use_pp else fin} input features, got {h.shape[1]}")
     st = strategy or pick_strategy(fin, fout, use_pp)
+    if GEMM_MODE != "ffma" and h.shape[0] >= UMMA_MIN_ROWS and not ops._aligned_mat(h):
+        # e.g. the raw [N, 13] BBOX features: one padded copy gives 16-byte aligned rows for TMA / 128-bit loads
+        hp = ops.empty_padded(h.shape[0], h.shape[1], h.device)
+        hp.copy_(h)
+        h = hp
     ctx = LayerCtx(strategy=st, agg=agg, h=h, ln=ln, relu=relu, fin=fin, fout=fout, w_edge=w_edge)
     if st == "pp":  # pre-propagated input: plain linear (models.py:49)
         z = ops.linear_fwd(h, None, W, b)
@@ -149,7 +165,10 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
         ops.linear_bwd_weight(dz, ctx.h, None, dW, db, accumulate)
         return ops.linear_bwd_data(dz, W, 0, W.shape[1]) if need_dh else None
     if ctx.strategy == "agg":
-        ops.linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
+        if use_umma_dw(dz.shape[0], fout, fin, fin, db is not None, dz, ctx.h, ctx.ah):
+            ops.umma_linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
+        else:
+            ops.linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
         if not need_dh:
             return None
         if ctx.pack is not None and ops._aligned_mat(dz):
@@ -161,7 +180,12 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
     # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
     #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn
     gq = aggregate_backward(g, dz, ctx.w_edge)
-    ops.linear_bwd_weight2(dz, gq, ctx.h, dW, 0, fin, db, accumulate)
+    if (GEMM_MODE != "ffma" and fout <= 32 and fin <= 256 and (db is None or fin % 128 != 0) and
+            (GEMM_MODE == "umma" or dz.shape[0] >= UMMA_MIN_ROWS) and
+            all(ops._aligned_mat(m) for m in (dz, gq, ctx.h))):
+        ops.umma_linear_bwd_weight2(dz, gq, ctx.h, dW, 0, fin, db, accumulate)
+    else:
+        ops.linear_bwd_weight2(dz, gq, ctx.h, dW, 0, fin, db, accumulate)
     if not need_dh:
         return None
     return ops.linear_bwd_data2(dz, 0, gq, fin, W, fin)

@@ -353,6 +353,48 @@ def umma_linear_bwd_data(dz, pack, fin: int, nseg: int):
     return dx1, dx2
 
 
+def umma_bwd_weight_supported(fo: int, k1: int, k2: int) -> bool:
+    return bool(lib().gte_umma_bwd_weight_supported(fo, k1, k2))
+
+
+def umma_linear_bwd_weight(dz, x1, x2, dW, db, accumulate=False, w_col0: int = 0):
+    """Tensor-core dW[:, c0:c0+k1+k2] (+)= dz^T [x1 | x2]; db (+)= colsum(dz) (needs k1 % 32 != 0)."""
+    dzp, lddz, fo = _mat(dz, "umma_dw.dz")
+    n = dz.shape[0]
+    x1p, ld1, k1 = _mat(x1, "umma_dw.x1")
+    x2p, ld2, k2 = (None, 0, 0)
+    if x2 is not None:
+        x2p, ld2, k2 = _mat(x2, "umma_dw.x2")
+    dWp, lddw, kw = _mat(dW, "umma_dw.dW")
+    if dW.shape[0] != fo or w_col0 + k1 + k2 > kw:
+        raise GteError("umma_linear_bwd_weight: dW shape mismatch")
+    l = lib()
+    ws = workspace(l.gte_umma_bwd_weight_workspace_bytes(n, fo, k1, k2), dz.device)
+    check(
+        l.gte_umma_linear_bwd_weight(dzp, lddz, fo, x1p, ld1, k1, x2p, ld2, k2, dWp + 4 * w_col0, lddw, _vec(db, "db", n=fo),
+                                     1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),
+        "gte_umma_linear_bwd_weight",
+    )
+
+
+def umma_linear_bwd_weight2(dz1, dz2, x, dW, col1: int, col2: int, db, accumulate=False):
+    """Tensor-core narrow-dz form: dW[:, col1:+k] (+)= dz1^T x ; dW[:, col2:+k] (+)= dz2^T x ; db (+)= colsum(dz1)."""
+    d1p, ld1, fo = _mat(dz1, "umma_dw2.dz1")
+    d2p, ld2, fo2 = _mat(dz2, "umma_dw2.dz2")
+    xp, ldx, k = _mat(x, "umma_dw2.x")
+    dWp, lddw, kw = _mat(dW, "umma_dw2.dW")
+    n = dz1.shape[0]
+    if fo2 != fo or dW.shape[0] != fo or max(col1, col2) + k > kw or dz2.shape[0] != n or x.shape[0] != n:
+        raise GteError("umma_linear_bwd_weight2: shape mismatch")
+    l = lib()
+    ws = workspace(l.gte_umma_bwd_weight2_workspace_bytes(n, fo, k), dz1.device)
+    check(
+        l.gte_umma_linear_bwd_weight2(d1p, ld1, d2p, ld2, fo, xp, ldx, k, dWp, lddw, col1, col2, _vec(db, "db", n=fo),
+                                      1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),
+        "gte_umma_linear_bwd_weight2",
+    )
+
+
 # ---------------------------------------------------------------- row ops ---
 def layernorm_act_fwd(z, gamma, beta, eps: float, relu: bool, out=None):
     zp, ldz, f = _mat(z, "ln.z")

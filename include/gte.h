@@ -227,6 +227,26 @@ int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const fl
                              float* dx1, int64_t lddx1, float* dx2, int64_t lddx2, int32_t n, int32_t fin,
                              gte_stream_t stream);
 
+/*
+ * Weight gradients on the tensor cores (MN-major tcgen05.mma operands straight from the row-major
+ * activations, 3xTF32, row chunks reduced in fixed order).  Same results contract as
+ * gte_linear_bwd_weight / gte_linear_bwd_weight2; fo, k1, k2 <= 256 (fo <= 32 for the *2 form);
+ * operands 16-byte aligned with ld % 4 == 0.  db is produced from the same pass through an
+ * all-ones padding column: it needs k1 % 32 != 0 (k % 128 != 0 for the *2 form), otherwise pass
+ * db = NULL and obtain it elsewhere (gte_layernorm_act_bwd's dz_colsum).
+ */
+int gte_umma_bwd_weight_supported(int32_t fo, int32_t k1, int32_t k2);
+size_t gte_umma_bwd_weight_workspace_bytes(int32_t n, int32_t fo, int32_t k1, int32_t k2);
+int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const float* x1, int64_t ldx1,
+                               int32_t k1, const float* x2, int64_t ldx2, int32_t k2, float* dW,
+                               int64_t lddw, float* db, int accumulate, int32_t n, void* ws,
+                               size_t ws_bytes, gte_stream_t stream);
+size_t gte_umma_bwd_weight2_workspace_bytes(int32_t n, int32_t fo, int32_t k);
+int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz2, int64_t lddz2,
+                                int32_t fo, const float* x, int64_t ldx, int32_t k, float* dW,
+                                int64_t lddw, int32_t col1, int32_t col2, float* db, int accumulate,
+                                int32_t n, void* ws, size_t ws_bytes, gte_stream_t stream);
+
 /* ------------------------------------------- row normalisation + act ---- */
 /*
  * y = act(LayerNorm(z; gamma, beta, eps)) per row over the first f columns

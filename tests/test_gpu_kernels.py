@@ -414,3 +414,42 @@ def test_spmm_paged_equals_generic(f):
     if fake[2] <= 1600:
         b = ops.spmm(ip, ix, w_row, x, pages=fake, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
         assert torch.equal(ops.spmm(ip, ix, w_row, x, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm), b)
+
+
+@pytest.mark.parametrize("n,fo,k1,k2,with_db", [(5000, 218, 218, 218, False), (2000, 218, 13, 13, True), (1000, 64, 100, 0, True),
+                                                (513, 256, 256, 256, False), (40000, 218, 218, 218, False), (7, 9, 20, 0, True)])
+def test_umma_linear_bwd_weight_3xtf32(n, fo, k1, k2, with_db):
+    gen = torch.Generator().manual_seed(n + fo)
+    dz = torch.randn(n, fo, generator=gen)
+    x1 = torch.randn(n, k1, generator=gen)
+    x2 = torch.randn(n, k2, generator=gen) * 2 if k2 else None
+    X = torch.cat([x1, x2], 1) if k2 else x1
+    dW = torch.full((fo, k1 + k2), 5.0, device=DEV)
+    db = torch.full((fo,), 5.0, device=DEV) if with_db else None
+    ops.umma_linear_bwd_weight(_padded(dz), _padded(x1), _padded(x2) if k2 else None, dW, db)
+    e = rel_err(dW, dz.double().t() @ X.double())
+    dWf = torch.empty_like(dW)
+    ops.linear_bwd_weight(_padded(dz), _padded(x1), _padded(x2) if k2 else None, dWf, None)
+    _log_err(f"bwd_weight n={n} fo={fo} k={k1}+{k2}: umma={e:.2e} ffma", rel_err(dWf, dz.double().t() @ X.double()))
+    assert e < 3e-6
+    if with_db:
+        assert rel_err(db, dz.double().sum(0)) < 3e-6
+    dW2 = torch.empty_like(dW)
+    ops.umma_linear_bwd_weight(_padded(dz), _padded(x1), _padded(x2) if k2 else None, dW2, None)
+    assert torch.equal(dW2, dW)  # deterministic
+    ops.umma_linear_bwd_weight(_padded(dz), _padded(x1), _padded(x2) if k2 else None, dW2, None, accumulate=True)
+    assert rel_err(dW2, 2 * (dz.double().t() @ X.double())) < 3e-6
+
+
+@pytest.mark.parametrize("n,fo,k", [(3000, 9, 218), (1025, 32, 100), (200, 5, 256 - 1)])
+def test_umma_linear_bwd_weight2_3xtf32(n, fo, k):
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randn(n, k, generator=gen)
+    dz1, dz2 = torch.randn(n, fo, generator=gen), torch.randn(n, fo, generator=gen)
+    dW = torch.full((fo, 2 * k), 3.0, device=DEV)
+    db = torch.full((fo,), 3.0, device=DEV)
+    ops.umma_linear_bwd_weight2(_padded(dz1), _padded(dz2), _padded(x), dW, 0, k, db)
+    e1, e2 = rel_err(dW[:, :k], dz1.double().t() @ x.double()), rel_err(dW[:, k:], dz2.double().t() @ x.double())
+    _log_err(f"bwd_weight2 n={n} fo={fo} k={k}: e1={e1:.2e} e2", e2)
+    assert e1 < 3e-6 and e2 < 3e-6
+    assert rel_err(db, dz1.double().sum(0)) < 3e-6
