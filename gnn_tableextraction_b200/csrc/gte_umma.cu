@@ -40,7 +40,7 @@ constexpr int UM_STAGES = 2;
 constexpr int UM_A_BYTES = UM_BM * 128;  // 16 KB
 constexpr int UM_MAX_BN = 256;
 constexpr int UM_ACC_STRIDE = 256;       // TMEM columns per accumulator stage
-constexpr int UM_STAGE_LD = 33;          // padded row of the epilogue transpose buffer
+constexpr int UM_STAGE_LD = EPI_LD;      // row pitch of the epilogue transpose buffer
 
 struct UmmaArgs {
   CUtensorMap tmA[2];       // per K segment: activations [M, K_s], box 32 x 128
@@ -67,7 +67,8 @@ struct UmmaArgs {
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_constant__ UmmaArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all operand tiles 1024-byte aligned)
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the shared address space visible to the compiler (pointer arithmetic only): LDS/STS, not generic LD/ST
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = P.BN * 128;
   const int stage_bytes = 2 * UM_A_BYTES + 2 * b_bytes;
   uint8_t* const tiles = base;
@@ -229,6 +230,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
       const int64_t row0 = (int64_t)mt * UM_BM + q * 32;  // first global row of this warp
       float* outp = P.out[grp];
       const int64_t ldo = P.ldo[grp];
+      const bool vec_out = ((reinterpret_cast<uintptr_t>(outp) & 15) == 0) && (ldo % 4 == 0);
+      const bool vec_y = P.y != nullptr && ((reinterpret_cast<uintptr_t>(P.y) & 15) == 0) && (P.ldy % 4 == 0);
       uint32_t v[32];
       auto load_chunk = [&](int c) {
         tmem_ld_32x32b_x32(t_base + c * 32, v);
@@ -270,37 +273,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
           P.rstd[grow] = rstd;
         }
       }
+      const int rows_valid = (int)min((int64_t)32, (int64_t)P.M - row0);
       for (int c = 0; c < nchunks; ++c) {
         load_chunk(c);
-        // z chunk -> transpose buffer -> coalesced rows
-        __syncwarp();
+        float zv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * UM_STAGE_LD + j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];
-        __syncwarp();
-        const int col = c * 32 + lane;
-        if (col < P.N) {
-          for (int rr = 0; rr < 32; ++rr) {
-            const int64_t grow = row0 + rr;
-            if (grow < P.M) outp[grow * ldo + col] = st[rr * UM_STAGE_LD + lane];
-          }
-        }
+        for (int j = 0; j < 32; ++j) zv[j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+        if (rows_valid > 0)
+          epi_store_chunk(st, zv, outp + row0 * ldo + c * 32, ldo, rows_valid, P.N - c * 32, vec_out);
         if (P.y != nullptr) {
-          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int cj = c * 32 + j;
-            float o = __uint_as_float(v[j]) + s_bias[cj];
+            float o = zv[j];
             if (P.fuse_ln) o = (o - mean) * rstd * s_gamma[cj] + s_beta[cj];
             if (P.relu) o = fmaxf(o, 0.f);
-            st[lane * UM_STAGE_LD + j] = o;
+            zv[j] = o;
           }
-          __syncwarp();
-          if (col < P.N) {
-            for (int rr = 0; rr < 32; ++rr) {
-              const int64_t grow = row0 + rr;
-              if (grow < P.M) P.y[grow * P.ldy + col] = st[rr * UM_STAGE_LD + lane];
-            }
-          }
+          if (rows_valid > 0)
+            epi_store_chunk(st, zv, P.y + row0 * P.ldy + c * 32, P.ldy, rows_valid, P.N - c * 32, vec_y);
         }
       }
       tc_fence_before();

@@ -30,7 +30,7 @@ constexpr int DW_KB = 32;                      // contraction rows per pipeline 
 constexpr int DW_BOX_BYTES = DW_KB * 128;      // one TMA box: 32 rows x 32 floats
 constexpr int DW_STAGES = 2;
 constexpr int DW_MAX_BOXES = 8;
-constexpr int DW_STAGE_LD = 33;
+constexpr int DW_STAGE_LD = EPI_LD;
 
 struct DwBox {
   int32_t map;  // index into tmB
@@ -60,7 +60,8 @@ struct DwArgs {
 
 __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant__ DwArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the shared address space visible to the compiler (pointer arithmetic only): LDS/STS, not generic LD/ST
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int a_bytes = 4 * DW_BOX_BYTES;
   const int b_bytes = P.max_boxes * DW_BOX_BYTES;
   const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
@@ -236,18 +237,15 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
         uint32_t v[32], v2[32];
         tmem_ld_32x32b_x32(t_base + c * 32, v);
         tmem_ld_32x32b_x32(t_base + 256 + c * 32, v2);
-        __syncwarp();
+        float val[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float val = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-          if (P.dbg_mode == 10) val = 1.0f;
-          if (P.dbg_mode == 11) val = __uint_as_float(v[j]);
-          if (P.dbg_mode == 12) val = __uint_as_float(v2[j]);
-          st[lane * DW_STAGE_LD + j] = val;
+          val[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+          if (P.dbg_mode == 10) val[j] = 1.0f;
+          if (P.dbg_mode == 11) val[j] = __uint_as_float(v[j]);
+          if (P.dbg_mode == 12) val[j] = __uint_as_float(v2[j]);
         }
-        __syncwarp();
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) outp[(int64_t)rr * P.ldp + c * 32 + lane] = st[rr * DW_STAGE_LD + lane];
+        epi_store_chunk(st, val, outp + c * 32, P.ldp, 32, 32, true);  // partial tiles are 128-byte aligned
       }
       tc_fence_before();
       mbar_arrive(smem_u32(bar_tempty));

@@ -122,6 +122,38 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128_32b(uint32_t saddr, uint3
 
 namespace gte {
 
+// ------------------------------------------------------------ epilogue store helper ----
+// Transposes one 32-row x 32-column accumulator chunk (thread = row, v[] = its 32 columns) through a
+// per-warp shared-memory tile and writes it to global memory with 128-bit, row-contiguous stores:
+// 8 lanes cover one 128-byte row segment, 4 rows per instruction.  `st` = warp-private [32][EPI_LD] floats.
+constexpr int EPI_LD = 36;  // 16-byte aligned rows; STS.128 / LDS.128 below are bank-conflict free
+__device__ __forceinline__ void epi_store_chunk(float* st, const float (&v)[32], float* out, int64_t ld, int rows_valid,
+                                                int cols_valid, bool vec_ok) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(st + lane * EPI_LD + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+  const int r_in = lane >> 3, c4 = (lane & 7) * 4;
+  if (c4 >= cols_valid) return;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + r_in;
+    if (row >= rows_valid) break;
+    const float4 val = *reinterpret_cast<const float4*>(st + row * EPI_LD + c4);
+    float* p = out + (int64_t)row * ld + c4;
+    if (vec_ok) {
+      *reinterpret_cast<float4*>(p) = val;  // may touch padding columns [N, ld): never interpreted
+    } else {
+      p[0] = val.x;
+      if (c4 + 1 < cols_valid) p[1] = val.y;
+      if (c4 + 2 < cols_valid) p[2] = val.z;
+      if (c4 + 3 < cols_valid) p[3] = val.w;
+    }
+  }
+}
+
 // ------------------------------------------------------------ host: TMA descriptors ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
