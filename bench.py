@@ -58,7 +58,7 @@ def peaks():
 
 # ------------------------------------------------------------ clocks -------
 class ClockSampler:
-    """Samples SM clock + throttle reasons during the timed region (pynvml, 100 ms)."""
+    """Samples SM clock + throttle reasons during the timed region (pynvml, every 10 ms)."""
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -94,7 +94,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01)
 
     def __enter__(self):
         if self.nv is not None:
@@ -365,10 +365,14 @@ def run_ours(args):
 
     # --- leg 2: end to end through the public API with HOST buffers ---------------------------------
     if use_graph:
+        trainer.prefetch_batch(host_batches[0])
+
         def e2e(i):
-            trainer.load_batch(host_batches[i % 3])  # H2D from pinned memory
-            trainer.replay()
-            stats_host.copy_(trainer.stats, non_blocking=True)  # D2H of [sum w*nll, sum w, #correct]
+            # every step: H2D of the NEXT batch from pinned memory (side stream, overlaps this step's kernels),
+            # the captured step on the current batch, D2H of [sum w*nll, sum w, #correct]
+            trainer.prefetch_batch(host_batches[(i + 1) % 3])
+            trainer.replay_prefetched()
+            stats_host.copy_(trainer.stats, non_blocking=True)
             stream.synchronize()  # the caller reads the loss every step (model_train.py:328 .item())
     else:
         def e2e(i):

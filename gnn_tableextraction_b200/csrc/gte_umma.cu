@@ -37,6 +37,7 @@ constexpr int UM_THREADS = 384;
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;               // floats per k block = one 128-byte swizzle row
 constexpr int UM_STAGES = 2;
+constexpr int UM_PREFETCH = 8;            // k-blocks of L2 prefetch lookahead for the activation tiles
 constexpr int UM_A_BYTES = UM_BM * 128;  // 16 KB
 constexpr int UM_MAX_BN = 256;
 constexpr int UM_ACC_STRIDE = 256;       // TMEM columns per accumulator stage
@@ -129,10 +130,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 prefetch cursor for the activation tiles, UM_PREFETCH k-blocks ahead (the packed weights are L2 resident)
+      int pf_tile = blockIdx.x, pf_seg = 0, pf_kb = 0;
+      auto pf_step = [&]() {
+        if (pf_tile >= total_tiles) return;
+        tma_prefetch_2d(&P.tmA[pf_seg], pf_kb * UM_BK, (pf_tile / P.ngroups) * UM_BM);
+        if (++pf_kb >= P.kblocks[pf_seg]) {
+          pf_kb = 0;
+          if (++pf_seg >= P.nseg) {
+            pf_seg = 0;
+            pf_tile += gridDim.x;
+          }
+        }
+      };
+      for (int i = 0; i < UM_PREFETCH; ++i) pf_step();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / P.ngroups, grp = tile % P.ngroups;
         for (int seg = 0; seg < P.nseg; ++seg) {
           for (int kb = 0; kb < P.kblocks[seg]; ++kb) {
+            pf_step();
             mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
             const uint32_t fb = smem_u32(&bar_full[stage]);
             mbar_expect_tx(fb, (uint32_t)(UM_A_BYTES + 2 * b_bytes));

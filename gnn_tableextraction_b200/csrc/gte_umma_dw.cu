@@ -29,6 +29,7 @@ constexpr int DW_THREADS = 384;
 constexpr int DW_KB = 32;                      // contraction rows per pipeline stage
 constexpr int DW_BOX_BYTES = DW_KB * 128;      // one TMA box: 32 rows x 32 floats
 constexpr int DW_STAGES = 2;
+constexpr int DW_PREFETCH = 6;                 // k-blocks of L2 prefetch lookahead
 constexpr int DW_MAX_BOXES = 8;
 constexpr int DW_STAGE_LD = EPI_LD;
 
@@ -115,6 +116,22 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 prefetch cursor running DW_PREFETCH k-blocks ahead of the loads
+      int pf_item = blockIdx.x, pf_kb = 0, pf_left = 0;
+      auto pf_step = [&]() {
+        if (pf_item >= total_items) return;
+        const int chunk = pf_item / P.items_per_chunk, sub = pf_item % P.items_per_chunk;
+        const DwGroup& G = P.grp[P.item_g[sub]];
+        const int mt = P.item_mt[sub];
+        const int row = chunk * P.chunk_rows + pf_kb * DW_KB;
+        for (int b = 0; b < 4; ++b) tma_prefetch_2d(&P.tmA[G.a], mt * 128 + b * 32, row);
+        for (int b = 0; b < G.nboxes; ++b) tma_prefetch_2d(&P.tmB[G.box[b].map], G.box[b].col, row);
+        if (++pf_kb >= chunk_kblocks(chunk)) {
+          pf_kb = 0;
+          pf_item += gridDim.x;
+        }
+      };
+      for (pf_left = 0; pf_left < DW_PREFETCH; ++pf_left) pf_step();
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
         const DwGroup& G = P.grp[P.item_g[sub]];
@@ -122,6 +139,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
         const int r0 = chunk * P.chunk_rows;
         const int nkb = chunk_kblocks(chunk);
         for (int kb = 0; kb < nkb; ++kb) {
+          pf_step();
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&bar_full[stage]);
           mbar_expect_tx(fb, (uint32_t)((4 + G.nboxes) * DW_BOX_BYTES));
@@ -160,7 +178,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
           const uint64_t dbh = make_desc_mn_sw128_32b(smem_u32(sB_hi(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
           const uint64_t dbl = make_desc_mn_sw128_32b(smem_u32(sB_lo(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
 #pragma unroll
-          for (int k = 0; k < DW_KB / 8; ++k) {
+          for (int k = 0; k < (P.dbg_mode == 22 ? 0 : DW_KB / 8); ++k) {
             const uint64_t adv = (uint64_t)((k * 1024) >> 4);  // next 8-row atom inside every box
             const uint32_t first = (kb | k) == 0 ? 0u : 1u;
             umma_tf32(d_cross, dal + adv, dbh + adv, idesc, first);
@@ -190,11 +208,17 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
         auto split = [&](uint8_t* hi_p, uint8_t* lo_p, int nf4) {
           float4* hi = reinterpret_cast<float4*>(hi_p);
           float4* lo = reinterpret_cast<float4*>(lo_p);
+          if (P.dbg_mode == 20) return;  // timing experiment: no split at all
           for (int idx = t; idx < nf4; idx += 128) {
             const float4 v = hi[idx];
             float4 h, l;
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-            l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+            if (P.dbg_mode == 21) {  // timing experiment: truncation masks instead of cvt.rna
+              h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+              l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            } else {
+              h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+              l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+            }
             hi[idx] = h;
             lo[idx] = l;
           }

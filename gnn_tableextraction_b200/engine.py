@@ -202,3 +202,43 @@ class SageTrainer:
     def replay(self) -> torch.Tensor:
         self._graph.replay()
         return self.stats
+
+    # -- pipelined input: the host->device copy of batch i+1 overlaps the step of batch i ----------------------
+    def prefetch_batch(self, host_batch: Dict[str, torch.Tensor]):
+        """Start the H2D copy of the NEXT batch on a side stream into a staging set (double buffered).
+        ``replay_prefetched()`` consumes the staging sets in order."""
+        if self._static is None:
+            raise GteError("prefetch_batch: call capture() first")
+        if int(host_batch["num_nodes"]) != self._static_meta[0] or int(host_batch["src"].numel()) != self._static_meta[1]:
+            raise GteError("prefetch_batch: batch shape differs from the captured one")
+        if getattr(self, "_stage_sets", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_sets = [{k: torch.empty_like(v) for k, v in self._static.items()} for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_w = self._stage_r = 0
+        if self._stage_w - self._stage_r >= 2:
+            raise GteError("prefetch_batch: both staging sets hold unconsumed batches; call replay_prefetched() first")
+        i = self._stage_w % 2
+        cs = self._copy_stream
+        if self._stage_w >= 2:
+            cs.wait_event(self._stage_free[i])  # staging set i was consumed by the step two batches ago
+        with torch.cuda.stream(cs):
+            for k in ("src", "dst", "weight", "feat", "label"):
+                self._stage_sets[i][k].copy_(host_batch[k], non_blocking=True)
+            self._stage_ready[i].record(cs)
+        self._stage_w += 1
+
+    def replay_prefetched(self) -> torch.Tensor:
+        """Run one captured step on the oldest prefetched batch."""
+        if getattr(self, "_stage_sets", None) is None or self._stage_r >= self._stage_w:
+            raise GteError("replay_prefetched: no prefetched batch")
+        i = self._stage_r % 2
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._stage_ready[i])
+        for k in ("src", "dst", "weight", "feat", "label"):
+            self._static[k].copy_(self._stage_sets[i][k], non_blocking=True)  # device-to-device, ~27 MB
+        self._stage_free[i].record(cur)
+        self._stage_r += 1
+        self._graph.replay()
+        return self.stats

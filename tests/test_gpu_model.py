@@ -239,3 +239,21 @@ def test_config2_scale_determinism_and_sanity():
     # and the first 4 pages agree with the oracle run on those 4 pages alone (pages are independent)
     om, _ = _oracle_and_cuda_models(6)
     assert rel_err(logits[:1200], om(oracle_graph_from_pages(pages[:4]))) < TOL
+
+
+def test_trainer_prefetched_replay_equals_plain_replay():
+    pages = [synth.make_pages(4, base_seed=s, n=64, k=5) for s in (1, 50, 90)]
+    hbs = [batch_pages_host(p) for p in pages]
+    _, m1 = _oracle_and_cuda_models(7, (13, 40, 9, 3))
+    _, m2 = _oracle_and_cuda_models(7, (13, 40, 9, 3))
+    t1, t2 = gte.SageTrainer(m1), gte.SageTrainer(m2)
+    t1.capture(hbs[0])
+    t2.capture(hbs[0])
+    t2.prefetch_batch(hbs[0])
+    for i in range(5):
+        t1.load_batch(hbs[i % 3])
+        s1 = t1.replay().clone()
+        t2.prefetch_batch(hbs[(i + 1) % 3])
+        s2 = t2.replay_prefetched().clone()
+        assert torch.equal(s1, s2), i
+    assert torch.equal(t1.flat_param, t2.flat_param)
