@@ -309,7 +309,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = gte.GcnSAGE(*MODEL_CFG[:3], MODEL_CFG[3], F.relu, 0).to(dev)
     trainer = gte.SageTrainer(model, lr=0.01, weight_decay=5e-4)
-    use_graph = (not args.no_graph) and world == 1
+    use_graph = not args.no_graph
     lib = gte.lib()
 
     dev_batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host_batches]
@@ -324,7 +324,17 @@ def run_ours(args):
     eager_step(dev_batches[0])
     launches_per_step = lib.gte_launch_count() - c0
     if use_graph:
-        trainer.capture(host_batches[0])
+        try:
+            trainer.capture(host_batches[0])  # data parallel: two graphs around the eager NCCL all-reduces
+        except Exception as exc:  # e.g. a NCCL build that cannot be captured: keep the eager step
+            if world == 1:
+                raise
+            print(f"[bench] rank {rank}: CUDA-graph capture failed ({type(exc).__name__}: {exc}); eager step", file=sys.stderr)
+            use_graph = False
+        if world > 1:  # all ranks must agree
+            flag = torch.tensor([1 if use_graph else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            use_graph = bool(flag.item())
 
     def barrier():
         if world > 1:

@@ -112,15 +112,27 @@ class SageTrainer:
         if self.world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
-    def _step_impl(self, g: PageGraphBatch, labels: torch.Tensor):
+    # The step in three kernel-only stages with the two collectives in between, so that under data
+    # parallelism each stage can be replayed from its own CUDA graph while NCCL runs eagerly.
+    def _stage_forward(self, g: PageGraphBatch, labels: torch.Tensor):
         logits, ctxs = self.forward(g)
         ops.cross_entropy_fwd(logits, labels, self.class_w, stats=self.stats)
-        self._all_reduce(self.stats)  # global sum w*nll, sum w, #correct
+        return logits, ctxs
+
+    def _stage_backward(self, g: PageGraphBatch, labels: torch.Tensor, logits, ctxs):
         dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, self.stats[1:2])
         self.backward(g, ctxs, dlogits)
-        self._all_reduce(self.flat_grad)
+
+    def _stage_update(self):
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
                       beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step_dev=self.step_dev)
+
+    def _step_impl(self, g: PageGraphBatch, labels: torch.Tensor):
+        logits, ctxs = self._stage_forward(g, labels)
+        self._all_reduce(self.stats)  # global sum w*nll, sum w, #correct
+        self._stage_backward(g, labels, logits, ctxs)
+        self._all_reduce(self.flat_grad)
+        self._stage_update()
         return logits
 
     # ------------------------------------------------------------- API -----
@@ -142,10 +154,13 @@ class SageTrainer:
         return logits
 
     # ----------------------------------------------------- CUDA graphs -----
-    def capture(self, host_batch: Dict[str, torch.Tensor]):
+    def capture(self, host_batch: Dict[str, torch.Tensor], split: Optional[bool] = None):
         """Capture the whole step (format build + forward + loss + backward +
         optimiser) for batches with exactly this node / edge count.  Later
-        batches are fed with ``load_batch`` + ``replay``."""
+        batches are fed with ``load_batch`` + ``replay``.  ``split`` (default: data-parallel
+        runs) captures two graphs around the eager collectives instead of one."""
+        if split is None:
+            split = self.world > 1
         dev = self.device
         n, e = int(host_batch["num_nodes"]), int(host_batch["src"].numel())
         f = int(host_batch["feat"].shape[1])
@@ -164,12 +179,15 @@ class SageTrainer:
         # replays read it): keep a reference on the trainer
         pages = self._static_pages = page_table(self._static_meta[2], self._static_meta[3], n, dev)
 
-        def body():
+        def make_graph():
             g = PageGraphBatch(st["src"], st["dst"], n, self._static_meta[2], self._static_meta[3])
             g._cache["pages"] = pages
             g.edata["feat"] = st["weight"]
             g.ndata["feat"] = st["feat"]
-            self._step_impl(g, st["label"])
+            return g
+
+        def body():
+            self._step_impl(make_graph(), st["label"])
 
         # warm-up on a side stream (allocator + lazy module state), restoring the optimiser state afterwards
         snap = (self.flat_param.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone())
@@ -180,14 +198,28 @@ class SageTrainer:
                 body()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            body()
+        if split:
+            # collectives stay outside the graphs: [graph 1: formats + forward + CE statistics] -> all-reduce(3 floats)
+            # -> [graph 2: CE gradient + backward] -> all-reduce(flat gradient) -> Adam (eager, 2 launches)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            keep = {}
+            with torch.cuda.graph(g1):
+                keep["g"] = make_graph()
+                keep["logits"], keep["ctxs"] = self._stage_forward(keep["g"], st["label"])
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self._stage_backward(keep["g"], st["label"], keep["logits"], keep["ctxs"])
+            self._graph_keep = keep  # activations live in the graphs' pool: keep their owners alive
+            self._graph = (g1, g2)
+            graph = self._graph
+        else:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            self._graph = graph
         self.flat_param.copy_(snap[0])
         self.exp_avg.copy_(snap[1])
         self.exp_avg_sq.copy_(snap[2])
         self.step_dev.copy_(snap[3])
-        self._graph = graph
         return graph
 
     def load_batch(self, host_batch: Dict[str, torch.Tensor]):
@@ -199,8 +231,19 @@ class SageTrainer:
         for k in ("src", "dst", "weight", "feat", "label"):
             st[k].copy_(host_batch[k], non_blocking=True)
 
+    def _replay_graphs(self):
+        if isinstance(self._graph, tuple):
+            g1, g2 = self._graph
+            g1.replay()
+            self._all_reduce(self.stats)
+            g2.replay()
+            self._all_reduce(self.flat_grad)
+            self._stage_update()
+        else:
+            self._graph.replay()
+
     def replay(self) -> torch.Tensor:
-        self._graph.replay()
+        self._replay_graphs()
         return self.stats
 
     # -- pipelined input: the host->device copy of batch i+1 overlaps the step of batch i ----------------------
@@ -240,5 +283,5 @@ class SageTrainer:
             self._static[k].copy_(self._stage_sets[i][k], non_blocking=True)  # device-to-device, ~27 MB
         self._stage_free[i].record(cur)
         self._stage_r += 1
-        self._graph.replay()
+        self._replay_graphs()
         return self.stats

@@ -183,14 +183,15 @@ def test_trainer_three_steps_match_oracle_adam():
     assert rel_err(tr.predict(g), om(og)) < 1e-3
 
 
-def test_trainer_graph_capture_replay_equals_eager():
+@pytest.mark.parametrize("split", [False, True])
+def test_trainer_graph_capture_replay_equals_eager(split):
     pages_a = synth.make_pages(4, base_seed=1, n=64, k=5)
     pages_b = synth.make_pages(4, base_seed=100, n=64, k=5)
     ha, hb = batch_pages_host(pages_a), batch_pages_host(pages_b)
     _, m1 = _oracle_and_cuda_models(4, (13, 40, 9, 3))
     _, m2 = _oracle_and_cuda_models(4, (13, 40, 9, 3))
     t1, t2 = gte.SageTrainer(m1), gte.SageTrainer(m2)
-    t2.capture(ha)
+    t2.capture(ha, split=split)
     for hbatch in (ha, hb, ha):
         s1 = t1.train_step(gte.PageGraphBatch.from_host(hbatch, DEV)).clone()
         t2.load_batch(hbatch)
