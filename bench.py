@@ -121,7 +121,7 @@ class OpTimer:
 
     NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
-             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2"]
+             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2", "umma_linear_fwd_stacked", "umma_linear_bwd_data2"]
 
     def __init__(self, ops, torch):
         self.ops, self.torch, self.rec, self.orig = ops, torch, [], {}
@@ -135,6 +135,10 @@ class OpTimer:
             return (name, int(a[0].shape[0]), int(k), int(a[2].shape[0]))
         if name == "linear_bwd_data":
             return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(a[3]))
+        if name == "umma_linear_fwd_stacked":  # (x, fin, pack, bias, fo)
+            return (name, int(a[0].shape[0]), int(a[1]), 2 * int(a[4]))
+        if name == "umma_linear_bwd_data2":  # (dz1, dz2, pack, fin)
+            return (name, int(a[0].shape[0]), 2 * int(a[0].shape[1]), int(a[3]))
         if name == "umma_linear_bwd_weight2":
             return (name, int(a[0].shape[0]), 2 * int(a[0].shape[1]), int(a[2].shape[1]))
         if name in ("linear_bwd_weight", "umma_linear_bwd_weight"):
@@ -193,10 +197,13 @@ def op_cost(key):
     if n == "linear_fwd":
         _, N, K, Fo = key
         return 4 * N * K + 4 * N * Fo + 4 * K * Fo, 2 * N * K * Fo
+    if n == "umma_linear_fwd_stacked":
+        _, N, K, Fo = key
+        return 4 * N * K + 4 * N * 32, 2 * N * K * Fo
     if n == "umma_linear_fwd":  # reads [h | ah], writes z and y
         _, N, K, Fo = key
         return 4 * N * K + 8 * N * Fo + 4 * K * Fo, 2 * N * K * Fo
-    if n in ("linear_bwd_data", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2"):
+    if n in ("linear_bwd_data", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_data2"):
         _, N, Fo, K = key
         return 4 * N * Fo + 4 * N * K + 4 * K * Fo, 2 * N * K * Fo
     if n in ("linear_bwd_weight", "umma_linear_bwd_weight", "umma_linear_bwd_weight2"):

@@ -61,6 +61,7 @@ struct UmmaArgs {
   float* rstd;
   float eps;
   int32_t fuse_ln, relu;
+  int32_t bias_n;  // number of valid bias entries (the stacked class-layer output is wider than its bias)
   int32_t variant;  // bit0: round-to-nearest hi/lo split, bit1: cross terms in their own accumulator
 };
 
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
   const int kb_total = P.kblocks[0] + (P.nseg > 1 ? P.kblocks[1] : 0);
 
   for (int i = threadIdx.x; i < UM_MAX_BN; i += UM_THREADS) {
-    s_bias[i] = (P.bias && i < P.N) ? P.bias[i] : 0.f;
+    s_bias[i] = (P.bias && i < P.bias_n) ? P.bias[i] : 0.f;
     s_gamma[i] = (P.gamma && i < P.N) ? P.gamma[i] : 1.f;
     s_beta[i] = (P.beta && i < P.N) ? P.beta[i] : 0.f;
   }
@@ -327,18 +328,28 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
 // fwd pack:  Pf[seg][half][BN][Kp]   Pf[seg][.][o][k] = W[o, seg*fin + k]          (K-major B of z = x W^T)
 // bwd pack:  Pb[grp][half][BNb][Kpb] Pb[grp][.][j][o] = W[o, grp*fin + j]          (K-major B of dx = dz W)
 // half 0 = tf32 hi, half 1 = tf32(lo); zero padded.
+// stacked pack (narrow layers, fo <= 16, nseg == 2): Ps[half][32][Kp], row o = W[o, 0:fin] (self block),
+//            row 16+o = W[o, fin:2fin] (neighbour block): ONE pass over x gives [x Ws^T | x Wn^T] side by side.
 __global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
                             float* __restrict__ Pf, int32_t BN, int32_t Kp, float* __restrict__ Pb, int32_t BNb,
-                            int32_t Kpb, int32_t variant) {
+                            int32_t Kpb, float* __restrict__ Ps, int32_t variant) {
   const int64_t per_f = (int64_t)BN * Kp, per_b = (int64_t)BNb * Kpb;
   const int64_t total_f = (int64_t)nseg * per_f, total_b = (int64_t)nseg * per_b;
+  const int64_t total_s = Ps ? (int64_t)32 * Kp : 0;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < total_f + total_b; i += stride) {
+  for (; i < total_f + total_b + total_s; i += stride) {
     float w = 0.f;
     float* dst;
     int64_t half_stride;
-    if (i < total_f) {
+    if (i >= total_f + total_b) {
+      const int64_t r = i - total_f - total_b;
+      const int row = (int)(r / Kp), k = (int)(r % Kp);
+      const int o = row & 15, blk = row >> 4;
+      if (o < fo && k < fin) w = W[(int64_t)o * ldw + (int64_t)blk * fin + k];
+      dst = Ps + r;
+      half_stride = total_s;
+    } else if (i < total_f) {
       const int seg = (int)(i / per_f);
       const int64_t r = i % per_f;
       const int o = (int)(r / Kp), k = (int)(r % Kp);
@@ -380,7 +391,7 @@ static int umma_variant() {
 
 struct PackDims {
   int BN, Kp, BNb, Kpb;
-  size_t fwd_floats, bwd_floats;
+  size_t fwd_floats, bwd_floats, stacked_floats;
 };
 static PackDims pack_dims(int fo, int fin, int nseg) {
   PackDims d;
@@ -390,6 +401,7 @@ static PackDims pack_dims(int fo, int fin, int nseg) {
   d.Kpb = round_up(fo, UM_BK);
   d.fwd_floats = (size_t)nseg * 2 * d.BN * d.Kp;
   d.bwd_floats = (size_t)nseg * 2 * d.BNb * d.Kpb;
+  d.stacked_floats = (fo <= 16 && nseg == 2) ? (size_t)2 * 32 * d.Kp : 0;
   return d;
 }
 
@@ -423,13 +435,13 @@ using namespace gte;
 extern "C" {
 
 int gte_umma_supported(int32_t fo, int32_t fin) {
-  return (fo >= 16 && fo <= UM_MAX_BN && fin >= 16 && fin <= UM_MAX_BN) ? 1 : 0;
+  return (fo >= 1 && fo <= UM_MAX_BN && fin >= 1 && fin <= UM_MAX_BN) ? 1 : 0;
 }
 
 size_t gte_umma_pack_bytes(int32_t fo, int32_t fin, int32_t nseg) {
   if (!gte_umma_supported(fo, fin) || nseg < 1 || nseg > 2) return 0;
   PackDims d = pack_dims(fo, fin, nseg);
-  return (d.fwd_floats + d.bwd_floats) * 4;
+  return (d.fwd_floats + d.bwd_floats + d.stacked_floats) * 4;
 }
 
 int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg, float* pack,
@@ -439,9 +451,10 @@ int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, 
   if (!gte_umma_supported(fo, fin)) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_pack_weights: fo=%d fin=%d unsupported", fo, fin);
   GTE_CHECK_ARG(aligned16(pack), "gte_umma_pack_weights: pack buffer must be 16-byte aligned");
   PackDims d = pack_dims(fo, fin, nseg);
-  const int64_t total = (int64_t)nseg * ((int64_t)d.BN * d.Kp + (int64_t)d.BNb * d.Kpb);
-  k_umma_pack<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(W, ldw, fo, fin, nseg, pack, d.BN, d.Kp,
-                                                                              pack + d.fwd_floats, d.BNb, d.Kpb, umma_variant());
+  const int64_t total = (int64_t)nseg * ((int64_t)d.BN * d.Kp + (int64_t)d.BNb * d.Kpb) + (int64_t)d.stacked_floats / 2;
+  k_umma_pack<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
+      W, ldw, fo, fin, nseg, pack, d.BN, d.Kp, pack + d.fwd_floats, d.BNb, d.Kpb,
+      d.stacked_floats ? pack + d.fwd_floats + d.bwd_floats : nullptr, umma_variant());
   GTE_CHECK_LAUNCH("k_umma_pack");
   return GTE_OK;
 }
@@ -483,6 +496,7 @@ int gte_umma_linear_fwd(const float* x1, int64_t ldx1, const float* x2, int64_t 
   a.y = y;
   a.ldy = ldy;
   a.bias = bias;
+  a.bias_n = fo;
   a.gamma = gamma;
   a.beta = beta;
   a.mean = mean;
@@ -523,6 +537,74 @@ int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const fl
   a.ldo[0] = lddx1;
   a.out[1] = dx2;
   a.ldo[1] = lddx2;
+  return launch_umma(a, as_stream(stream));
+}
+
+// Narrow (class) layer, project-then-aggregate: out[n, 32] = x [Ws | . | Wn | .]^T (+ bias on the first fo columns):
+// columns [0, fo) = x Ws^T + b, columns [16, 16+fo) = x Wn^T.  One pass over x.
+int gte_umma_linear_fwd_stacked(const float* x, int64_t ldx, int32_t fin, const float* pack, const float* bias, int32_t fo,
+                                float* out, int64_t ldo, int32_t n, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0, "gte_umma_linear_fwd_stacked: negative n");
+  if (fo < 1 || fo > 16 || !gte_umma_supported(fo, fin))
+    return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_fwd_stacked: fo=%d fin=%d unsupported (fo <= 16)", fo, fin);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(x && pack && out, "gte_umma_linear_fwd_stacked: null argument");
+  GTE_CHECK_ARG(aligned16(x) && ldx % 4 == 0 && ldx >= fin && ldo >= 32,
+                "gte_umma_linear_fwd_stacked: x must be 16-byte aligned with ld %% 4 == 0; out needs ld >= 32");
+  PackDims d = pack_dims(fo, fin, 2);
+  const float* ps = pack + d.fwd_floats + d.bwd_floats;
+  UmmaArgs a{};
+  a.nseg = 1;
+  a.ngroups = 1;
+  a.M = n;
+  a.N = 32;
+  a.BN = 32;
+  a.kblocks[0] = d.Kp / UM_BK;
+  int rc = make_map(&a.tmA[0], x, n, fin, ldx, UM_BM);
+  if (rc) return rc;
+  rc = make_map(&a.tmBhi[0][0], ps, 32, d.Kp, d.Kp, 32);
+  if (rc) return rc;
+  rc = make_map(&a.tmBlo[0][0], ps + (size_t)32 * d.Kp, 32, d.Kp, d.Kp, 32);
+  if (rc) return rc;
+  a.out[0] = out;
+  a.ldo[0] = ldo;
+  a.bias = bias;
+  a.bias_n = fo;
+  return launch_umma(a, as_stream(stream));
+}
+
+// dx = dz1 W[:, :fin] + dz2 W[:, fin:2fin]   (two K segments, one output; class layer backward)
+int gte_umma_linear_bwd_data2(const float* dz1, int64_t lddz1, const float* dz2, int64_t lddz2, int32_t fo,
+                              const float* pack, float* dx, int64_t lddx, int32_t n, int32_t fin, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0, "gte_umma_linear_bwd_data2: negative n");
+  if (!gte_umma_supported(fo, fin)) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_data2: fo=%d fin=%d unsupported", fo, fin);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(dz1 && dz2 && pack && dx, "gte_umma_linear_bwd_data2: null argument");
+  GTE_CHECK_ARG(aligned16(dz1) && lddz1 % 4 == 0 && lddz1 >= fo && aligned16(dz2) && lddz2 % 4 == 0 && lddz2 >= fo,
+                "gte_umma_linear_bwd_data2: dz must be 16-byte aligned with ld %% 4 == 0");
+  GTE_CHECK_ARG(lddx >= fin, "gte_umma_linear_bwd_data2: output leading dimension < fin");
+  PackDims d = pack_dims(fo, fin, 2);
+  const float* pb = pack + d.fwd_floats;
+  const size_t per = (size_t)d.BNb * d.Kpb;
+  UmmaArgs a{};
+  a.nseg = 2;
+  a.ngroups = 1;
+  a.M = n;
+  a.N = fin;
+  a.BN = d.BNb;
+  const float* dzs[2] = {dz1, dz2};
+  const int64_t lds[2] = {lddz1, lddz2};
+  for (int s = 0; s < 2; ++s) {
+    a.kblocks[s] = d.Kpb / UM_BK;
+    int rc = make_map(&a.tmA[s], dzs[s], n, fo, lds[s], UM_BM);
+    if (rc) return rc;
+    rc = make_map(&a.tmBhi[0][s], pb + (size_t)s * 2 * per, d.BNb, d.Kpb, d.Kpb, d.BNb);
+    if (rc) return rc;
+    rc = make_map(&a.tmBlo[0][s], pb + (size_t)s * 2 * per + per, d.BNb, d.Kpb, d.Kpb, d.BNb);
+    if (rc) return rc;
+  }
+  a.out[0] = dx;
+  a.ldo[0] = lddx;
   return launch_umma(a, as_stream(stream));
 }
 

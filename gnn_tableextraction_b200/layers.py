@@ -61,13 +61,15 @@ def pick_strategy(fin: int, fout: int, use_pp: bool) -> str:
 
 
 def use_umma(n: int, fin: int, fout: int, *mats) -> bool:
+    """Tensor-core projection.  Also used for narrow K (input layer, K = 2*13): the kernel then is an
+    output-bandwidth-bound fused bias+LayerNorm+ReLU epilogue, still far ahead of GEMM + separate LayerNorm."""
     if GEMM_MODE == "ffma" or not ops.umma_supported(fout, fin):
         return False
     if not all(ops._aligned_mat(m) for m in mats if m is not None):
         return False
     if GEMM_MODE == "umma":
         return True
-    return n >= UMMA_MIN_ROWS and fin >= UMMA_MIN_WIDTH and fout >= UMMA_MIN_WIDTH
+    return n >= UMMA_MIN_ROWS and max(fin, fout) >= UMMA_MIN_WIDTH
 
 
 def use_umma_dw(n: int, fo: int, k1: int, k2: int, db_needed: bool, *mats) -> bool:
@@ -131,8 +133,14 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
             return (y if y is not None else z), ctx
         z = ops.linear_fwd(h, ah, W, b)
     elif st == "proj":
-        s = ops.linear_fwd(h, None, W, b, w_col0=0)
-        p = ops.linear_fwd(h, None, W, None, w_col0=fin)
+        if fout <= 16 and use_umma(h.shape[0], fin, fout, h):
+            # one tensor-core pass over h: [h Ws^T + b | h Wn^T] side by side, aggregated through column views
+            ctx.pack = ops.umma_pack_weights(W, fin, 2)
+            sp = ops.umma_linear_fwd_stacked(h, fin, ctx.pack, b, fout)
+            s, p = sp[:, :fout], sp[:, 16:16 + fout]
+        else:
+            s = ops.linear_fwd(h, None, W, b, w_col0=0)
+            p = ops.linear_fwd(h, None, W, None, w_col0=fin)
         z = aggregate_forward(g, p, w_edge, agg, addend=s)
     else:
         raise _lib.GteError(f"unknown strategy {st}")
@@ -188,6 +196,8 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
         ops.linear_bwd_weight2(dz, gq, ctx.h, dW, 0, fin, db, accumulate)
     if not need_dh:
         return None
+    if ctx.pack is not None and ops._aligned_mat(dz) and ops._aligned_mat(gq):
+        return ops.umma_linear_bwd_data2(dz, gq, ctx.pack, fin)
     return ops.linear_bwd_data2(dz, 0, gq, fin, W, fin)
 
 

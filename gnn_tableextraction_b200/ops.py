@@ -353,6 +353,32 @@ def umma_linear_bwd_data(dz, pack, fin: int, nseg: int):
     return dx1, dx2
 
 
+def umma_linear_fwd_stacked(x, fin: int, pack, bias, fo: int):
+    """[n, 32] buffer: cols [0, fo) = x Ws^T + b, cols [16, 16+fo) = x Wn^T (class layer, one pass over x)."""
+    xp, ldx, k = _mat(x, "umma_stacked.x")
+    if k != fin:
+        raise GteError("umma_linear_fwd_stacked: x shape mismatch")
+    n = x.shape[0]
+    out = torch.empty((n, 32), dtype=torch.float32, device=x.device)
+    check(lib().gte_umma_linear_fwd_stacked(xp, ldx, fin, _vec(pack, "pack"), _vec(bias, "bias", n=fo), fo, out.data_ptr(),
+                                            32, n, _stream()), "gte_umma_linear_fwd_stacked")
+    return out
+
+
+def umma_linear_bwd_data2(dz1, dz2, pack, fin: int):
+    """dx = dz1 W[:, :fin] + dz2 W[:, fin:2 fin] on tensor cores."""
+    d1p, ld1, fo = _mat(dz1, "umma_bwd2.dz1")
+    d2p, ld2, fo2 = _mat(dz2, "umma_bwd2.dz2")
+    if fo2 != fo or dz2.shape[0] != dz1.shape[0]:
+        raise GteError("umma_linear_bwd_data2: shape mismatch")
+    n = dz1.shape[0]
+    dx = empty_padded(n, fin, dz1.device)
+    dxp, lddx, _ = _mat(dx, "umma_bwd2.dx")
+    check(lib().gte_umma_linear_bwd_data2(d1p, ld1, d2p, ld2, fo, _vec(pack, "pack"), dxp, lddx, n, fin, _stream()),
+          "gte_umma_linear_bwd_data2")
+    return dx
+
+
 def umma_bwd_weight_supported(fo: int, k1: int, k2: int) -> bool:
     return bool(lib().gte_umma_bwd_weight_supported(fo, k1, k2))
 

@@ -199,7 +199,7 @@ int gte_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz2, in
 /* ------------------------------------ tensor-core route (tcgen05, 3xTF32) -- */
 /*
  * Same contractions as gte_linear_fwd / gte_linear_bwd_data for the wide hidden
- * layers (16 <= fin, fo <= 256), on tcgen05.mma kind::tf32 with the
+ * layers (fin, fo <= 256), on tcgen05.mma kind::tf32 with the
  * error-compensated 3xTF32 operand split (fp32-level accuracy: a_lo*b_hi +
  * a_hi*b_lo + a_hi*b_hi accumulated in fp32 TMEM), TMA-staged operands and the
  * bias / LayerNorm / ReLU epilogue of models.py:63-66 fused.  Activations must be
@@ -226,6 +226,20 @@ int gte_umma_linear_fwd(const float* x1, int64_t ldx1, const float* x2, int64_t 
 int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const float* pack, int32_t nseg,
                              float* dx1, int64_t lddx1, float* dx2, int64_t lddx2, int32_t n, int32_t fin,
                              gte_stream_t stream);
+
+/*
+ * Class-layer (fo <= 16) forms of the project-then-aggregate strategy.  `pack` from
+ * gte_umma_pack_weights(W, fo, fin, nseg = 2).
+ *   fwd_stacked: out[n, 32]: columns [0, fo) = x W[:, :fin]^T + bias, columns [16, 16+fo) = x W[:, fin:]^T
+ *                (one pass over x; the aggregation then reads the two column blocks as views)
+ *   bwd_data2:   dx = dz1 W[:, :fin] + dz2 W[:, fin:2 fin]
+ */
+int gte_umma_linear_fwd_stacked(const float* x, int64_t ldx, int32_t fin, const float* pack,
+                                const float* bias, int32_t fo, float* out, int64_t ldo, int32_t n,
+                                gte_stream_t stream);
+int gte_umma_linear_bwd_data2(const float* dz1, int64_t lddz1, const float* dz2, int64_t lddz2,
+                              int32_t fo, const float* pack, float* dx, int64_t lddx, int32_t n,
+                              int32_t fin, gte_stream_t stream);
 
 /*
  * Weight gradients on the tensor cores (MN-major tcgen05.mma operands straight from the row-major

@@ -453,3 +453,41 @@ def test_umma_linear_bwd_weight2_3xtf32(n, fo, k):
     _log_err(f"bwd_weight2 n={n} fo={fo} k={k}: e1={e1:.2e} e2", e2)
     assert e1 < 3e-6 and e2 < 3e-6
     assert rel_err(db, dz1.double().sum(0)) < 3e-6
+
+
+def test_umma_class_layer_forms():
+    """stacked forward + two-segment input gradient of the project-then-aggregate class layer"""
+    n, fin, fo = 3000, 218, 9
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(n, fin, generator=gen)
+    W = (torch.rand(fo, 2 * fin, generator=gen) - 0.5) * 0.1
+    b = torch.randn(fo, generator=gen)
+    pack = ops.umma_pack_weights(W.to(DEV), fin, 2)
+    sp = ops.umma_linear_fwd_stacked(_padded(x), fin, pack, b.to(DEV), fo)
+    assert sp.shape == (n, 32)
+    assert rel_err(sp[:, :fo], x.double() @ W.double()[:, :fin].t() + b.double()) < 3e-6
+    assert rel_err(sp[:, 16:16 + fo], x.double() @ W.double()[:, fin:].t()) < 3e-6
+    assert torch.all(sp[:, fo:16] == 0) and torch.all(sp[:, 16 + fo:] == 0)
+    dz1, dz2 = torch.randn(n, fo, generator=gen), torch.randn(n, fo, generator=gen)
+    dx = ops.umma_linear_bwd_data2(_padded(dz1), _padded(dz2), pack, fin)
+    assert rel_err(dx, dz1.double() @ W.double()[:, :fin] + dz2.double() @ W.double()[:, fin:]) < 3e-6
+
+
+def test_umma_input_layer_narrow_k():
+    """input layer on tensor cores: K = 13 + 13 (raw BBOX magnitudes up to 5e3), fused LayerNorm + ReLU"""
+    pages = synth.make_pages(5)
+    n = 1500
+    feat = torch.from_numpy(np.concatenate([p.feat for p in pages]))
+    ah = feat * 0.7 + 3.0
+    gen = torch.Generator().manual_seed(2)
+    W = (torch.rand(218, 26, generator=gen) - 0.5) * (2 / 26 ** 0.5)
+    b = torch.randn(218, generator=gen) * 0.1
+    gamma, beta = torch.rand(218, generator=gen) + 0.5, torch.randn(218, generator=gen) * 0.1
+    z64 = torch.cat([feat, ah], 1).double() @ W.double().t() + b.double()
+    y64 = F.relu(F.layer_norm(z64, (218,), gamma.double(), beta.double(), 1e-5))
+    pack = ops.umma_pack_weights(W.to(DEV), 13, 2)
+    z, y, mean, rstd = ops.umma_linear_fwd(_padded(feat), _padded(ah), 13, pack, b.to(DEV), 218, gamma=gamma.to(DEV),
+                                           beta=beta.to(DEV), relu=True, fuse_ln=True)
+    zf = ops.linear_fwd(_padded(feat), _padded(ah), W.to(DEV), b.to(DEV))
+    _log_err(f"input layer K=26: umma_z={rel_err(z, z64):.2e} umma_y={rel_err(y, y64):.2e} ffma_z", rel_err(zf, z64))
+    assert rel_err(z, z64) < 3e-6 and rel_err(y, y64) < 5e-6
