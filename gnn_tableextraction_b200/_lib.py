@@ -42,6 +42,7 @@ SIGNATURES = {
     "gte_umma_pack_weights": (ci, [vp, i64, i32, i32, i32, vp, vp]),
     "gte_umma_linear_fwd": (ci, [vp, i64, vp, i64, i32, vp, vp, vp, vp, f32, ci, ci, vp, i64, vp, i64, vp, vp, i32, i32, vp]),
     "gte_umma_linear_bwd_data": (ci, [vp, i64, i32, vp, i32, vp, i64, vp, i64, i32, i32, vp]),
+    "gte_umma_debug_times": (ci, [vp, i32]),
     "gte_umma_linear_fwd_stacked": (ci, [vp, i64, i32, vp, vp, i32, vp, i64, i32, vp]),
     "gte_umma_linear_bwd_data2": (ci, [vp, i64, vp, i64, i32, vp, vp, i64, i32, i32, vp]),
     "gte_umma_bwd_weight_supported": (ci, [i32, i32, i32]),

@@ -33,6 +33,9 @@
 
 namespace gte {
 
+// diagnostic: per-CTA, per-tile role timestamps (clock64) when UmmaArgs::dbg != 0; read with gte_umma_debug_times()
+__device__ long long g_umma_dbg[148 * 16 * 8];
+
 constexpr int UM_THREADS = 384;
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;               // floats per k block = one 128-byte swizzle row
@@ -61,11 +64,38 @@ struct UmmaArgs {
   float* rstd;
   float eps;
   int32_t fuse_ln, relu;
+  int32_t dbg;
   int32_t bias_n;  // number of valid bias entries (the stacked class-layer output is wider than its bias)
   int32_t variant;  // bit0: round-to-nearest hi/lo split, bit1: cross terms in their own accumulator
 };
 
+// x[j] = accumulator (main [+ cross-term accumulator]) + bias for the 32 columns of one chunk of this thread's row.
+// Everything is compile-time indexed so the 32-register TMEM load windows stay in registers (no local memory).
+template <bool SPLIT>
+__device__ __forceinline__ void epi_load_chunk(uint32_t taddr, const float* bias_c, float (&x)[32]) {
+  uint32_t v[32];
+  tmem_ld_32x32b_x32_nowait(taddr, v);
+  if constexpr (SPLIT) {
+    uint32_t v2[32];
+    tmem_ld_32x32b_x32_nowait(taddr + UM_ACC_STRIDE, v2);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+  } else {
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+  }
+  const float4* b4 = reinterpret_cast<const float4*>(bias_c);
+#pragma unroll
+  for (int qd = 0; qd < 8; ++qd) {
+    const float4 b = b4[qd];
+    x[4 * qd] += b.x; x[4 * qd + 1] += b.y; x[4 * qd + 2] += b.z; x[4 * qd + 3] += b.w;
+  }
+}
+
 // ------------------------------------------------------------ the kernel ---
+template <bool SPLIT>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_constant__ UmmaArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all operand tiles 1024-byte aligned)
@@ -96,6 +126,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
   const int m_tiles = (P.M + UM_BM - 1) / UM_BM;
   const int total_tiles = m_tiles * P.ngroups;
   const int kb_total = P.kblocks[0] + (P.nseg > 1 ? P.kblocks[1] : 0);
+  auto stamp = [&](int tile, int slot) {
+    if (P.dbg && blockIdx.x < 148) {
+      const int t = (tile - blockIdx.x) / gridDim.x;
+      if (t < 16) g_umma_dbg[(blockIdx.x * 16 + t) * 8 + slot] = clock64();
+    }
+  };
 
   for (int i = threadIdx.x; i < UM_MAX_BN; i += UM_THREADS) {
     s_bias[i] = (P.bias && i < P.bias_n) ? P.bias[i] : 0.f;
@@ -147,10 +183,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
       for (int i = 0; i < UM_PREFETCH; ++i) pf_step();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / P.ngroups, grp = tile % P.ngroups;
+        stamp(tile, 7);
         for (int seg = 0; seg < P.nseg; ++seg) {
           for (int kb = 0; kb < P.kblocks[seg]; ++kb) {
             pf_step();
-            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+            mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
             const uint32_t fb = smem_u32(&bar_full[stage]);
             mbar_expect_tx(fb, (uint32_t)(UM_A_BYTES + 2 * b_bytes));
             tma_load_2d(smem_u32(sA_hi_p(stage)), &P.tmA[seg], fb, kb * UM_BK, mt * UM_BM);
@@ -170,11 +207,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const bool split_acc = (P.variant & 2) != 0;
-      const int nacc = split_acc ? 1 : 2;
+      constexpr bool split_acc = SPLIT;
+      constexpr int nacc = SPLIT ? 1 : 2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+        stamp(tile, 4);
+        mbar_wait_backoff(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
         tc_fence_after();
+        stamp(tile, 5);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * UM_ACC_STRIDE);
         const uint32_t d_cross = split_acc ? tmem_base + UM_ACC_STRIDE : d_tmem;
         for (int kb = 0; kb < kb_total; ++kb) {
@@ -195,6 +234,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
           umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
         }
+        stamp(tile, 6);
         umma_commit(smem_u32(&bar_tfull[acc]));
         if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
@@ -206,7 +246,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < kb_total; ++kb) {
-        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
         float4* hi = reinterpret_cast<float4*>(sA_hi_p(stage));
         float4* lo = reinterpret_cast<float4*>(sA_lo_p(stage));
 #pragma unroll
@@ -235,82 +275,91 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
     float* st = s_stage + q * 32 * UM_STAGE_LD;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool split_acc = (P.variant & 2) != 0;
-    const int nacc = split_acc ? 1 : 2;
+    constexpr int nacc = SPLIT ? 1 : 2;
     const int nchunks = (P.N + 31) / 32;
     const float inv_n = 1.0f / (float)P.N;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / P.ngroups, grp = tile % P.ngroups;
+      if (warp == 8 && lane == 0) stamp(tile, 0);
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
+      if (warp == 8 && lane == 0) stamp(tile, 1);
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * UM_ACC_STRIDE);
       const int64_t row0 = (int64_t)mt * UM_BM + q * 32;  // first global row of this warp
       float* outp = P.out[grp];
       const int64_t ldo = P.ldo[grp];
       const bool vec_out = ((reinterpret_cast<uintptr_t>(outp) & 15) == 0) && (ldo % 4 == 0);
       const bool vec_y = P.y != nullptr && ((reinterpret_cast<uintptr_t>(P.y) & 15) == 0) && (P.ldy % 4 == 0);
-      uint32_t v[32];
-      auto load_chunk = [&](int c) {
-        tmem_ld_32x32b_x32(t_base + c * 32, v);
-        if (split_acc) {
-          uint32_t v2[32];
-          tmem_ld_32x32b_x32(t_base + UM_ACC_STRIDE + c * 32, v2);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-        }
-      };
+      float x[32];
+#define load_chunk(c) epi_load_chunk<SPLIT>(t_base + (c) * 32, s_bias + (c) * 32, x)
       float mean = 0.f, rstd = 1.f;
       if (P.fuse_ln) {
-        float s = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
+        // two passes over TMEM (mean, then centred second moment): exact like nn.LayerNorm; the last chunk
+        // is the only one that needs per-column predicates
+        const int nfull = P.N / 32, ntail = P.N % 32;
+        float s1 = 0.f;
+        for (int c = 0; c < nfull; ++c) {
+          load_chunk(c);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s1 += x[j];
+        }
+        if (ntail) {
+          load_chunk(nfull);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s1 += (j < ntail) ? x[j] : 0.f;
+        }
+        mean = s1 * inv_n;
+        float s2 = 0.f;
+        for (int c = 0; c < nfull; ++c) {
           load_chunk(c);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int col = c * 32 + j;
-            if (col < P.N) s += __uint_as_float(v[j]) + s_bias[col];
+            const float d = x[j] - mean;
+            s2 = fmaf(d, d, s2);
           }
         }
-        mean = s * inv_n;
-        float qv = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-          load_chunk(c);
+        if (ntail) {
+          load_chunk(nfull);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int col = c * 32 + j;
-            if (col < P.N) {
-              const float d = __uint_as_float(v[j]) + s_bias[col] - mean;
-              qv = fmaf(d, d, qv);
-            }
+            const float d = (j < ntail) ? x[j] - mean : 0.f;
+            s2 = fmaf(d, d, s2);
           }
         }
-        rstd = 1.0f / sqrtf(qv * inv_n + P.eps);
+        rstd = 1.0f / sqrtf(s2 * inv_n + P.eps);
         const int64_t grow = row0 + lane;
         if (grow < P.M) {
           P.mean[grow] = mean;
           P.rstd[grow] = rstd;
         }
       }
+      if (warp == 8 && lane == 0) stamp(tile, 2);
       const int rows_valid = (int)min((int64_t)32, (int64_t)P.M - row0);
       for (int c = 0; c < nchunks; ++c) {
         load_chunk(c);
-        float zv[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) zv[j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];
         if (rows_valid > 0)
-          epi_store_chunk(st, zv, outp + row0 * ldo + c * 32, ldo, rows_valid, P.N - c * 32, vec_out);
+          epi_store_chunk(st, x, outp + row0 * ldo + c * 32, ldo, rows_valid, P.N - c * 32, vec_out);
         if (P.y != nullptr) {
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c * 32);
+          const float4* e4 = reinterpret_cast<const float4*>(s_beta + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int cj = c * 32 + j;
-            float o = zv[j];
-            if (P.fuse_ln) o = (o - mean) * rstd * s_gamma[cj] + s_beta[cj];
-            if (P.relu) o = fmaxf(o, 0.f);
-            zv[j] = o;
+          for (int qd = 0; qd < 8; ++qd) {
+            const float4 gm = g4[qd], bt = e4[qd];
+            const float gv[4] = {gm.x, gm.y, gm.z, gm.w}, bv[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float o = x[4 * qd + e];
+              if (P.fuse_ln) o = (o - mean) * rstd * gv[e] + bv[e];
+              if (P.relu) o = fmaxf(o, 0.f);
+              x[4 * qd + e] = o;
+            }
           }
           if (rows_valid > 0)
-            epi_store_chunk(st, zv, P.y + row0 * P.ldy + c * 32, P.ldy, rows_valid, P.N - c * 32, vec_y);
+            epi_store_chunk(st, x, P.y + row0 * P.ldy + c * 32, P.ldy, rows_valid, P.N - c * 32, vec_y);
         }
       }
+#undef load_chunk
+      if (warp == 8 && lane == 0) stamp(tile, 3);
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[acc]));
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
@@ -414,16 +463,22 @@ static int launch_umma(UmmaArgs& a, cudaStream_t st) {
   const size_t smem = umma_smem_bytes(a.BN);
   static size_t configured = 0;
   if (smem > configured) {
-    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "k_umma_gemm(smem attr)");
+    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "k_umma_gemm(smem attr)");
     configured = smem;
   }
   a.variant = umma_variant();
+  a.dbg = getenv("GTE_UMMA_DBG") ? 1 : 0;
   const int tiles = ((a.M + UM_BM - 1) / UM_BM) * a.ngroups;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
   if (grid < 1) return GTE_OK;
-  k_umma_gemm<<<grid, UM_THREADS, smem, st>>>(a);
+  if (a.variant & 2)
+    k_umma_gemm<true><<<grid, UM_THREADS, smem, st>>>(a);
+  else
+    k_umma_gemm<false><<<grid, UM_THREADS, smem, st>>>(a);
   GTE_CHECK_LAUNCH("k_umma_gemm");
   return GTE_OK;
 }
@@ -606,6 +661,13 @@ int gte_umma_linear_bwd_data2(const float* dz1, int64_t lddz1, const float* dz2,
   a.out[0] = dx;
   a.ldo[0] = lddx;
   return launch_umma(a, as_stream(stream));
+}
+
+// diagnostic only: copy the role timestamps of the last k_umma_gemm launch run with GTE_UMMA_DBG=1 (148 x 16 x 8 int64)
+int gte_umma_debug_times(int64_t* out_host, int32_t count) {
+  if (!out_host || count <= 0 || count > 148 * 16 * 8) return fail(GTE_ERR_INVALID, "gte_umma_debug_times: bad argument");
+  GTE_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_umma_dbg, (size_t)count * 8), "gte_umma_debug_times");
+  return GTE_OK;
 }
 
 }  // extern "C"

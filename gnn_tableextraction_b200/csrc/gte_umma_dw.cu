@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
         const int nkb = chunk_kblocks(chunk);
         for (int kb = 0; kb < nkb; ++kb) {
           pf_step();
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&bar_full[stage]);
           mbar_expect_tx(fb, (uint32_t)((4 + G.nboxes) * DW_BOX_BYTES));
           const int row = r0 + kb * DW_KB;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
         uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         if (P.dbg_mode == 13) idesc &= ~((1u << 15) | (1u << 16));
-        mbar_wait(smem_u32(bar_tempty), acc_phase ^ 1);
+        mbar_wait_backoff(smem_u32(bar_tempty), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_main = tmem_base, d_cross = tmem_base + 256;
         const int nkb = chunk_kblocks(chunk);
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
       const int r0 = chunk * P.chunk_rows;
       const int nkb = chunk_kblocks(chunk);
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
         auto split = [&](uint8_t* hi_p, uint8_t* lo_p, int nf4) {
           float4* hi = reinterpret_cast<float4*>(hi_p);
           float4* lo = reinterpret_cast<float4*>(lo_p);
@@ -259,8 +259,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
       float* outp = P.partial + (int64_t)chunk * P.chunk_stride + (int64_t)(mt * 128 + q * 32) * P.ldp + G.pcol0;
       for (int c = 0; c < G.nboxes; ++c) {
         uint32_t v[32], v2[32];
-        tmem_ld_32x32b_x32(t_base + c * 32, v);
-        tmem_ld_32x32b_x32(t_base + 256 + c * 32, v2);
+        tmem_ld_32x32b_x32_nowait(t_base + c * 32, v);
+        tmem_ld_32x32b_x32_nowait(t_base + 256 + c * 32, v2);
+        tmem_wait_ld();
         float val[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {

@@ -227,6 +227,9 @@ int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const fl
                              float* dx1, int64_t lddx1, float* dx2, int64_t lddx2, int32_t n, int32_t fin,
                              gte_stream_t stream);
 
+/* Diagnostic: role timestamps (clock64) of the last tensor-core projection launched with GTE_UMMA_DBG=1. */
+int gte_umma_debug_times(int64_t* out_host, int32_t count);
+
 /*
  * Class-layer (fo <= 16) forms of the project-then-aggregate strategy.  `pack` from
  * gte_umma_pack_weights(W, fo, fin, nseg = 2).
