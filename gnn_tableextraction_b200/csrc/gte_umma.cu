@@ -44,12 +44,16 @@ constexpr int UM_PREFETCH = 8;            // k-blocks of L2 prefetch lookahead f
 constexpr int UM_A_BYTES = UM_BM * 128;  // 16 KB
 constexpr int UM_MAX_BN = 256;
 constexpr int UM_ACC_STRIDE = 256;       // TMEM columns per accumulator stage
-constexpr int UM_STAGE_LD = EPI_LD;      // row pitch of the epilogue transpose buffer
+// per epilogue warp: one or two 32x32 fp32 store tiles (TMA store, 1024-byte aligned); the legacy
+// [32][36] transposition tile (4608 B) must fit as well
+__host__ __device__ constexpr int um_epi_bytes(int nbuf) { return nbuf == 2 ? 8192 : 5120; }
 
 struct UmmaArgs {
   CUtensorMap tmA[2];       // per K segment: activations [M, K_s], box 32 x 128
   CUtensorMap tmBhi[2][2];  // [group][segment]: packed weights hi [BN, Kpad], box 32 x BN
   CUtensorMap tmBlo[2][2];
+  CUtensorMap tmOut[2];     // per group: z / dx, box 32 x 32 (TMA store)
+  CUtensorMap tmY;          // y (TMA store)
   int32_t nseg, ngroups;
   int32_t kblocks[2];
   int32_t M, N, BN;
@@ -65,6 +69,8 @@ struct UmmaArgs {
   float eps;
   int32_t fuse_ln, relu;
   int32_t dbg;
+  int32_t tma_store;  // outputs are TMA-store compatible (16-byte aligned, ld % 4 == 0)
+  int32_t epi_bufs;   // store tiles per epilogue warp (2 unless shared memory is tight)
   int32_t bias_n;  // number of valid bias entries (the stacked class-layer output is wider than its bias)
   int32_t variant;  // bit0: round-to-nearest hi/lo split, bit1: cross terms in their own accumulator
 };
@@ -109,8 +115,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
   auto sB_hi_p = [&](int s) { return tiles + s * stage_bytes + 2 * UM_A_BYTES; };
   auto sB_lo_p = [&](int s) { return tiles + s * stage_bytes + 2 * UM_A_BYTES + b_bytes; };
   base = tiles + UM_STAGES * stage_bytes;
-  float* s_stage = reinterpret_cast<float*>(base);                 // [4 warps][32][33]
-  float* s_bias = s_stage + 4 * 32 * UM_STAGE_LD;                  // [256]
+  uint8_t* s_stage = base;                                         // [4 warps][2][4096 B], 1024-byte aligned
+  float* s_bias = reinterpret_cast<float*>(s_stage + 4 * um_epi_bytes(P.epi_bufs));  // [256]
   float* s_gamma = s_bias + UM_MAX_BN;
   float* s_beta = s_gamma + UM_MAX_BN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + UM_MAX_BN);  // 8-byte aligned by construction
@@ -272,7 +278,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
   } else if (warp >= 8) {
     // ================================ epilogue ====================================
     const int q = warp & 3;                     // TMEM lane quarter this warp may touch
-    float* st = s_stage + q * 32 * UM_STAGE_LD;
+    uint8_t* stb = s_stage + q * um_epi_bytes(P.epi_bufs);
+    float* st = reinterpret_cast<float*>(stb);  // legacy store path: [32][EPI_LD] floats fit the same buffer
+    int store_seq = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int nacc = SPLIT ? 1 : 2;
@@ -337,7 +345,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
       const int rows_valid = (int)min((int64_t)32, (int64_t)P.M - row0);
       for (int c = 0; c < nchunks; ++c) {
         load_chunk(c);
-        if (rows_valid > 0)
+        if (P.tma_store)
+          epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
+        else if (rows_valid > 0)
           epi_store_chunk(st, x, outp + row0 * ldo + c * 32, ldo, rows_valid, P.N - c * 32, vec_out);
         if (P.y != nullptr) {
           const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c * 32);
@@ -354,7 +364,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
               x[4 * qd + e] = o;
             }
           }
-          if (rows_valid > 0)
+          if (P.tma_store)
+            epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
+          else if (rows_valid > 0)
             epi_store_chunk(st, x, P.y + row0 * P.ldy + c * 32, P.ldy, rows_valid, P.N - c * 32, vec_y);
         }
       }
@@ -365,6 +377,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
     }
   }
+  if (warp >= 8 && lane == 0) tma_store_wait_all();  // shared store tiles must outlive their TMA reads
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -454,13 +467,36 @@ static PackDims pack_dims(int fo, int fin, int nseg) {
   return d;
 }
 
-static size_t umma_smem_bytes(int BN) {
-  return 1024 + (size_t)UM_STAGES * (2 * UM_A_BYTES + 2 * (size_t)BN * 128) + 4 * 32 * UM_STAGE_LD * 4 + 3 * UM_MAX_BN * 4 +
-         (3 * UM_STAGES + 4) * 8 + 16;
+static size_t umma_smem_bytes(int BN, int epi_bufs) {
+  return 1024 + (size_t)UM_STAGES * (2 * UM_A_BYTES + 2 * (size_t)BN * 128) + 4 * (size_t)um_epi_bytes(epi_bufs) +
+         3 * UM_MAX_BN * 4 + (3 * UM_STAGES + 4) * 8 + 16;
+}
+
+// TMA-store descriptors for the outputs (used when every output is 16-byte aligned with ld % 4 == 0)
+static int setup_output_maps(UmmaArgs& a) {
+  bool ok = true;
+  for (int g = 0; g < a.ngroups; ++g) ok = ok && aligned16(a.out[g]) && a.ldo[g] % 4 == 0;
+  if (a.y) ok = ok && aligned16(a.y) && a.ldy % 4 == 0;
+  a.tma_store = ok ? 1 : 0;
+  if (!ok) return GTE_OK;
+  for (int g = 0; g < a.ngroups; ++g) {
+    int rc = make_tmap_2d(&a.tmOut[g], a.out[g], a.M, a.N, a.ldo[g], 32, 32);
+    if (rc) return rc;
+  }
+  if (a.y) {
+    int rc = make_tmap_2d(&a.tmY, a.y, a.M, a.N, a.ldy, 32, 32);
+    if (rc) return rc;
+  }
+  return GTE_OK;
 }
 
 static int launch_umma(UmmaArgs& a, cudaStream_t st) {
-  const size_t smem = umma_smem_bytes(a.BN);
+  {
+    int rc = setup_output_maps(a);
+    if (rc) return rc;
+  }
+  a.epi_bufs = umma_smem_bytes(a.BN, 2) <= 227 * 1024 ? 2 : 1;
+  const size_t smem = umma_smem_bytes(a.BN, a.epi_bufs);
   static size_t configured = 0;
   if (smem > configured) {
     GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

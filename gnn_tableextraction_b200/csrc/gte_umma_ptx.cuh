@@ -163,6 +163,44 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128_32b(uint32_t saddr, uint3
 
 namespace gte {
 
+// ------------------------------------------------------------ TMA stores (smem -> global) ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One 32-row x 32-column accumulator chunk (thread = row) -> dense, 128B-swizzled shared tile [32][32] floats
+// -> one asynchronous TMA store (bounds clipped by the tensor map).  `buf` is 1024-byte aligned and warp private;
+// `seq` counts this warp's stores: with nbuf == 2 two buffers alternate (one older store may still be reading).
+__device__ __forceinline__ void epi_store_chunk_tma(uint8_t* bufs, int nbuf, int& seq, const float (&v)[32],
+                                                    const CUtensorMap* map, int32_t col0, int32_t row0) {
+  const int lane = threadIdx.x & 31;
+  uint8_t* buf = bufs + (nbuf == 2 ? (seq & 1) * 4096 : 0);
+  if (seq >= nbuf) {
+    if (lane == 0) {
+      if (nbuf == 2) tma_store_wait_read<1>();
+      else tma_store_wait_read<0>();
+    }
+    __syncwarp();
+  }
+  float* rowp = reinterpret_cast<float*>(buf) + lane * 32;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(map, smem_u32(buf), col0, row0);
+    tma_store_commit();
+  }
+  ++seq;
+}
+
 // ------------------------------------------------------------ epilogue store helper ----
 // Transposes one 32-row x 32-column accumulator chunk (thread = row, v[] = its 32 columns) through a
 // per-warp shared-memory tile and writes it to global memory with 128-bit, row-contiguous stores:
