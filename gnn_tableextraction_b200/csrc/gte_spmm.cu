@@ -17,6 +17,7 @@
 // write y, indptr, indices, weights); the gathered rows
 // (4*E*F bytes) are served by L1/L2 because a page's sources are page-local.
 #include "gte_common.cuh"
+#include "gte_umma_ptx.cuh"
 
 namespace gte {
 
@@ -319,6 +320,459 @@ static int launch_spmm_paged(const int32_t* indptr, const int32_t* indices, cons
   return GTE_OK;
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Packed + persistent + double-buffered page kernel (the headline conv-layer kernel).
+//
+// What bounds k_spmm_paged above at F = 218, degree 10 (ncu, profiles/): no single pipe -- the
+// shared-memory pipe is ~45 % busy, the issue slots ~40 %, DRAM ~25 %: every CTA waits for its own
+// staging before it computes, about half of the instructions issue and address that staging, every
+// row waits a global-memory round trip for its normaliser / addend, and two 32-bit metadata words
+// are re-read per (edge, row group).  This variant
+//   * reads the edges pre-packed as 8-byte (page-local source row, weight * source scale) pairs
+//     (k_paged_pack_edges, once per graph and direction instead of once per CTA and slice),
+//   * runs one persistent CTA per SM over a contiguous range of (page, column slice) items with two
+//     shared-memory stages filled by the TMA unit (x slice: 2-D tensor boxes; packed edges: one bulk
+//     copy; row pointers / normalisers: 4-byte cp.async) while the previous item is reduced,
+//   * gives each lane V 128-bit column chunks of TWO rows at a time (G lanes per row) with the next
+//     group's metadata loaded ahead, so 8 independent 128-bit shared loads are in flight per lane,
+//   * prefetches the addend rows of the next item into L2 when it stages that item.
+// Sums run in row order exactly like the kernels above (deterministic, same rounding).
+constexpr int PK_CONSUMERS = 512;               // 16 consumer warps
+constexpr int PK_THREADS = PK_CONSUMERS + 32;   // + 1 producer warp
+constexpr int PK_BOX_BIG = 64;    // rows per large TMA box
+constexpr int PK_BOX_SMALL = 8;   // rows per small TMA box (page tail): at most 7 rows over-read per page
+constexpr uint32_t PK_OUTSIDE = 0xFFFFFFFFu;  // packed source row of an edge that leaves its page
+
+__global__ void __launch_bounds__(256)
+    k_paged_pack_edges(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                       const int32_t* __restrict__ eid, const float* __restrict__ w, const float* __restrict__ pre_scale,
+                       const int32_t* __restrict__ page_off, uint2* __restrict__ packed, int32_t* __restrict__ page_flag) {
+  const int page = blockIdx.x;
+  const int32_t n0 = page_off[page], n1 = page_off[page + 1];
+  const int32_t np = n1 - n0;
+  const int32_t e0 = indptr[n0], e1 = indptr[n1];
+  int outside = 0;
+  for (int32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int32_t c = __ldg(indices + e);
+    float wv = w ? __ldg(w + (eid ? __ldg(eid + e) : e)) : 1.0f;
+    if (pre_scale) wv *= __ldg(pre_scale + c);
+    const int32_t sl = c - n0;
+    const bool inside = sl >= 0 && sl < np;
+    packed[e] = inside ? make_uint2((uint32_t)sl, __float_as_uint(wv)) : make_uint2(PK_OUTSIDE, 0u);
+    outside |= inside ? 0 : 1;
+  }
+  outside = __syncthreads_or(outside);
+  if (threadIdx.x == 0) page_flag[page] = outside;
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
+  acc.x = fmaf(w, x.x, acc.x);
+  acc.y = fmaf(w, x.y, acc.y);
+  acc.z = fmaf(w, x.z, acc.z);
+  acc.w = fmaf(w, x.w, acc.w);
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+struct PkStageLayout {
+  uint32_t x_bytes, pk_bytes, ptr_bytes, nrm_bytes, info_bytes;
+  // stages start on 128-byte boundaries (TMA destination alignment)
+  __host__ __device__ uint32_t stage_bytes() const {
+    return (x_bytes + pk_bytes + ptr_bytes + nrm_bytes + info_bytes + 127u) & ~127u;
+  }
+};
+__host__ __device__ inline PkStageLayout pk_layout(int cs, int32_t np_cap, int32_t ne_cap) {
+  PkStageLayout l;
+  // staged rows (whole TMA boxes) + one all-zero row that padding / outside edges gather from
+  l.x_bytes = ((((uint32_t)np_cap + PK_BOX_SMALL - 1) / PK_BOX_SMALL * PK_BOX_SMALL) + 1) * cs * 4;
+  l.pk_bytes = (((uint32_t)ne_cap + 2) * 8 + 15u) & ~15u;  // +2: the bulk copy starts and ends on even edges
+  l.ptr_bytes = (((uint32_t)np_cap + 1) * 4 + 15u) & ~15u;
+  l.nrm_bytes = ((uint32_t)np_cap * 4 + 15u) & ~15u;
+  l.info_bytes = 32;  // PkItem of the staged item, written by the producer warp
+  return l;
+}
+
+struct PkItem {
+  int32_t n0, np, e0, ne, c0, flag, staged, pad;
+};
+
+struct PkMaps {
+  CUtensorMap big, small;  // x as [rows, f] fp32, boxes CS x 64 rows / CS x 8 rows, no swizzle
+};
+
+struct PkRowArgs {
+  const uint8_t* xb;     // staged x slice [rows][CS] (+ one all-zero row at index zrow), already offset by lane * 16
+  const uint2* spk;      // staged packed edges of the page
+  const int32_t* sptr;   // staged row pointers
+  const float* snrm;     // staged row normalisers
+  uint32_t zrow;
+  bool slow;
+  PkItem it;
+  const int32_t *indptr, *indices, *eid;
+  const float *w, *pre_scale, *row_norm;
+  int mode;
+  const float* x;
+  int64_t ldx;
+  const float* addend;
+  int64_t ldadd;
+  float* y;
+  int64_t ldy;
+  int32_t f;
+  int32_t dbg;  // experiment switches (GTE_SPMM_DBG): 1 = skip the gather loop, 2 = skip the stores, 4 = skip the x staging
+};
+
+// One pass of a row group over R (1 or 2) rows of a staged item: G lanes per row, each lane VV (<= V) 128-bit
+// column chunks, U = 2 edges per step.  Every gather is unconditional: edges past the end of a row, and edges that
+// leave the page, read the all-zero row with weight 0 (0 * 0: no NaN can be manufactured from someone else's Inf),
+// and columns >= f were zero-filled by the TMA unit -- so all R*U*VV loads of a step are in flight together.
+template <int G, int V, int VV, int R>
+__device__ __forceinline__ void pk_row_pass(const PkRowArgs& A, int32_t rl0) {
+  constexpr int CS = G * V * 4;
+  constexpr int ROW_BYTES = CS * 4;
+  constexpr int NG = PK_CONSUMERS / G;
+  constexpr int U = 2;
+  const int lane = threadIdx.x % G;
+  const PkItem& cur = A.it;
+  int col[VV];
+  bool on[VV];
+#pragma unroll
+  for (int v = 0; v < VV; ++v) {
+    col[v] = cur.c0 + (lane + v * G) * 4;
+    on[v] = col[v] < A.f;
+  }
+  int64_t row[R];
+  int32_t beg[R], end[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    const int32_t rl = rl0 + q * NG;
+    row[q] = (int64_t)cur.n0 + rl;
+    if (cur.staged) {
+      beg[q] = A.sptr[rl] - cur.e0;
+      end[q] = A.sptr[rl + 1] - cur.e0;
+    } else {
+      beg[q] = __ldg(A.indptr + row[q]) - cur.e0;
+      end[q] = __ldg(A.indptr + row[q] + 1) - cur.e0;
+    }
+  }
+  // row-end operands first: their latency overlaps the neighbour loop
+  float4 av[R][VV];
+  float nrm[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+#pragma unroll
+    for (int v = 0; v < VV; ++v) {
+      av[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (A.addend && on[v]) av[q][v] = __ldg(reinterpret_cast<const float4*>(A.addend + row[q] * A.ldadd + col[v]));
+    }
+    nrm[q] = 1.0f;
+    if (A.mode == GTE_AGG_SUM_NORM) nrm[q] = cur.staged ? A.snrm[rl0 + q * NG] : __ldg(A.row_norm + row[q]);
+  }
+  float4 acc[R][VV];
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int v = 0; v < VV; ++v) acc[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cur.staged) {
+    int32_t len = end[0] - beg[0];
+    if (R == 2) len = max(len, end[R - 1] - beg[R - 1]);
+    if (A.dbg & 1) len = 0;
+    auto load_meta = [&](int32_t j, uint2 (&m)[R][U]) {
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int32_t e = beg[q] + j + u;
+          m[q][u] = make_uint2(PK_OUTSIDE, 0u);
+          if (e < end[q]) m[q][u] = A.spk[e];
+        }
+    };
+    auto step = [&](const uint2 (&m)[R][U]) {
+      float4 xv[R][U][VV];
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint8_t* xr = A.xb + min(m[q][u].x, A.zrow) * ROW_BYTES;  // PK_OUTSIDE -> the zero row
+#pragma unroll
+          for (int v = 0; v < VV; ++v) xv[q][u][v] = *reinterpret_cast<const float4*>(xr + v * (G * 16));
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)  // edge order inside each row is preserved
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+#pragma unroll
+          for (int v = 0; v < VV; ++v) fma4(acc[q][v], __uint_as_float(m[q][u].y), xv[q][u][v]);
+    };
+    // two metadata buffers alternate (no register rotation): the next step's metadata is in flight under this
+    // step's gathers
+    uint2 ma[R][U], mb[R][U];
+    load_meta(0, ma);
+    for (int32_t j = 0; j < len; j += 2 * U) {
+      load_meta(j + U, mb);
+      step(ma);
+      if (j + U >= len) break;
+      load_meta(j + 2 * U, ma);
+      step(mb);
+    }
+  }
+  if (A.slow) {  // rare: edges leaving the page (not block diagonal) or a page larger than the staging capacity
+#pragma unroll 1
+    for (int q = 0; q < R; ++q) {
+      for (int32_t j = beg[q]; j < end[q]; ++j) {
+        const int32_t c = __ldg(A.indices + cur.e0 + j);
+        const int32_t sl = c - cur.n0;
+        if (cur.staged && sl >= 0 && sl < cur.np) continue;  // already accumulated from shared memory
+        float wt = A.w ? __ldg(A.w + (A.eid ? __ldg(A.eid + cur.e0 + j) : cur.e0 + j)) : 1.0f;
+        if (A.pre_scale) wt *= __ldg(A.pre_scale + c);
+#pragma unroll
+        for (int v = 0; v < VV; ++v)
+          if (on[v]) {
+            const float4 xg = __ldg(reinterpret_cast<const float4*>(A.x + (int64_t)c * A.ldx + col[v]));
+            if (q == 0) fma4(acc[0][v], wt, xg);
+            else fma4(acc[R - 1][v], wt, xg);
+          }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    const int32_t deg = end[q] - beg[q];
+    const float d = (float)(deg > 1 ? deg : 1);
+#pragma unroll
+    for (int v = 0; v < VV; ++v) {
+      if (!on[v]) continue;
+      float4 r = acc[q][v];
+      if (A.mode == GTE_AGG_MEAN) {
+        r.x /= d; r.y /= d; r.z /= d; r.w /= d;
+      } else if (A.mode == GTE_AGG_SUM_NORM) {
+        r.x *= nrm[q]; r.y *= nrm[q]; r.z *= nrm[q]; r.w *= nrm[q];
+      }
+      if (A.addend) {
+        r.x += av[q][v].x; r.y += av[q][v].y; r.z += av[q][v].z; r.w += av[q][v].w;
+      }
+      if (!(A.dbg & 2) || r.x == 12345.678f) *reinterpret_cast<float4*>(A.y + row[q] * A.ldy + col[v]) = r;
+    }
+  }
+}
+
+template <int G, int V, int VV>
+__device__ __forceinline__ void pk_rows(const PkRowArgs& A) {
+  constexpr int NG = PK_CONSUMERS / G;
+  const int grp = threadIdx.x / G;
+  for (int32_t rl0 = grp; rl0 < A.it.np; rl0 += 2 * NG) {
+    if (rl0 + NG < A.it.np)
+      pk_row_pass<G, V, VV, 2>(A, rl0);
+    else
+      pk_row_pass<G, V, VV, 1>(A, rl0);  // odd row out: no padded second row (its gathers would be pure waste)
+  }
+}
+
+// Warp-specialised: warps 0..15 reduce rows (consumers), warp 16 stages items (producer).  Two shared-memory
+// stages cycle through full[s] (producer -> consumers: TMA bytes landed + small copies stored) and empty[s]
+// (consumer warps -> producer: stage may be overwritten) mbarriers; there is no CTA-wide barrier in the loop, so a
+// warp that finishes its rows early starts on the next item at once and the warps drift out of lock step.
+template <int G, int V>
+__global__ void __launch_bounds__(PK_THREADS, 1)
+    k_spmm_paged_pk(const __grid_constant__ PkMaps maps, const int32_t* __restrict__ indptr,
+                    const uint2* __restrict__ packed, const int32_t* __restrict__ page_flag,
+                    const int32_t* __restrict__ indices, const int32_t* __restrict__ eid, const float* __restrict__ w,
+                    const float* __restrict__ pre_scale, const float* __restrict__ row_norm, int mode,
+                    const float* __restrict__ x, int64_t ldx, const float* __restrict__ addend, int64_t ldadd,
+                    float* __restrict__ y, int64_t ldy, const int32_t* __restrict__ page_off, int32_t f, int32_t num_items,
+                    int32_t nslices, int32_t items_per_cta, int32_t np_cap, int32_t ne_cap, int32_t dbg) {
+  extern __shared__ __align__(128) uint8_t pk_smem[];
+  constexpr int CS = G * V * 4;            // columns per slice
+  constexpr int ROW_BYTES = CS * 4;
+  const PkStageLayout L = pk_layout(CS, np_cap, ne_cap);
+  const uint32_t stage_bytes = L.stage_bytes();
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(pk_smem);
+  const uint32_t bars = smem0 + 2 * stage_bytes;  // full[0], full[1], empty[0], empty[1]
+  const uint32_t off_pk = L.x_bytes, off_ptr = off_pk + L.pk_bytes, off_nrm = off_ptr + L.ptr_bytes,
+                 off_info = off_nrm + L.nrm_bytes;
+  const int tid = threadIdx.x;
+
+  const int item_beg = blockIdx.x * items_per_cta;
+  const int item_end = min(num_items, item_beg + items_per_cta);
+  if (item_beg >= item_end) return;
+  if (tid == 0) {
+    mbar_init(bars, 2);        // producer: expect_tx arrive + "small copies stored" arrive
+    mbar_init(bars + 8, 2);
+    mbar_init(bars + 16, PK_CONSUMERS / 32);  // one arrive per consumer warp
+    mbar_init(bars + 24, PK_CONSUMERS / 32);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.big);
+    tma_prefetch_desc(&maps.small);
+  }
+  for (int i = tid; i < 2 * (ROW_BYTES / 4); i += PK_THREADS) {  // the all-zero row of both stages
+    const int st = i / (ROW_BYTES / 4), c = i % (ROW_BYTES / 4);
+    reinterpret_cast<float*>(pk_smem + (size_t)st * stage_bytes + L.x_bytes - ROW_BYTES)[c] = 0.f;
+  }
+  __syncthreads();
+
+  if (tid >= PK_CONSUMERS) {
+    // ================================== producer warp ==================================
+    const int pl = tid - PK_CONSUMERS;  // lane
+    auto load_item = [&](int item) {
+      PkItem it = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (item < item_end) {
+        const int page = item / nslices;
+        it.c0 = (item - page * nslices) * CS;
+        it.n0 = __ldg(page_off + page);
+        it.np = __ldg(page_off + page + 1) - it.n0;
+        it.e0 = __ldg(indptr + it.n0);
+        it.ne = __ldg(indptr + it.n0 + it.np) - it.e0;
+        it.flag = __ldg(page_flag + page);
+        it.staged = (it.np <= np_cap && it.ne <= ne_cap) ? 1 : 0;
+      }
+      return it;
+    };
+    PkItem it = load_item(item_beg);
+    for (int item = item_beg, s = 0, k = 0; item < item_end; ++item, s ^= 1, ++k) {
+      const PkItem nxt = load_item(item + 1);  // in flight while this item is staged
+      if (k >= 2) mbar_wait_backoff(bars + 16 + s * 8, (uint32_t)((k >> 1) - 1) & 1u);  // consumers released stage s
+      uint8_t* sbase = pk_smem + (size_t)s * stage_bytes;
+      const uint32_t sx = smem0 + s * stage_bytes;
+      const uint32_t bar = bars + s * 8;
+      if (pl == 0) {
+        *reinterpret_cast<PkItem*>(sbase + off_info) = it;
+        if (it.staged) {
+          const int nbig = (dbg & 4) ? 0 : it.np / PK_BOX_BIG;
+          const int nsmall = (dbg & 4) ? 0 : (it.np - nbig * PK_BOX_BIG + PK_BOX_SMALL - 1) / PK_BOX_SMALL;
+          const int e_lo = it.e0 & ~1;  // 16-byte aligned start of the bulk copy
+          const uint32_t pk_copy = it.ne > 0 ? (uint32_t)((it.e0 + it.ne - e_lo + 1) & ~1) * 8u : 0u;
+          mbar_expect_tx(bar, (uint32_t)(nbig * PK_BOX_BIG + nsmall * PK_BOX_SMALL) * ROW_BYTES + pk_copy);
+          for (int b = 0; b < nbig; ++b)
+            tma_load_2d(sx + b * PK_BOX_BIG * ROW_BYTES, &maps.big, bar, it.c0, it.n0 + b * PK_BOX_BIG);
+          for (int b = 0; b < nsmall; ++b)
+            tma_load_2d(sx + (nbig * PK_BOX_BIG + b * PK_BOX_SMALL) * ROW_BYTES, &maps.small, bar, it.c0,
+                        it.n0 + nbig * PK_BOX_BIG + b * PK_BOX_SMALL);
+          if (pk_copy) bulk_load_1d(sx + off_pk, packed + e_lo, pk_copy, bar);
+        } else {
+          mbar_arrive(bar);  // nothing in flight: the page runs from global memory
+        }
+      }
+      if (it.staged) {  // row pointers and normalisers: plain loads + shared stores by the 32 producer lanes
+        int32_t* sptr = reinterpret_cast<int32_t*>(sbase + off_ptr);
+        float* snrm = reinterpret_cast<float*>(sbase + off_nrm);
+        const int32_t* ip = indptr + it.n0;
+        for (int i = pl; i <= it.np; i += 32) sptr[i] = __ldg(ip + i);
+        if (mode == GTE_AGG_SUM_NORM) {
+          const float* nr = row_norm + it.n0;
+          for (int i = pl; i < it.np; i += 32) snrm[i] = __ldg(nr + i);
+        }
+      }
+      if (addend) {  // pull the addend rows of this slice into L2 ahead of the consumers
+        for (int i = pl; i < it.np * 2; i += 32) {
+          const int col = it.c0 + (i & 1) * 32;
+          if (col < f) asm volatile("prefetch.global.L2 [%0];" ::"l"(addend + (int64_t)(it.n0 + (i >> 1)) * ldadd + col));
+        }
+      }
+      __syncwarp();
+      if (pl == 0) mbar_arrive(bar);  // release: item info + small copies are in shared memory
+      it = nxt;
+    }
+  } else {
+    // ================================== consumer warps ==================================
+    const int lane = tid % G;
+    PkRowArgs A;
+    A.zrow = L.x_bytes / ROW_BYTES - 1;
+    A.indptr = indptr; A.indices = indices; A.eid = eid; A.w = w; A.pre_scale = pre_scale; A.row_norm = row_norm;
+    A.mode = mode; A.x = x; A.ldx = ldx; A.addend = addend; A.ldadd = ldadd; A.y = y; A.ldy = ldy; A.f = f; A.dbg = dbg;
+    for (int item = item_beg, s = 0, k = 0; item < item_end; ++item, s ^= 1, ++k) {
+      mbar_wait(bars + s * 8, (uint32_t)(k >> 1) & 1u);
+      const uint8_t* sbase = pk_smem + (size_t)s * stage_bytes;
+      A.it = *reinterpret_cast<const PkItem*>(sbase + off_info);
+      A.xb = sbase + lane * 16;
+      A.spk = reinterpret_cast<const uint2*>(sbase + off_pk) + (A.it.e0 & 1);  // entry j of the page: spk[j]
+      A.sptr = reinterpret_cast<const int32_t*>(sbase + off_ptr);
+      A.snrm = reinterpret_cast<const float*>(sbase + off_nrm);
+      A.slow = !A.it.staged || A.it.flag != 0;
+      // the last slice of a row may need only the first of the two column chunks (F = 218: 7 of 16 chunks)
+      if (V == 2 && A.it.c0 + G * 4 >= f)
+        pk_rows<G, V, 1>(A);
+      else
+        pk_rows<G, V, V>(A);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(bars + 16 + s * 8);  // this warp is done with stage s
+    }
+  }
+}
+
+static size_t pk_smem_bytes(int cs, int32_t np_cap, int32_t ne_cap) {
+  return 2 * (size_t)pk_layout(cs, np_cap, ne_cap).stage_bytes() + 32;
+}
+
+constexpr size_t PK_SMEM_MAX = 227 * 1024;
+
+// (G, V) for feature width f and page capacity, or G = 0 when two stages do not fit in shared memory
+static void pk_pick(int32_t f, int32_t np_cap, int32_t ne_cap, int* G, int* V) {
+  const int fv = (f + 3) / 4;
+  *G = 0;
+  *V = 0;
+  if (fv > 8 && pk_smem_bytes(64, np_cap, ne_cap) <= PK_SMEM_MAX) {
+    *G = 8, *V = 2;
+  } else if (fv > 4 && pk_smem_bytes(32, np_cap, ne_cap) <= PK_SMEM_MAX) {
+    *G = 8, *V = 1;
+  } else if (pk_smem_bytes(16, np_cap, ne_cap) <= PK_SMEM_MAX) {
+    *G = 4, *V = 1;
+  }
+}
+
+static int pk_dbg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GTE_SPMM_DBG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <int G, int V>
+static int launch_spmm_paged_pk(const int32_t* indptr, const uint2* packed, const int32_t* page_flag,
+                                const int32_t* indices, const int32_t* eid, const float* w, const float* pre_scale,
+                                const float* row_norm, int mode, const float* x, int64_t ldx, const float* addend,
+                                int64_t ldadd, float* y, int64_t ldy, const int32_t* page_off, int32_t num_pages,
+                                int32_t np_cap, int32_t ne_cap, int32_t n_rows, int32_t f, cudaStream_t st) {
+  constexpr int CS = G * V * 4;
+  const size_t smem = pk_smem_bytes(CS, np_cap, ne_cap);
+  static size_t configured = 0;
+  static int occ_smem = -1, occ = 1;
+  if (smem > configured) {
+    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_paged_pk<G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "k_spmm_paged_pk(smem attr)");
+    configured = smem;
+  }
+  if (occ_smem != (int)smem) {
+    int o = 1;
+    GTE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_spmm_paged_pk<G, V>, PK_THREADS, smem),
+                   "k_spmm_paged_pk(occupancy)");
+    occ = o < 1 ? 1 : o;
+    occ_smem = (int)smem;
+  }
+  PkMaps maps;
+  {
+    int rc = make_tmap_2d(&maps.big, x, n_rows, f, ldx, CS, PK_BOX_BIG, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = make_tmap_2d(&maps.small, x, n_rows, f, ldx, CS, PK_BOX_SMALL, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  const int nslices = (int)ceil_div64((f + 3) / 4, G * V);
+  const int64_t items = (int64_t)num_pages * nslices;
+  GTE_CHECK_ARG(items < (int64_t)1 << 31, "gte_spmm_paged_packed: too many (page, slice) items");
+  int grid = (int)(items < (int64_t)sm_count() * occ ? items : (int64_t)sm_count() * occ);
+  const int per = (int)ceil_div64(items, grid);
+  grid = (int)ceil_div64(items, per);
+  k_spmm_paged_pk<G, V><<<grid, PK_THREADS, smem, st>>>(maps, indptr, packed, page_flag, indices, eid, w, pre_scale, row_norm,
+                                                       mode, x, ldx, addend, ldadd, y, ldy, page_off, f, (int32_t)items,
+                                                       nslices, per, np_cap, ne_cap, pk_dbg());
+  GTE_CHECK_LAUNCH("k_spmm_paged_pk");
+  return GTE_OK;
+}
+
 }  // namespace gte
 
 using namespace gte;
@@ -394,4 +848,58 @@ extern "C" int gte_spmm_paged(const int32_t* indptr, const int32_t* indices, con
   if (G == 16) GTE_PAGED_GO(16);
   GTE_PAGED_GO(8);
 #undef GTE_PAGED_GO
+}
+
+extern "C" int gte_paged_pack_edges(const int32_t* indptr, const int32_t* indices, const int32_t* eid, const float* w,
+                                    const float* pre_scale, const int32_t* page_off, int32_t num_pages,
+                                    uint64_t* packed, int32_t* page_flag, gte_stream_t stream) {
+  GTE_CHECK_ARG(num_pages >= 0, "gte_paged_pack_edges: negative size");
+  if (num_pages == 0) return GTE_OK;
+  GTE_CHECK_ARG(indptr && indices && page_off && packed && page_flag, "gte_paged_pack_edges: null argument");
+  GTE_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 7u) == 0, "gte_paged_pack_edges: packed must be 8-byte aligned");
+  k_paged_pack_edges<<<num_pages, 256, 0, as_stream(stream)>>>(indptr, indices, eid, w, pre_scale, page_off,
+                                                              reinterpret_cast<uint2*>(packed), page_flag);
+  GTE_CHECK_LAUNCH("k_paged_pack_edges");
+  return GTE_OK;
+}
+
+extern "C" size_t gte_spmm_paged_packed_smem_bytes(int32_t max_page_nodes, int32_t max_page_edges, int32_t f) {
+  if (max_page_nodes < 0 || max_page_edges < 0 || f <= 0) return 0;
+  int G, V;
+  pk_pick(f, max_page_nodes, max_page_edges, &G, &V);
+  return G ? pk_smem_bytes(G * V * 4, max_page_nodes, max_page_edges) : 0;
+}
+
+extern "C" int gte_spmm_paged_packed(const int32_t* indptr, const uint64_t* packed, const int32_t* page_flag,
+                                     const int32_t* indices, const int32_t* eid, const float* w, const float* pre_scale,
+                                     const float* row_norm, int mode, const float* x, int64_t ldx, const float* addend,
+                                     int64_t ldadd, float* y, int64_t ldy, const int32_t* page_off, int32_t num_pages,
+                                     int32_t max_page_nodes, int32_t max_page_edges, int32_t n_rows, int32_t f,
+                                     gte_stream_t stream) {
+  GTE_CHECK_ARG(n_rows >= 0 && f >= 0 && num_pages >= 0 && max_page_nodes >= 0 && max_page_edges >= 0,
+                "gte_spmm_paged_packed: negative size");
+  GTE_CHECK_ARG(mode == GTE_AGG_SUM || mode == GTE_AGG_SUM_NORM || mode == GTE_AGG_MEAN, "gte_spmm_paged_packed: bad mode %d",
+                mode);
+  if (n_rows == 0 || f == 0 || num_pages == 0) return GTE_OK;
+  GTE_CHECK_ARG(indptr && packed && page_flag && indices && x && y && page_off, "gte_spmm_paged_packed: null argument");
+  GTE_CHECK_ARG(mode != GTE_AGG_SUM_NORM || row_norm, "gte_spmm_paged_packed: SUM_NORM needs row_norm");
+  GTE_CHECK_ARG(ldx >= f && ldy >= f && (!addend || ldadd >= f), "gte_spmm_paged_packed: leading dimension < f");
+  GTE_CHECK_ARG(x != y, "gte_spmm_paged_packed: x and y must not alias");
+  const bool vec = aligned16(x) && aligned16(y) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
+                   (!addend || (aligned16(addend) && ldadd % 4 == 0));
+  int G, V;
+  pk_pick(f, max_page_nodes, max_page_edges, &G, &V);
+  if (!vec || G == 0)
+    return fail(GTE_ERR_UNSUPPORTED,
+                "gte_spmm_paged_packed: operands not 16-byte aligned or pages too large to stage (query "
+                "gte_spmm_paged_packed_smem_bytes first); use gte_spmm_paged");
+  cudaStream_t st = as_stream(stream);
+  const uint2* pk = reinterpret_cast<const uint2*>(packed);
+#define GTE_PK_GO(GG, VV)                                                                                                  \
+  return launch_spmm_paged_pk<GG, VV>(indptr, pk, page_flag, indices, eid, w, pre_scale, row_norm, mode, x, ldx, addend, \
+                                      ldadd, y, ldy, page_off, num_pages, max_page_nodes, max_page_edges, n_rows, f, st)
+  if (G == 8 && V == 2) GTE_PK_GO(8, 2);
+  if (G == 8) GTE_PK_GO(8, 1);
+  GTE_PK_GO(4, 1);
+#undef GTE_PK_GO
 }

@@ -179,16 +179,7 @@ class PageGraphBatch:
         return v
 
     def _weights(self, which: str, w: torch.Tensor) -> torch.Tensor:
-        if w.dtype != torch.float32:
-            w = w.float()
-        if w.dim() != 1:
-            if w.dim() == 2 and w.shape[1] == 1:
-                w = w.reshape(-1)
-            else:
-                raise GteError(f"edge weights must be [E] (loader.py:344), got {tuple(w.shape)}")
-        if w.numel() != self.num_edges():
-            raise GteError(f"edge weights: {w.numel()} values for {self.num_edges()} edges")
-        w = w.contiguous()
+        w = _edge_weight_1d(w, self.num_edges())
         key = (w.data_ptr(), w._version, int(w.numel()))
         hit = self._cache.get(which)
         if hit is not None and hit[0] == key:
@@ -198,12 +189,40 @@ class PageGraphBatch:
         self._cache[which] = (key, out, w)  # holding `w` keeps its address from being recycled
         return out
 
+    def packed_edges(self, which: str, w: torch.Tensor) -> "ops.PackedEdges":
+        """Edges of the CSC (``which='csc'``, forward) or of the CSR with the source-side scale
+        ``norm[dst]`` folded in (``'csr'``, backward), packed once per batch for the page kernel."""
+        w = _edge_weight_1d(w, self.num_edges())
+        key = (w.data_ptr(), w._version, int(w.numel()))
+        name = "pk_" + which
+        hit = self._cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        indptr, indices, eid = self.csc() if which == "csc" else self.csr()
+        pk = ops.paged_pack_edges(indptr, indices, w, self.pages(), eid=eid,
+                                  pre_scale=self.norm() if which == "csr" else None)
+        self._cache[name] = (key, pk, w)
+        return pk
+
     def weights_csc(self, w: torch.Tensor) -> torch.Tensor:
         """Edge weights permuted into CSC row order (``edata['feat'][eid]``)."""
         return self._weights("w_csc", w)
 
     def weights_csr(self, w: torch.Tensor) -> torch.Tensor:
         return self._weights("w_csr", w)
+
+
+def _edge_weight_1d(w: torch.Tensor, num_edges: int) -> torch.Tensor:
+    if w.dtype != torch.float32:
+        w = w.float()
+    if w.dim() != 1:
+        if w.dim() == 2 and w.shape[1] == 1:
+            w = w.reshape(-1)
+        else:
+            raise GteError(f"edge weights must be [E] (loader.py:344), got {tuple(w.shape)}")
+    if w.numel() != num_edges:
+        raise GteError(f"edge weights: {w.numel()} values for {num_edges} edges")
+    return w.contiguous()
 
 
 def page_table(batch_num_nodes, batch_num_edges, num_nodes: int, device):

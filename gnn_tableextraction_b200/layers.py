@@ -83,6 +83,18 @@ def use_umma_dw(n: int, fo: int, k1: int, k2: int, db_needed: bool, *mats) -> bo
     return GEMM_MODE == "umma" or n >= UMMA_MIN_ROWS
 
 
+SPMM_MODE = os.environ.get("GTE_SPMM", "auto")  # auto | packed | paged | rows (diagnostics / A-B runs)
+
+
+def _use_packed(g: PageGraphBatch, x: torch.Tensor, addend: Optional[torch.Tensor]) -> bool:
+    """The persistent page kernel needs a page table, 16-byte aligned rows and two stages of the
+    largest page in shared memory; everything else goes to gte_spmm_paged / gte_spmm."""
+    if SPMM_MODE in ("paged", "rows"):
+        return False
+    return (ops.paged_packed_supported(g.pages(), x.shape[1]) and ops._aligned_mat(x)
+            and (addend is None or ops._aligned_mat(addend)))
+
+
 def _agg_mode(agg: str) -> int:
     return _lib.GTE_AGG_SUM_NORM if agg == GCN else _lib.GTE_AGG_MEAN
 
@@ -91,6 +103,9 @@ def aggregate_forward(g: PageGraphBatch, h: torch.Tensor, w_edge: torch.Tensor, 
                       addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``update_all(u_mul_e, sum|mean)`` (+ ``* norm``): models.py:53-54,69-71,149."""
     indptr, indices, _ = g.csc()
+    if _use_packed(g, h, addend):
+        return ops.spmm_packed(indptr, g.packed_edges("csc", w_edge), h, g.pages(), mode=_agg_mode(agg),
+                               row_norm=g.norm() if agg == GCN else None, addend=addend)
     return ops.spmm(indptr, indices, g.weights_csc(w_edge), h, mode=_agg_mode(agg),
                     row_norm=g.norm() if agg == GCN else None, addend=addend, pages=g.pages())
 
@@ -99,6 +114,9 @@ def aggregate_backward(g: PageGraphBatch, d_out: torch.Tensor, w_edge: torch.Ten
                        addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     """d h[u] = sum_{u->v} w_e * norm[v] * d_out[v] (+ addend[u]) on the CSR (reverse graph)."""
     indptr, indices, _ = g.csr()
+    if _use_packed(g, d_out, addend):
+        return ops.spmm_packed(indptr, g.packed_edges("csr", w_edge), d_out, g.pages(), mode=_lib.GTE_AGG_SUM,
+                               addend=addend)
     return ops.spmm(indptr, indices, g.weights_csr(w_edge), d_out, mode=_lib.GTE_AGG_SUM, pre_scale=g.norm(),
                     addend=addend, pages=g.pages())
 

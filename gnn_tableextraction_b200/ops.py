@@ -176,6 +176,68 @@ def spmm(indptr, indices, w, x, *, mode=_lib.GTE_AGG_SUM, row_norm=None, pre_sca
     return out
 
 
+class PackedEdges:
+    """Edges of one direction of a page batch in the layout ``gte_spmm_paged_packed`` stages:
+    ``packed`` [E] int64 = (page-local source row | weight * source scale), ``page_flag`` [P] int32.
+    Holds the raw arrays the kernel's slow path (edges leaving a page) falls back to."""
+
+    __slots__ = ("packed", "page_flag", "indices", "eid", "w", "pre_scale")
+
+    def __init__(self, packed, page_flag, indices, eid, w, pre_scale):
+        self.packed, self.page_flag, self.indices, self.eid, self.w, self.pre_scale = packed, page_flag, indices, eid, w, pre_scale
+
+
+def paged_packed_supported(pages, f: int) -> bool:
+    """Do two shared-memory stages of the largest page fit (``gte_spmm_paged_packed_smem_bytes`` > 0)?"""
+    if pages is None or pages[1] <= 0 or f <= 0:
+        return False
+    return lib().gte_spmm_paged_packed_smem_bytes(int(pages[2]), int(pages[3]), int(f)) > 0
+
+
+def paged_pack_edges(indptr, indices, w, pages, *, eid=None, pre_scale=None) -> PackedEdges:
+    """Pack one direction's edges once per batch: ``w`` is in row order, or in edge order with ``eid``
+    (then ``edata['feat'][eid]`` is folded into the packing); ``pre_scale`` is the source-side scale."""
+    page_off, num_pages = pages[0], pages[1]
+    _req_cuda(indptr, indices, w, eid, pre_scale, page_off)
+    e = indices.numel()
+    packed = torch.empty(e + 2, dtype=torch.int64, device=indices.device)  # 16-byte bulk copies may over-read one entry
+    flag = torch.empty(max(num_pages, 1), dtype=torch.int32, device=indices.device)
+    check(
+        lib().gte_paged_pack_edges(_vec(indptr, "indptr", torch.int32), _vec(indices, "indices", torch.int32),
+                                   _vec(eid, "eid", torch.int32, e), _vec(w, "w", n=e), _vec(pre_scale, "pre_scale"),
+                                   _vec(page_off, "page_off", torch.int32, num_pages + 1), num_pages, packed.data_ptr(),
+                                   flag.data_ptr(), _stream()),
+        "gte_paged_pack_edges",
+    )
+    return PackedEdges(packed, flag, indices, eid, w, pre_scale)
+
+
+def spmm_packed(indptr, pk: PackedEdges, x, pages, *, mode=_lib.GTE_AGG_SUM, row_norm=None, addend=None, out=None):
+    """``spmm`` on pre-packed page edges (the persistent, double-buffered kernel); same result."""
+    xp, ldx, f = _mat(x, "spmm.x")
+    n_rows = indptr.numel() - 1
+    if out is None:
+        out = empty_padded(n_rows, f, x.device)
+    yp, ldy, fy = _mat(out, "spmm.y")
+    if fy != f or out.shape[0] != n_rows:
+        raise GteError("spmm: output shape mismatch")
+    ap, lda = None, 0
+    if addend is not None:
+        ap, lda, fa = _mat(addend, "spmm.addend")
+        if fa != f or addend.shape[0] != n_rows:
+            raise GteError("spmm: addend shape mismatch")
+    page_off, num_pages, max_nodes, max_edges = pages
+    check(
+        lib().gte_spmm_paged_packed(_vec(indptr, "indptr", torch.int32), pk.packed.data_ptr(), pk.page_flag.data_ptr(),
+                                    _vec(pk.indices, "indices", torch.int32), _vec(pk.eid, "eid", torch.int32),
+                                    _vec(pk.w, "w"), _vec(pk.pre_scale, "pre_scale"), _vec(row_norm, "row_norm", n=n_rows),
+                                    mode, xp, ldx, ap, lda, yp, ldy, _vec(page_off, "page_off", torch.int32, num_pages + 1),
+                                    num_pages, max_nodes, max_edges, n_rows, f, _stream()),
+        "gte_spmm_paged_packed",
+    )
+    return out
+
+
 # ------------------------------------------------------------------ dense ---
 def linear_fwd(x1, x2, W, bias, out=None, w_col0: int = 0):
     """z = x1 W[:, c0:c0+k1]^T + x2 W[:, c0+k1:c0+k1+k2]^T + bias (x2 may be None)."""

@@ -143,6 +143,34 @@ int gte_spmm_paged(const int32_t* indptr, const int32_t* indices, const float* w
                    int32_t max_page_nodes, int32_t max_page_edges, int32_t n_rows, int32_t f,
                    gte_stream_t stream);
 
+/*
+ * The headline conv-layer kernel: same contract and same sums (row order, deterministic) as
+ * gte_spmm_paged, on edges pre-packed per (graph, direction) by gte_paged_pack_edges:
+ *   packed[j] = (page-local source row of edge j | bits of w[j] * pre_scale[c_j]) as one 64-bit word,
+ *   page_flag[p] = 1 when page p has an edge whose source lies outside the page (served by a slow
+ *   global path from the raw `indices` / `w` / `eid` / `pre_scale`, so the result stays correct).
+ * `w` is either in row order (`eid` NULL) or in original edge order with `eid` the row-order -> edge
+ * map from gte_csx_from_coo (w_row[j] = w[eid[j]]: the edge-weight permutation `edata['feat'][eid]`
+ * is folded into the packing).  The kernel is persistent (one CTA per SM over a contiguous range of
+ * (page, 64-column slice) items) and double buffered: the cp.async staging of the next item overlaps
+ * the shared-memory gather/reduce of the current one.  gte_spmm_paged_packed_smem_bytes returns 0
+ * when two stages of the largest page do not fit in shared memory (use gte_spmm_paged then);
+ * gte_spmm_paged_packed itself returns GTE_ERR_UNSUPPORTED in that case or for unaligned operands.
+ * Workspaces (caller-owned): packed [E + 1] uint64, 16-byte aligned (the 16-byte bulk copies that stage a page's
+ * edges may read one entry past the last edge), page_flag [num_pages] int32.
+ */
+int gte_paged_pack_edges(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
+                         const float* w, const float* pre_scale, const int32_t* page_off,
+                         int32_t num_pages, uint64_t* packed, int32_t* page_flag, gte_stream_t stream);
+size_t gte_spmm_paged_packed_smem_bytes(int32_t max_page_nodes, int32_t max_page_edges, int32_t f);
+int gte_spmm_paged_packed(const int32_t* indptr, const uint64_t* packed, const int32_t* page_flag,
+                          const int32_t* indices, const int32_t* eid, const float* w,
+                          const float* pre_scale, const float* row_norm, int mode,
+                          const float* x, int64_t ldx, const float* addend, int64_t ldadd,
+                          float* y, int64_t ldy, const int32_t* page_off, int32_t num_pages,
+                          int32_t max_page_nodes, int32_t max_page_edges, int32_t n_rows, int32_t f,
+                          gte_stream_t stream);
+
 /* ------------------------------------------------- dense projection ----- */
 /*
  * z[n,fo] = x1[n,k1] W[:, 0:k1]^T + x2[n,k2] W[:, k1:k1+k2]^T + bias

@@ -25,8 +25,11 @@ def time_ms(fn, warm=3, it=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / it
 
-for E_target in (1_000_000, 5_000_000, 20_000_000, 50_000_000):
-    for deg in (5, 10, 20, 40):
+E_TARGETS = [int(v) for v in os.environ.get("SWEEP_E", "1000000,5000000,20000000,50000000").split(",")]
+DEGS = [int(v) for v in os.environ.get("SWEEP_DEG", "5,10,20,40").split(",")]
+FS = [int(v) for v in os.environ.get("SWEEP_F", "32,64,128,218,256,512").split(",")]
+for E_target in E_TARGETS:
+    for deg in DEGS:
         n = max(PAGE, (E_target // deg) // PAGE * PAGE)
         e = n * deg
         pages = n // PAGE
@@ -38,7 +41,7 @@ for E_target in (1_000_000, 5_000_000, 20_000_000, 50_000_000):
         w = torch.rand(e, device=DEV, generator=gen)
         norm = ops.degree_norm(indptr)
         page_off = torch.arange(pages + 1, device=DEV, dtype=torch.int32) * PAGE
-        for f in (32, 64, 128, 218, 256, 512):
+        for f in FS:
             if n * f * 4 * 2 > 60e9:
                 continue
             x = ops.empty_padded(n, f, DEV); x.normal_(generator=gen)
@@ -50,10 +53,18 @@ for E_target in (1_000_000, 5_000_000, 20_000_000, 50_000_000):
                 ms = time_ms(lambda: ops.spmm(indptr, idx, w, x, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm, out=y, pages=pg))
                 rec[name] = {"ms": round(ms, 4), "GBs": round(alg / ms / 1e6, 1), "frac_measured": round(alg / ms / 1e6 / pk, 3),
                              "frac_8TBs": round(alg / ms / 1e6 / 8000, 3)}
+            pg = (page_off, pages, PAGE, PAGE * deg)
+            if ops.paged_packed_supported(pg, f):  # the persistent double-buffered kernel on pre-packed edges
+                pke = ops.paged_pack_edges(indptr, idx_paged, w, pg)
+                ms = time_ms(lambda: ops.spmm_packed(indptr, pke, x, pg, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm, out=y))
+                rec["packed"] = {"ms": round(ms, 4), "GBs": round(alg / ms / 1e6, 1), "frac_measured": round(alg / ms / 1e6 / pk, 3),
+                                 "frac_8TBs": round(alg / ms / 1e6 / 8000, 3)}
+                rec["pack_ms"] = round(time_ms(lambda: ops.paged_pack_edges(indptr, idx_paged, w, pg)), 4)
+                del pke
             out.append(rec)
             print(json.dumps(rec), flush=True)
             del x, y
         del indptr, idx_paged, idx_rand, w, norm
         torch.cuda.empty_cache()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump({"peak_hbm_gbs_measured": pk, "rows": out}, open(os.path.join(ROOT, "gpurun_out", "conv_sweep.json"), "w"), indent=0)
+json.dump({"peak_hbm_gbs_measured": pk, "rows": out}, open(os.path.join(ROOT, "gpurun_out", os.environ.get("SWEEP_OUT", "conv_sweep.json")), "w"), indent=0)

@@ -416,6 +416,71 @@ def test_spmm_paged_equals_generic(f):
         assert torch.equal(ops.spmm(ip, ix, w_row, x, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm), b)
 
 
+@pytest.mark.parametrize("f", [3, 9, 13, 20, 33, 64, 100, 218, 300, 512])
+@pytest.mark.parametrize("ragged", [True, False])
+def test_spmm_paged_packed_equals_generic(f, ragged):
+    """persistent double-buffered kernel on pre-packed edges == generic row kernel, bit for bit
+    (forward CSC with norm / mean, backward CSR with norm[dst] folded into the packing + addend)"""
+    pages = synth.make_pages(41, ragged=ragged, k=7, n=120)
+    s, d, w, noff, _ = csx.batch_coo(pages)
+    n = int(noff[-1])
+    ip, ix, ei = ops.csx_from_coo(_i32(d), _i32(s), n)
+    wd = _f32(w)
+    w_row = ops.gather_f32(wd, ei)
+    norm = ops.degree_norm(ip)
+    x = _padded(torch.randn(n, f))
+    add = _padded(torch.randn(n, f))
+    pre = torch.rand(n, device=DEV)
+    pg = (_i32(noff), len(pages), int(max(p.num_nodes for p in pages)), int(max(p.num_edges for p in pages)))
+    assert ops.paged_packed_supported(pg, f)
+    pk = ops.paged_pack_edges(ip, ix, wd, pg, eid=ei)               # weights in edge order + eid
+    pk_row = ops.paged_pack_edges(ip, ix, w_row, pg)                # weights already in row order
+    e = ix.numel()
+    assert torch.equal(pk.packed[:e], pk_row.packed[:e]) and int(pk.page_flag.sum()) == 0
+    pk_pre = ops.paged_pack_edges(ip, ix, wd, pg, eid=ei, pre_scale=pre)
+    for kw, p_ in ((dict(mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm), pk), (dict(mode=_lib.GTE_AGG_MEAN), pk),
+                   (dict(mode=_lib.GTE_AGG_SUM, addend=add), pk_pre)):
+        a = ops.spmm(ip, ix, w_row, x, pre_scale=p_.pre_scale, **kw)
+        b = ops.spmm_packed(ip, p_, x, pg, **kw)
+        assert torch.equal(a, b)
+    # unweighted extension (w = None == all ones)
+    pk1 = ops.paged_pack_edges(ip, ix, None, pg)
+    assert torch.equal(ops.spmm(ip, ix, None, x), ops.spmm_packed(ip, pk1, x, pg))
+
+
+def test_spmm_paged_packed_wrong_page_table_and_small_capacity():
+    """a page table that does not describe a block-diagonal graph (edges leave their page), and page
+    capacities smaller than the real pages: the slow path keeps the result correct"""
+    pages = synth.make_pages(9, ragged=True, k=7)
+    s, d, w, noff, _ = csx.batch_coo(pages)
+    n = int(noff[-1])
+    ip, ix, ei = ops.csx_from_coo(_i32(d), _i32(s), n)
+    wd = _f32(w)
+    w_row = ops.gather_f32(wd, ei)
+    norm = ops.degree_norm(ip)
+    x = _padded(torch.randn(n, 70))
+    ref = ops.spmm(ip, ix, w_row, x, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
+    halves = sorted(set(int(v) for v in noff) | set(int((a + b) // 2) for a, b in zip(noff[:-1], noff[1:])))
+    cuts = np.array(halves, dtype=np.int32)  # every page cut in two: many edges leave their half page
+    ipc = ip.cpu().numpy()
+    fake = (_i32(cuts), len(cuts) - 1, int(np.diff(cuts).max()), int(np.diff(ipc[cuts]).max()))
+    assert ops.paged_packed_supported(fake, 70)
+    pk = ops.paged_pack_edges(ip, ix, wd, fake, eid=ei)
+    assert int(pk.page_flag.sum()) > 0
+    out = ops.spmm_packed(ip, pk, x, fake, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
+    assert rel_err(out, ref) < 1e-6  # inside-page edges first, outside edges after: same terms, other order
+    # true page table, capacities under-stated: pages that do not fit a stage run from global memory
+    pg_small = (_i32(noff), len(pages), int(min(p.num_nodes for p in pages)) + 1, 64)
+    pk2 = ops.paged_pack_edges(ip, ix, wd, pg_small, eid=ei)
+    out2 = ops.spmm_packed(ip, pk2, x, pg_small, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
+    assert torch.equal(out2, ref)
+    # empty pages in the table
+    noff2 = np.concatenate([[0, 0], noff[1:3], [noff[2]], noff[3:]]).astype(np.int32)
+    pg2 = (_i32(noff2), len(noff2) - 1, int(np.diff(noff2).max()), int(max(p.num_edges for p in pages)))
+    pk3 = ops.paged_pack_edges(ip, ix, wd, pg2, eid=ei)
+    assert torch.equal(ops.spmm_packed(ip, pk3, x, pg2, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm), ref)
+
+
 @pytest.mark.parametrize("n,fo,k1,k2,with_db", [(5000, 218, 218, 218, False), (2000, 218, 13, 13, True), (1000, 64, 100, 0, True),
                                                 (513, 256, 256, 256, False), (40000, 218, 218, 218, False), (7, 9, 20, 0, True)])
 def test_umma_linear_bwd_weight_3xtf32(n, fo, k1, k2, with_db):
