@@ -119,7 +119,7 @@ class ClockSampler:
 class OpTimer:
     """Wraps the tensor-level ops with CUDA events on the launching stream."""
 
-    NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "linear_fwd", "linear_bwd_data",
+    NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "spmm_packed", "paged_pack_edges", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
              "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2", "umma_linear_fwd_stacked", "umma_linear_bwd_data2"]
 
@@ -130,6 +130,8 @@ class OpTimer:
         if name == "spmm":
             x = a[3]
             return (name, int(a[0].numel() - 1), int(x.shape[1]), int(a[1].numel()), kw.get("addend") is not None)
+        if name == "spmm_packed":  # (indptr, packed edges, x, pages)
+            return ("spmm", int(a[0].numel() - 1), int(a[2].shape[1]), int(a[1].indices.numel()), kw.get("addend") is not None)
         if name == "linear_fwd":
             k = a[0].shape[1] + (a[1].shape[1] if a[1] is not None else 0)
             return (name, int(a[0].shape[0]), int(k), int(a[2].shape[0]))
