@@ -119,7 +119,7 @@ class ClockSampler:
 class OpTimer:
     """Wraps the tensor-level ops with CUDA events on the launching stream."""
 
-    NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "spmm_packed", "paged_pack_edges", "linear_fwd", "linear_bwd_data",
+    NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "spmm_packed", "paged_pack_edges", "gram_stream", "wide_out", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
              "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2", "umma_linear_fwd_stacked", "umma_linear_bwd_data2"]
 
@@ -132,6 +132,10 @@ class OpTimer:
             return (name, int(a[0].numel() - 1), int(x.shape[1]), int(a[1].numel()), kw.get("addend") is not None)
         if name == "spmm_packed":  # (indptr, packed edges, x, pages)
             return ("spmm", int(a[0].numel() - 1), int(a[2].shape[1]), int(a[1].indices.numel()), kw.get("addend") is not None)
+        if name == "gram_stream":  # (P wide, Q1, Q2, ...)
+            return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(a[1].shape[1]) + (int(a[2].shape[1]) if a[2] is not None else 0))
+        if name == "wide_out":  # (A1, A2, B1, B2, sj, sc, c, ...)
+            return (name, int(a[0].shape[0]), int(a[0].shape[1]) + (int(a[1].shape[1]) if a[1] is not None else 0), int(a[6]))
         if name == "linear_fwd":
             k = a[0].shape[1] + (a[1].shape[1] if a[1] is not None else 0)
             return (name, int(a[0].shape[0]), int(k), int(a[2].shape[0]))
@@ -211,6 +215,9 @@ def op_cost(key):
     if n in ("linear_bwd_weight", "umma_linear_bwd_weight", "umma_linear_bwd_weight2"):
         _, N, Fo, K = key
         return 4 * N * Fo + 4 * N * K + 4 * K * Fo, 2 * N * K * Fo
+    if n in ("gram_stream", "wide_out"):
+        _, N, a, b = key
+        return 4 * N * (a + b), 2 * N * a * b
     if n == "layernorm_act_fwd":
         return 8 * key[1] * key[2], 10 * key[1] * key[2]
     if n == "layernorm_act_bwd":
@@ -225,6 +232,9 @@ def cpu_oracle_run(pages_per_step: int, steps: int, warmup: int, budget_s: float
     import numpy as np
     import torch
     import torch.nn.functional as F
+
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
 
     from gnn_tableextraction_b200 import synth
     from oracle import sage_oracle as so

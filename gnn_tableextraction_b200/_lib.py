@@ -34,6 +34,10 @@ SIGNATURES = {
     "gte_paged_pack_edges": (ci, [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
     "gte_spmm_paged_packed_smem_bytes": (sz, [i32, i32, i32]),
     "gte_spmm_paged_packed": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
+    "gte_gram_stream_workspace_bytes": (sz, [i32, i32]),
+    "gte_gram_stream": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, vp, i64, i64, vp, i64, i64, vp, ci, vp, sz, vp]),
+    "gte_wide_out": (ci, [vp, i64, i32, vp, i64, i32, vp, vp, i64, i64, vp, vp, vp, f32, ci, ci, vp, vp, i64, vp, i64, vp, vp,
+                          i32, i32, vp]),
     "gte_linear_fwd": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, vp, vp, i64, i32, i32, vp]),
     "gte_linear_bwd_data": (ci, [vp, i64, i32, vp, i64, i32, i32, vp, vp, i64, i32, ci, vp]),
     "gte_linear_bwd_data2": (ci, [vp, i64, i32, vp, i64, i32, i32, vp, i64, i32, vp, vp, i64, i32, ci, vp]),

@@ -19,6 +19,10 @@ for s in "${srcs[@]}"; do
     pids+=($!)
   fi
 done
-for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+fail=0
+for p in "${pids[@]:-}"; do
+  if [[ -n "$p" ]]; then wait "$p" || fail=1; fi
+done
+if [[ $fail -ne 0 ]]; then echo "build.sh: compilation failed" >&2; exit 1; fi
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$out" "${objs[@]}" -lcudart
 echo "built $out"

@@ -32,6 +32,7 @@ from .graph import PageGraphBatch
 GEMM_MODE = os.environ.get("GTE_GEMM", "auto")
 UMMA_MIN_ROWS = 1024
 UMMA_MIN_WIDTH = 64
+SKINNY_MIN_ROWS = 256  # below this the generic kernels are launch-latency bound anyway
 
 GCN = "gcn"    # sum, then * 1/in_deg (0 for isolated nodes)  -- GcnSAGELayer
 MEAN = "mean"  # sum / max(in_deg, 1)                          -- WeightedMeanSAGELayer (DGL fn.mean)
@@ -149,6 +150,12 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
                                                            eps=eps, relu=relu, fuse_ln=ln)
             ctx.z = z
             return (y if y is not None else z), ctx
+        if (ln or not relu) and ops.wide_out_supported(fin, fin, fout, h, ah) and h.shape[0] >= SKINNY_MIN_ROWS:
+            # exact-fp32 route for a narrow input (K = 2 * fin <= 32): one streaming pass, bias + LayerNorm + ReLU fused
+            z, y, ctx.mean, ctx.rstd = ops.wide_out(h, ah, W.data_ptr(), W.data_ptr() + 4 * fin, 1, W.stride(0), fout, b,
+                                                    gamma=gamma, beta=beta, eps=eps, relu=relu, fuse_ln=ln)
+            ctx.z = z
+            return (y if y is not None else z), ctx
         z = ops.linear_fwd(h, ah, W, b)
     elif st == "proj":
         if fout <= 16 and use_umma(h.shape[0], fin, fout, h):
@@ -193,6 +200,10 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
     if ctx.strategy == "agg":
         if use_umma_dw(dz.shape[0], fout, fin, fin, db is not None, dz, ctx.h, ctx.ah):
             ops.umma_linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
+        elif (db is None and 2 * fin <= 32 and dz.shape[0] >= SKINNY_MIN_ROWS and dW.stride(1) == 1
+              and ops.gram_stream_supported(fout, 2 * fin, dz, ctx.h, ctx.ah)):
+            # narrow input: stream dz once against [h | ah] (exact fp32, fixed-order reduction)
+            ops.gram_stream(dz, ctx.h, ctx.ah, dW, dW.stride(0), 1, dW[:, fin:], dW.stride(0), 1, accumulate=accumulate)
         else:
             ops.linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
         if not need_dh:
@@ -206,7 +217,11 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
     # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
     #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn
     gq = aggregate_backward(g, dz, ctx.w_edge)
-    if (GEMM_MODE != "ffma" and fout <= 32 and fin <= 256 and (db is None or fin % 128 != 0) and
+    if (2 * fout <= 32 and dz.shape[0] >= SKINNY_MIN_ROWS and dW.stride(1) == 1 and GEMM_MODE != "umma"
+            and ops.gram_stream_supported(fin, 2 * fout, ctx.h, dz, gq)):
+        # class layer: stream the wide input once against [dz | A^T dz]; the column sums of dz are the bias gradient
+        ops.gram_stream(ctx.h, dz, gq, dW, 1, dW.stride(0), dW[:, fin:], 1, dW.stride(0), qsum=db, accumulate=accumulate)
+    elif (GEMM_MODE != "ffma" and fout <= 32 and fin <= 256 and (db is None or fin % 128 != 0) and
             (GEMM_MODE == "umma" or dz.shape[0] >= UMMA_MIN_ROWS) and
             all(ops._aligned_mat(m) for m in (dz, gq, ctx.h))):
         ops.umma_linear_bwd_weight2(dz, gq, ctx.h, dW, 0, fin, db, accumulate)
@@ -216,6 +231,8 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
         return None
     if ctx.pack is not None and ops._aligned_mat(dz) and ops._aligned_mat(gq):
         return ops.umma_linear_bwd_data2(dz, gq, ctx.pack, fin)
+    if ops.wide_out_supported(fout, fout, fin, dz, gq) and dz.shape[0] >= SKINNY_MIN_ROWS and W.stride(1) == 1:
+        return ops.wide_out(dz, gq, W.data_ptr(), W.data_ptr() + 4 * fin, W.stride(0), 1, fin)[0]  # exact fp32
     return ops.linear_bwd_data2(dz, 0, gq, fin, W, fin)
 
 

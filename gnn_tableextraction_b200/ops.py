@@ -243,6 +243,60 @@ def spmm_packed(indptr, pk: PackedEdges, x, pages, *, mode=_lib.GTE_AGG_SUM, row
     return out
 
 
+# ------------------------------------------------- narrow dense streams ---
+def gram_stream_supported(wide: int, nq: int, *mats) -> bool:
+    return 0 < wide <= 256 and 0 < nq <= 32 and _aligned_mat(mats[0]) and all(m is None or m.is_cuda for m in mats)
+
+
+def gram_stream(P, Q1, Q2, out1, sa1: int, sb1: int, out2=None, sa2: int = 0, sb2: int = 0, qsum=None, accumulate=False):
+    """C[a][b] = sum_r P[r,a] * [Q1|Q2][r,b] scattered to ``out1`` / ``out2`` with element strides
+    (``sa``, ``sb``); ``qsum`` = column sums of Q1.  See gte.h (gte_gram_stream)."""
+    pp, ldp, wide = _mat(P, "gram.P")
+    n = P.shape[0]
+    q1p, ldq1, nq1 = _mat(Q1, "gram.Q1")
+    q2p, ldq2, nq2 = (None, 0, 0)
+    if Q2 is not None:
+        q2p, ldq2, nq2 = _mat(Q2, "gram.Q2")
+    if Q1.shape[0] != n or (Q2 is not None and Q2.shape[0] != n):
+        raise GteError("gram_stream: row mismatch")
+    _req_cuda(out1, out2, qsum)
+    l = lib()
+    need = l.gte_gram_stream_workspace_bytes(n, wide)
+    ws = workspace(need, P.device)
+    check(l.gte_gram_stream(pp, ldp, wide, q1p, ldq1, nq1, q2p, ldq2, nq2, n, out1.data_ptr(), sa1, sb1, _ptr(out2), sa2, sb2,
+                            _ptr(qsum), 1 if accumulate else 0, ws.data_ptr(), ws.numel(), _stream()), "gte_gram_stream")
+
+
+def wide_out_supported(k1: int, k2: int, c: int, *mats) -> bool:
+    return 0 < k1 <= 16 and 0 <= k2 <= 16 and 0 < c <= 256 and all(m is None or _aligned_mat(m) for m in mats)
+
+
+def wide_out(A1, A2, B1_ptr: int, B2_ptr: Optional[int], sj: int, sc: int, c: int, bias=None, *, gamma=None, beta=None,
+             eps: float = 1e-5, relu: bool = False, fuse_ln: bool = False, row_scale=None):
+    """z = [A1|A2] B (+ bias) (* row_scale) with the narrow operand on the contraction side; with
+    ``fuse_ln`` returns (z, y, mean, rstd), else (z, None, None, None).  See gte.h (gte_wide_out)."""
+    a1p, lda1, k1 = _mat(A1, "wide_out.A1")
+    n = A1.shape[0]
+    a2p, lda2, k2 = (None, 0, 0)
+    if A2 is not None:
+        a2p, lda2, k2 = _mat(A2, "wide_out.A2")
+    dev = A1.device
+    z = empty_padded(n, c, dev)
+    zp, ldz, _ = _mat(z, "wide_out.z")
+    y = mean = rstd = None
+    yp, ldy = None, 0
+    if fuse_ln:
+        y = empty_padded(n, c, dev)
+        yp, ldy, _ = _mat(y, "wide_out.y")
+        mean = torch.empty(n, dtype=torch.float32, device=dev)
+        rstd = torch.empty(n, dtype=torch.float32, device=dev)
+    check(lib().gte_wide_out(a1p, lda1, k1, a2p, lda2, k2, B1_ptr, B2_ptr, sj, sc, _vec(bias, "bias", n=c),
+                             _vec(gamma, "gamma", n=c), _vec(beta, "beta", n=c), eps, 1 if relu else 0, 1 if fuse_ln else 0,
+                             _vec(row_scale, "row_scale", n=n), zp, ldz, yp, ldy, _ptr(mean), _ptr(rstd), n, c, _stream()),
+          "gte_wide_out")
+    return z, y, mean, rstd
+
+
 # ------------------------------------------------------------------ dense ---
 def linear_fwd(x1, x2, W, bias, out=None, w_col0: int = 0):
     """z = x1 W[:, c0:c0+k1]^T + x2 W[:, c0+k1:c0+k1+k2]^T + bias (x2 may be None)."""

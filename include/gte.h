@@ -171,6 +171,36 @@ int gte_spmm_paged_packed(const int32_t* indptr, const uint64_t* packed, const i
                           int32_t max_page_nodes, int32_t max_page_edges, int32_t n_rows, int32_t f,
                           gte_stream_t stream);
 
+/* ---------------------------------- narrow dense operands (streams) ----- */
+/*
+ * `nn.Linear` and its autograd (models.py:27,63) where one operand is at most 32 columns wide -- the
+ * input layer (2 x 13 features) and the class layer (9 classes): HBM streams on CUDA cores (exact fp32
+ * FMA), not tensor-core tiles.
+ *
+ * gte_gram_stream:  C[a][b] = sum_r P[r,a] * Q[r,b],  P [n, wide <= 256] (16-byte aligned rows),
+ *   Q = [Q1 | Q2] with nq1 + nq2 <= 32 columns.  Block b < nq1 goes to out1[a*sa1 + b*sb1], block
+ *   b >= nq1 to out2[a*sa2 + (b-nq1)*sb2] (strides in floats, so either orientation of the weight
+ *   gradient can be written); `qsum` (may be NULL) receives the column sums of Q1 (the bias gradient when
+ *   Q1 = dz).  Row ranges are reduced in fixed order: deterministic.  Weight gradients of
+ *   the input layer: P = dz, Q = [h | ah]; of the class layer: P = h, Q = [dz | A^T dz].
+ *
+ * gte_wide_out:  z[r,c] = (sum_j A1[r,j] B1(j,c) + sum_j A2[r,j] B2(j,c) + bias[c]) * row_scale[r],
+ *   element B(j,c) at B[j*sj + c*sc]; k1, k2 <= 16, C <= 256; with fuse_ln also
+ *   y = relu?(LayerNorm(z) * gamma + beta) and the per-row mean / rstd (two-pass statistics held in
+ *   registers).  Input-layer forward: A = [h | ah], B1 = W, B2 = W + k1, sj = 1, sc = ldw.  Class-layer
+ *   input gradient: A = [dz | A^T dz], B1 = W, B2 = W + fin, sj = ldw, sc = 1.
+ */
+size_t gte_gram_stream_workspace_bytes(int32_t n, int32_t wide);
+int gte_gram_stream(const float* P, int64_t ldp, int32_t wide, const float* Q1, int64_t ldq1, int32_t nq1,
+                    const float* Q2, int64_t ldq2, int32_t nq2, int32_t n,
+                    float* out1, int64_t sa1, int64_t sb1, float* out2, int64_t sa2, int64_t sb2,
+                    float* qsum, int accumulate, void* ws, size_t ws_bytes, gte_stream_t stream);
+int gte_wide_out(const float* A1, int64_t lda1, int32_t k1, const float* A2, int64_t lda2, int32_t k2,
+                 const float* B1, const float* B2, int64_t sj, int64_t sc, const float* bias,
+                 const float* gamma, const float* beta, float eps, int relu, int fuse_ln,
+                 const float* row_scale, float* z, int64_t ldz, float* y, int64_t ldy,
+                 float* mean, float* rstd, int32_t n, int32_t C, gte_stream_t stream);
+
 /* ------------------------------------------------- dense projection ----- */
 /*
  * z[n,fo] = x1[n,k1] W[:, 0:k1]^T + x2[n,k2] W[:, k1:k1+k2]^T + bias

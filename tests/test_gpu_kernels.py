@@ -556,3 +556,71 @@ def test_umma_input_layer_narrow_k():
     zf = ops.linear_fwd(_padded(feat), _padded(ah), W.to(DEV), b.to(DEV))
     _log_err(f"input layer K=26: umma_z={rel_err(z, z64):.2e} umma_y={rel_err(y, y64):.2e} ffma_z", rel_err(zf, z64))
     assert rel_err(z, z64) < 3e-6 and rel_err(y, y64) < 5e-6
+
+
+# ------------------------------------------------- narrow dense streams ----
+@pytest.mark.parametrize("n,wide,nq1,nq2", [(5000, 218, 13, 13), (3001, 218, 9, 9), (2, 7, 3, 0), (777, 256, 16, 16),
+                                            (40000, 218, 13, 13), (64, 100, 1, 0), (2049, 33, 5, 2)])
+def test_gram_stream_matches_fp64(n, wide, nq1, nq2):
+    """C = P^T [Q1|Q2] (+ column sums of Q1), both output orientations, accumulate, run-to-run bit identical"""
+    gen = torch.Generator().manual_seed(n + wide)
+    P = torch.randn(n, wide, generator=gen)
+    Q1 = torch.randn(n, nq1, generator=gen)
+    Q2 = torch.randn(n, nq2, generator=gen) if nq2 else None
+    Pd, Q1d = _padded(P), _padded(Q1)
+    Q2d = _padded(Q2) if nq2 else None
+    # orientation 1: out[a, b] row-major [wide, nq1+nq2] (input-layer dW = dz^T [h|ah])
+    out = torch.full((wide, nq1 + nq2), 7.0, device=DEV)
+    qs = torch.full((nq1,), 7.0, device=DEV)
+    ld = nq1 + nq2
+    ops.gram_stream(Pd, Q1d, Q2d, out, ld, 1, out[:, nq1:] if nq2 else None, ld, 1, qsum=qs)
+    ref = P.double().T @ torch.cat([Q1, Q2], 1).double() if nq2 else P.double().T @ Q1.double()
+    assert rel_err(out, ref) < 2e-6
+    assert rel_err(qs, Q1.double().sum(0)) < 2e-6
+    out_b = torch.full((wide, nq1 + nq2), -1.0, device=DEV)
+    ops.gram_stream(Pd, Q1d, Q2d, out_b, ld, 1, out_b[:, nq1:] if nq2 else None, ld, 1)
+    assert torch.equal(out, out_b)  # deterministic
+    # orientation 2: transposed blocks [nq, 2*wide] (class-layer dW = [dz|G]^T h), accumulate on top of ones
+    outT = torch.ones((max(nq1, nq2), 2 * wide), device=DEV)
+    ops.gram_stream(Pd, Q1d, Q2d, outT, 1, 2 * wide, outT[:, wide:] if nq2 else None, 1, 2 * wide, accumulate=True)
+    assert rel_err(outT[:nq1, :wide] - 1, ref[:, :nq1].T) < 2e-6
+    if nq2:
+        assert rel_err(outT[:nq2, wide:] - 1, ref[:, nq1:].T) < 2e-6
+
+
+@pytest.mark.parametrize("n,k1,k2,c,ln,relu", [(5000, 13, 13, 218, True, True), (3001, 9, 9, 218, False, False),
+                                               (7, 13, 0, 40, True, False), (40000, 13, 13, 218, True, True),
+                                               (1000, 16, 16, 256, True, True), (513, 5, 3, 31, False, False)])
+def test_wide_out_matches_fp64(n, k1, k2, c, ln, relu):
+    """z = [A1|A2] B + bias (narrow contraction, wide output) with fused LayerNorm + ReLU, both B orientations"""
+    gen = torch.Generator().manual_seed(n + c)
+    A1 = torch.randn(n, k1, generator=gen) * 30          # large-magnitude inputs like the BBOX features
+    A2 = torch.randn(n, k2, generator=gen) if k2 else None
+    W = torch.randn(c, k1 + k2, generator=gen) * 0.2     # nn.Linear layout [out, in]
+    b = torch.randn(c, generator=gen)
+    gam, bet = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
+    A1d = _padded(A1)
+    A2d = _padded(A2) if k2 else None
+    Wd = W.to(DEV)
+    x = torch.cat([A1, A2], 1).double() if k2 else A1.double()
+    zref = x @ W.double().T + b.double()
+    z, y, mean, rstd = ops.wide_out(A1d, A2d, Wd.data_ptr(), Wd.data_ptr() + 4 * k1, 1, k1 + k2, c, b.to(DEV),
+                                    gamma=gam.to(DEV), beta=bet.to(DEV), eps=1e-5, relu=relu, fuse_ln=ln)
+    assert rel_err(z, zref) < 2e-6
+    if ln:
+        yref = F.layer_norm(zref, (c,), gam.double(), bet.double(), 1e-5)
+        if relu:
+            yref = F.relu(yref)
+        assert rel_err(y, yref) < 5e-6
+        assert rel_err(mean, zref.mean(1)) < 2e-6
+        assert rel_err(rstd, 1.0 / torch.sqrt(zref.var(1, unbiased=False) + 1e-5)) < 5e-6
+    else:
+        assert y is None
+    # transposed B (class-layer input gradient: dx = dz Ws + G Wn with W stored [o, 2*c]), row scale
+    if k2 == k1:
+        W3 = torch.randn(k1, 2 * c, generator=gen) * 0.2
+        W3d = W3.to(DEV)
+        rs = torch.rand(n, generator=gen)
+        z2, _, _, _ = ops.wide_out(A1d, A2d, W3d.data_ptr(), W3d.data_ptr() + 4 * c, 2 * c, 1, c, None, row_scale=rs.to(DEV))
+        ref2 = (A1.double() @ W3.double()[:, :c] + A2.double() @ W3.double()[:, c:]) * rs.double()[:, None]
+        assert rel_err(z2, ref2) < 2e-6
