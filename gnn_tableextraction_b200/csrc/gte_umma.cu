@@ -511,7 +511,13 @@ static int launch_umma(UmmaArgs& a, cudaStream_t st) {
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
   if (grid < 1) return GTE_OK;
-  if (a.variant & 2)
+  // The cross-term accumulator exists to keep the long main accumulation chain free of the small terms (the
+  // tensor core truncates when it accumulates).  A contraction of one or two k-blocks (the input layer: K = 26,
+  // the class-layer input gradient: K = 18) has no long chain: one accumulator is just as exact, and it frees
+  // TMEM for a second accumulator stage (epilogue of tile i overlaps the MMAs of tile i+1) and halves the
+  // epilogue's TMEM reads.
+  const int kb_total = a.kblocks[0] + (a.nseg > 1 ? a.kblocks[1] : 0);
+  if ((a.variant & 2) && kb_total > 2)
     k_umma_gemm<true><<<grid, UM_THREADS, smem, st>>>(a);
   else
     k_umma_gemm<false><<<grid, UM_THREADS, smem, st>>>(a);
