@@ -9,7 +9,7 @@
 // One persistent CTA per SM, 12 warps, warp-specialised:
 //   warp 0      TMA producer: raw A tile [128 x 32] + packed W_hi/W_lo tiles [BN x 32]
 //               (SWIZZLE_128B, K-major) into a 2-stage smem ring
-//   warps 4-7   split A in place (hi) + side buffer (lo) -- position preserving, so
+//   warps 2-7   split A in place (hi) + side buffer (lo) -- position preserving, so
 //               the swizzle does not matter -- then fence.proxy.async + arrive
 //   warp 1      elected lane issues 12 tcgen05.mma (M=128, N=BN, K=8) per 32-wide k block
 //               into one of two TMEM accumulator stages; tcgen05.commit frees smem / signals
@@ -40,6 +40,7 @@ constexpr int UM_THREADS = 384;
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;               // floats per k block = one 128-byte swizzle row
 constexpr int UM_STAGES = 2;
+constexpr int UM_SPLIT_THREADS = 192;     // warps 2..7 split the A operand
 constexpr int UM_PREFETCH = 8;            // k-blocks of L2 prefetch lookahead for the activation tiles
 constexpr int UM_A_BYTES = UM_BM * 128;  // 16 KB
 constexpr int UM_MAX_BN = 256;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < UM_STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_ready[s]), 128);
+      mbar_init(smem_u32(&bar_ready[s]), UM_SPLIT_THREADS);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -245,9 +246,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
         if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================================ operand split ===============================
-    const int t = threadIdx.x - 128;
+  } else if (warp >= 2 && warp < 8) {
+    // ================================ operand split (6 warps: 2..7) ================
+    const int t = threadIdx.x - 64;
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -256,8 +257,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
         float4* hi = reinterpret_cast<float4*>(sA_hi_p(stage));
         float4* lo = reinterpret_cast<float4*>(sA_lo_p(stage));
 #pragma unroll
-        for (int i = 0; i < UM_A_BYTES / 16 / 128; ++i) {
-          const int idx = t + 128 * i;
+        for (int i = 0; i < (UM_A_BYTES / 16 + UM_SPLIT_THREADS - 1) / UM_SPLIT_THREADS; ++i) {
+          const int idx = t + UM_SPLIT_THREADS * i;
+          if (idx >= UM_A_BYTES / 16) break;
           const float4 v = hi[idx];
           float4 h, l;
           if (P.variant & 1) {

@@ -29,6 +29,7 @@ constexpr int DW_THREADS = 384;
 constexpr int DW_KB = 32;                      // contraction rows per pipeline stage
 constexpr int DW_BOX_BYTES = DW_KB * 128;      // one TMA box: 32 rows x 32 floats
 constexpr int DW_STAGES = 2;
+constexpr int DW_SPLIT_THREADS = 192;           // warps 2..7 split the operands
 constexpr int DW_PREFETCH = 6;                 // k-blocks of L2 prefetch lookahead
 constexpr int DW_MAX_BOXES = 8;
 constexpr int DW_STAGE_LD = EPI_LD;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < DW_STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_ready[s]), 128);
+      mbar_init(smem_u32(&bar_ready[s]), DW_SPLIT_THREADS);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(bar_tfull), 1);
@@ -192,9 +193,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
         acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================================ operand split ===============================
-    const int t = threadIdx.x - 128;
+  } else if (warp >= 2 && warp < 8) {
+    // ================================ operand split (6 warps: 2..7) ================
+    const int t = threadIdx.x - 64;
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
           float4* hi = reinterpret_cast<float4*>(hi_p);
           float4* lo = reinterpret_cast<float4*>(lo_p);
           if (P.dbg_mode == 20) return;  // timing experiment: no split at all
-          for (int idx = t; idx < nf4; idx += 128) {
+          for (int idx = t; idx < nf4; idx += DW_SPLIT_THREADS) {
             const float4 v = hi[idx];
             float4 h, l;
             if (P.dbg_mode == 21) {  // timing experiment: truncation masks instead of cvt.rna
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
         // all-ones column: element (row kk, tile column c) of an MN-major SW128 box tile
         const int ones_col = G.ones_b_col >= 0 ? G.ones_b_col : ((G.ones_a_col >= 0 && G.ones_a_col / 128 == mt) ? G.ones_a_col % 128 : -1);
         if (ones_col >= 0) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // the splits above wrote the same words
+          asm volatile("bar.sync 1, %0;" ::"n"(DW_SPLIT_THREADS) : "memory");  // the splits above wrote the same words
           if (t < DW_KB) {
             const int kk = t;
             if (r0 + kb * DW_KB + kk < P.n) {
