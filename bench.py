@@ -225,6 +225,31 @@ def op_cost(key):
     return 0, 0
 
 
+def ncu_traffic(op_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind an op, from the committed
+    `ncu --set full` summary (profiles/r01_kernel_metrics.json, written by scripts/summarize_profiles.py from a
+    capture of this same workload).  None when no capture of that kernel at this size is on file."""
+    path = os.path.join(ROOT, "profiles", "r01_kernel_metrics.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        m = json.load(open(path))
+    except Exception:
+        return None
+    name = op_key[0]
+    if name == "umma_linear_bwd_weight":
+        recs = [r for k, v in m.items() if k.startswith("k_umma_dw grid") for r in v]
+        want = max(recs, key=lambda r: r.get("time_us", 0)) if (recs and op_key[3] > 64) else None
+    elif name == "spmm":
+        recs = [r for k, v in m.items() if k.startswith("k_spmm_paged_pk<8, 2>") for r in v
+                if r.get("capture", "").startswith("r01_spmm_cfg2")]
+        recs = sorted(recs, key=lambda r: r.get("dram_bytes", 0))
+        want = (recs[-1] if op_key[4] else recs[0]) if recs else None  # with addend = the larger traffic
+    else:
+        want = None
+    return None if want is None else {"bytes": want["dram_bytes"], "capture": "profiles/r01_kernel_metrics.json: " + want["capture"]}
+
+
 # ------------------------------------------------------------- CPU arm -----
 def cpu_oracle_run(pages_per_step: int, steps: int, warmup: int, budget_s: float):
     """Times the oracle port (torch-only restatement of the reference's DGL CPU path:
@@ -453,6 +478,10 @@ def run_ours(args):
                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": b / dms / 1e6 / pk["hbm_gbs"], "traffic": None,
                         "peak_source": pk["source"]}
         roofline["share_of_step"] = round(dms * dcnt / step_ms, 4)
+        tr = ncu_traffic(dkey)
+        if tr:
+            roofline["traffic"], roofline["traffic_source"] = tr["bytes"], tr["capture"]
+            roofline["alg_bytes"] = b
         # the conv (aggregation) kernel of the hidden layer: the HBM-roofline number north_star asks for
         sp = [(k, v) for k, v in tab.items() if k[0] == "spmm" and k[2] == MODEL_CFG[1]]
         if sp:
@@ -461,6 +490,9 @@ def run_ours(args):
             conv = {"kernel": "/".join(str(x) for x in k), "bound": "hbm", "achieved": b / ms / 1e6, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": b / ms / 1e6 / pk["hbm_gbs"], "frac_of_8TBs_nominal": b / ms / 1e6 / 8000.0,
                     "ms": ms, "alg_bytes": b, "traffic": None}
+            tr = ncu_traffic(k)
+            if tr:
+                conv["traffic"], conv["traffic_source"] = tr["bytes"], tr["capture"]
 
     # --- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None
