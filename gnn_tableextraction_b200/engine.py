@@ -153,6 +153,29 @@ class SageTrainer:
             logits, _ = self.forward(g, keep_ctx=False)
         return logits
 
+    @torch.no_grad()
+    def predict_pages(self, g: PageGraphBatch, labels: Optional[torch.Tensor] = None):
+        """The predict loop of model_predict.py:130-154 for a whole batch of pages in one pass:
+        returns (preds int32 [N] on device, per-page accuracy float64 tensor [P] on device or None).
+        ``all_pred.extend(preds.tolist())`` and ``mean_test_acc += acc`` of the reference become
+        ``preds.tolist()`` and ``acc.sum()`` over the batches."""
+        if labels is None:
+            labels = g.ndata.get("label")
+        pages = g.pages()
+        if pages is None:  # one huge graph: a single "page"
+            pages = page_table([g.num_nodes()], [g.num_edges()], g.num_nodes(), g.device)
+            if pages is None:
+                off = torch.tensor([0, g.num_nodes()], dtype=torch.int32, device=g.device)
+                pages = (off, 1, g.num_nodes(), g.num_edges())
+        with torch.cuda.device(self.device):
+            logits, _ = self.forward(g, keep_ctx=False)
+            preds, correct = ops.page_predictions(logits, pages[0], pages[1], labels)
+        acc = None
+        if correct is not None:
+            sizes = (pages[0][1:] - pages[0][:-1]).to(torch.float64)
+            acc = correct.to(torch.float64) / sizes
+        return preds, acc
+
     # ----------------------------------------------------- CUDA graphs -----
     def capture(self, host_batch: Dict[str, torch.Tensor], split: Optional[bool] = None):
         """Capture the whole step (format build + forward + loss + backward +

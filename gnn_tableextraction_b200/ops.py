@@ -682,3 +682,39 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, e
                             _ptr(step_dev), float(grad_scale), _stream()),
         "gte_adam_step",
     )
+
+
+# ------------------------------------------- either side of the layers ----
+def page_predictions(logits, page_off, num_pages: int, labels=None):
+    """``logits.argmax(1)`` for a batch of pages + per-page number of correct predictions
+    (model_predict.py:144-148).  Returns (preds int32 [N], page_correct int32 [P] or None)."""
+    lp, ld, c = _mat(logits, "page_predictions.logits")
+    n = logits.shape[0]
+    preds = torch.empty(n, dtype=torch.int32, device=logits.device)
+    correct = None
+    labp, ldt = None, _lib.GTE_LABEL_I64
+    if labels is not None:
+        if labels.numel() != n:
+            raise GteError("page_predictions: one label per node expected")
+        labp, ldt = _labels(labels)
+        correct = torch.empty(max(num_pages, 1), dtype=torch.int32, device=logits.device)
+    check(lib().gte_page_predictions(lp, ld, n, c, labp, ldt, _vec(page_off, "page_off", torch.int32, num_pages + 1), num_pages,
+                                     preds.data_ptr(), _ptr(correct), _stream()), "gte_page_predictions")
+    return preds, (correct[:num_pages] if correct is not None else None)
+
+
+def bbox_features(boxes: torch.Tensor, counts: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """13 BBOX features per text box (bbox.py:49-111) from int32 boxes [n,4] and character-class counts [n,3]."""
+    _req_cuda(boxes, counts)
+    if boxes.dtype != torch.int32 or counts.dtype != torch.int32 or boxes.dim() != 2 or boxes.shape[1] != 4 \
+            or counts.shape != (boxes.shape[0], 3):
+        raise GteError("bbox_features: boxes int32 [n,4] and counts int32 [n,3] expected")
+    n = boxes.shape[0]
+    if out is None:
+        out = empty_padded(n, 13, boxes.device)
+    op, ldo, f = _mat(out, "bbox_features.out")
+    if f != 13 or out.shape[0] != n:
+        raise GteError("bbox_features: output must be [n, 13]")
+    check(lib().gte_bbox_features(boxes.contiguous().data_ptr(), counts.contiguous().data_ptr(), n, op, ldo, _stream()),
+          "gte_bbox_features")
+    return out

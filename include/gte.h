@@ -378,6 +378,27 @@ int gte_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float weight_decay, int64_t step_host, int64_t* step_dev, float grad_scale,
                   gte_stream_t stream);
 
+/* ---------------------------------------- either side of the layers ---- */
+/*
+ * Batched predict tail (model_predict.py:144-154): preds[i] = argmax_j logits[i, j] (first maximal index; NaN
+ * counts as maximal, like torch.argmax) as int32, and -- when `labels` is given -- page_correct[p] =
+ * #(preds == labels) over the nodes [page_off[p], page_off[p+1]) of page p, from which the reference's per-page
+ * accuracy `correct / g.num_nodes()` and its mean over pages follow.  `page_correct` may be NULL.
+ */
+int gte_page_predictions(const float* logits, int64_t ld, int32_t n, int32_t c, const void* labels,
+                         int label_dtype, const int32_t* page_off, int32_t num_pages, int32_t* preds,
+                         int32_t* page_correct, gte_stream_t stream);
+
+/*
+ * BBOX node features on the device (src/components/nlp/bbox.py:49-54 get_shape, :57-111 get_histogram, called
+ * per batch at model_train.py:293): boxes [n, 4] int32 = [x0, y0, x1, y1]; counts [n, 3] int32 = (letters,
+ * digits, other symbols) of the box text with blanks removed (str.isalpha / str.isdigit are host string
+ * operations and stay on the host).  out [n, 13] fp32 = [w, h, cx, cy, w*h, x0, y0, x1, y1, hist0..hist3],
+ * computed in float64 like the Python original and cast to float32 (model_train.py:295).
+ */
+int gte_bbox_features(const int32_t* boxes, const int32_t* counts, int32_t n, float* out, int64_t ldo,
+                      gte_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -624,3 +624,41 @@ def test_wide_out_matches_fp64(n, k1, k2, c, ln, relu):
         z2, _, _, _ = ops.wide_out(A1d, A2d, W3d.data_ptr(), W3d.data_ptr() + 4 * c, 2 * c, 1, c, None, row_scale=rs.to(DEV))
         ref2 = (A1.double() @ W3.double()[:, :c] + A2.double() @ W3.double()[:, c:]) * rs.double()[:, None]
         assert rel_err(z2, ref2) < 2e-6
+
+
+# ------------------------------------------- either side of the layers ----
+def test_bbox_features_bit_exact_vs_reference_golden():
+    """gte_bbox_features == the reference's get_shape / get_histogram (golden vectors), bit for bit"""
+    import os
+    from conftest import GOLDEN
+    from gnn_tableextraction_b200 import features
+
+    d = np.load(os.path.join(GOLDEN, "bbox_features.npz"), allow_pickle=True)
+    out = features.bbox_features(d["boxes"], d["counts"], DEV)
+    assert out.shape == (4000, 13) and out.stride(0) % 4 == 0
+    assert np.array_equal(out.cpu().numpy(), d["feat"])
+    out2 = features.bbox_features(d["boxes"], [str(t) for t in d["texts"]], DEV)   # from the texts
+    assert torch.equal(out, out2)
+    assert features.bbox_features(d["boxes"][:0], d["counts"][:0], DEV).shape == (0, 13)
+
+
+@pytest.mark.parametrize("ldt", [torch.float32, torch.int64, torch.int32])
+def test_page_predictions_match_torch_argmax(ldt):
+    from oracle import bbox_oracle as bo
+
+    gen = torch.Generator().manual_seed(5)
+    sizes = [300, 1, 0, 77, 512, 300]
+    n, c = sum(sizes), 9
+    logits = torch.randn(n, c, generator=gen)
+    logits[5] = torch.tensor([0.0, 3.0, 3.0, 1.0, 3.0, 0.0, 0.0, 0.0, 0.0])  # tie -> first maximal index
+    logits[6, 4] = float("nan")                                                 # NaN is maximal (torch.argmax)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    labels[::3] = logits.argmax(1)[::3]
+    off = _i32(np.concatenate([[0], np.cumsum(sizes)]))
+    preds, correct = ops.page_predictions(_padded(logits), off, len(sizes), labels.to(ldt).to(DEV))
+    assert torch.equal(preds.cpu().long(), logits.argmax(1))
+    ref_preds, accs, _ = bo.page_predictions(logits.numpy(), labels.numpy(), sizes)
+    want = [int(round(a * s)) for a, s in zip(accs, sizes)]
+    assert correct.cpu().tolist() == want
+    p2, c2 = ops.page_predictions(_padded(logits), off, len(sizes))
+    assert torch.equal(p2, preds) and c2 is None

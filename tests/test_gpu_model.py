@@ -258,3 +258,39 @@ def test_trainer_prefetched_replay_equals_plain_replay():
         s2 = t2.replay_prefetched().clone()
         assert torch.equal(s1, s2), i
     assert torch.equal(t1.flat_param, t2.flat_param)
+
+
+def test_predict_pages_matches_reference_predict_loop():
+    """SageTrainer.predict_pages (one batched pass) == model_predict.py:130-154 page by page on the oracle:
+    same predictions, same per-page accuracies, same mean accuracy"""
+    import torch.nn.functional as F
+    import gnn_tableextraction_b200 as gte
+    from gnn_tableextraction_b200 import synth
+    from oracle import bbox_oracle as bo
+    from oracle import sage_oracle as so
+    from helpers import oracle_graph_from_pages
+
+    pages = synth.make_pages(7, ragged=True, k=6)
+    torch.manual_seed(3)
+    om = so.OracleGcnSAGE(13, 64, 9, 3, F.relu, 0)
+    cm = gte.GcnSAGE(13, 64, 9, 3, F.relu, 0)
+    cm.load_state_dict(om.state_dict())
+    cm = cm.to("cuda").eval()
+    om.eval()
+    all_pred, accs = [], []
+    with torch.no_grad():
+        for p in pages:  # the reference loop: one forward per page
+            og = oracle_graph_from_pages([p])
+            logits = om(og)
+            pr = logits.argmax(1)
+            accs.append((pr == og.ndata["label"].long()).sum().item() / p.num_nodes)
+            all_pred.extend(pr.tolist())
+    g = gte.PageGraphBatch.from_pages(pages, "cuda")
+    preds, acc = gte.SageTrainer(cm).predict_pages(g)
+    got = preds.cpu().tolist()
+    # argmax may flip only where the two best logits are within fp32 noise of each other
+    diff = [i for i, (a, b) in enumerate(zip(got, all_pred)) if a != b]
+    assert len(diff) <= 2, f"{len(diff)} predictions differ"
+    if not diff:
+        assert np.allclose(acc.cpu().numpy(), np.asarray(accs), atol=1e-12)
+        assert abs(acc.mean().item() - sum(accs) / len(accs)) < 1e-12

@@ -3,12 +3,14 @@ models.py (tests/golden/make_golden.py), one unit test per assumed DGL semantic
 (S1..S8 of oracle/dgl_shim.py), and the integer oracle for the sparse formats."""
 import math
 
+import os
+
 import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import TOL, load_golden, rel_err, sub
+from conftest import GOLDEN, TOL, load_golden, rel_err, sub
 from helpers import oracle_graph_from_golden, oracle_graph_from_pages
 from gnn_tableextraction_b200 import synth
 from oracle import csx, dgl_shim
@@ -267,3 +269,34 @@ def test_synth_page_shape():
     pb = synth.make_page(42, k=5, bidirectional=True)
     k2 = set(zip(pb.src.tolist(), pb.dst.tolist()))
     assert all((d, s) in k2 for s, d in k2)  # symmetric structure
+
+
+# ------------------------------------------- either side of the layers ----
+def test_bbox_oracle_matches_reference_golden():
+    """oracle/bbox_oracle.py == the reference's own get_shape / get_histogram (tests/golden/make_bbox_golden.py),
+    bit for bit, including the 75 rows that take the "keep sum 1" branch and the host-side class counting"""
+    from oracle import bbox_oracle as bo
+
+    d = np.load(os.path.join(GOLDEN, "bbox_features.npz"), allow_pickle=True)
+    feat = bo.bbox_features(d["boxes"], d["counts"])
+    assert feat.dtype == np.float32 and np.array_equal(feat, d["feat"])
+    counts = np.asarray([bo.text_class_counts(str(t)) for t in d["texts"]], dtype=np.int32)
+    assert np.array_equal(counts, d["counts"])
+    assert np.allclose(feat[:, 9:].sum(1), 1.0, atol=1e-6)
+    assert np.array_equal(bo.bbox_features(d["boxes"][:0], d["counts"][:0]), np.zeros((0, 13), np.float32))
+    # the product's host-side counter agrees with the oracle's
+    from gnn_tableextraction_b200.features import text_class_counts
+
+    assert np.array_equal(text_class_counts([str(t) for t in d["texts"]]), d["counts"])
+
+
+def test_page_predictions_oracle():
+    from oracle import bbox_oracle as bo
+
+    rng = np.random.default_rng(0)
+    logits = rng.normal(size=(10, 4)).astype(np.float32)
+    logits[3] = [1.0, 2.0, 2.0, 0.0]  # tie: first maximal index
+    labels = logits.argmax(1).astype(np.float32)
+    labels[0] = (labels[0] + 1) % 4
+    preds, accs, mean = bo.page_predictions(logits, labels, [4, 6])
+    assert preds[3] == 1 and accs == [0.75, 1.0] and abs(mean - 0.875) < 1e-12
