@@ -407,6 +407,7 @@ struct PkMaps {
 struct PkRowArgs {
   const uint8_t* xb;     // staged x slice [rows][CS] (+ one all-zero row at index zrow), already offset by lane * 16
   const uint2* spk;      // staged packed edges of the page
+  const uint2* gpk;      // the same entries in global memory (MG variant: metadata through L1 instead of a stage)
   const int32_t* sptr;   // staged row pointers
   const float* snrm;     // staged row normalisers
   uint32_t zrow;
@@ -429,7 +430,7 @@ struct PkRowArgs {
 // column chunks, U = 2 edges per step.  Every gather is unconditional: edges past the end of a row, and edges that
 // leave the page, read the all-zero row with weight 0 (0 * 0: no NaN can be manufactured from someone else's Inf),
 // and columns >= f were zero-filled by the TMA unit -- so all R*U*VV loads of a step are in flight together.
-template <int G, int V, int VV, int R>
+template <int G, int V, int VV, int R, bool MG>
 __device__ __forceinline__ void pk_row_pass(const PkRowArgs& A, int32_t rl0) {
   constexpr int CS = G * V * 4;
   constexpr int ROW_BYTES = CS * 4;
@@ -487,7 +488,7 @@ __device__ __forceinline__ void pk_row_pass(const PkRowArgs& A, int32_t rl0) {
         for (int u = 0; u < U; ++u) {
           const int32_t e = beg[q] + j + u;
           m[q][u] = make_uint2(PK_OUTSIDE, 0u);
-          if (e < end[q]) m[q][u] = A.spk[e];
+          if (e < end[q]) m[q][u] = MG ? __ldg(A.gpk + e) : A.spk[e];
         }
     };
     auto step = [&](const uint2 (&m)[R][U]) {
@@ -559,15 +560,15 @@ __device__ __forceinline__ void pk_row_pass(const PkRowArgs& A, int32_t rl0) {
   }
 }
 
-template <int G, int V, int VV>
+template <int G, int V, int VV, bool MG>
 __device__ __forceinline__ void pk_rows(const PkRowArgs& A) {
   constexpr int NG = PK_CONSUMERS / G;
   const int grp = threadIdx.x / G;
   for (int32_t rl0 = grp; rl0 < A.it.np; rl0 += 2 * NG) {
     if (rl0 + NG < A.it.np)
-      pk_row_pass<G, V, VV, 2>(A, rl0);
+      pk_row_pass<G, V, VV, 2, MG>(A, rl0);
     else
-      pk_row_pass<G, V, VV, 1>(A, rl0);  // odd row out: no padded second row (its gathers would be pure waste)
+      pk_row_pass<G, V, VV, 1, MG>(A, rl0);  // odd row out: no padded second row (its gathers would be pure waste)
   }
 }
 
@@ -575,7 +576,10 @@ __device__ __forceinline__ void pk_rows(const PkRowArgs& A) {
 // stages cycle through full[s] (producer -> consumers: TMA bytes landed + small copies stored) and empty[s]
 // (consumer warps -> producer: stage may be overwritten) mbarriers; there is no CTA-wide barrier in the loop, so a
 // warp that finishes its rows early starts on the next item at once and the warps drift out of lock step.
-template <int G, int V>
+// MG: the packed edges are NOT staged (pages with many edges): consumers read them from global memory through L1
+// (a row's entries are contiguous, 16 per cache line) and the stages hold only the x slice, so the 64-column
+// configuration fits whatever the degree.
+template <int G, int V, bool MG>
 __global__ void __launch_bounds__(PK_THREADS, 1)
     k_spmm_paged_pk(const __grid_constant__ PkMaps maps, const int32_t* __restrict__ indptr,
                     const uint2* __restrict__ packed, const int32_t* __restrict__ page_flag,
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
   extern __shared__ __align__(128) uint8_t pk_smem[];
   constexpr int CS = G * V * 4;            // columns per slice
   constexpr int ROW_BYTES = CS * 4;
-  const PkStageLayout L = pk_layout(CS, np_cap, ne_cap);
+  const PkStageLayout L = pk_layout(CS, np_cap, MG ? 0 : ne_cap);
   const uint32_t stage_bytes = L.stage_bytes();
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(pk_smem);
   const uint32_t bars = smem0 + 2 * stage_bytes;  // full[0], full[1], empty[0], empty[1]
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
         it.e0 = __ldg(indptr + it.n0);
         it.ne = __ldg(indptr + it.n0 + it.np) - it.e0;
         it.flag = __ldg(page_flag + page);
-        it.staged = (it.np <= np_cap && it.ne <= ne_cap) ? 1 : 0;
+        it.staged = (it.np <= np_cap && (MG || it.ne <= ne_cap)) ? 1 : 0;
       }
       return it;
     };
@@ -643,7 +647,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
           const int nbig = (dbg & 4) ? 0 : it.np / PK_BOX_BIG;
           const int nsmall = (dbg & 4) ? 0 : (it.np - nbig * PK_BOX_BIG + PK_BOX_SMALL - 1) / PK_BOX_SMALL;
           const int e_lo = it.e0 & ~1;  // 16-byte aligned start of the bulk copy
-          const uint32_t pk_copy = it.ne > 0 ? (uint32_t)((it.e0 + it.ne - e_lo + 1) & ~1) * 8u : 0u;
+          const uint32_t pk_copy = (!MG && it.ne > 0) ? (uint32_t)((it.e0 + it.ne - e_lo + 1) & ~1) * 8u : 0u;
           mbar_expect_tx(bar, (uint32_t)(nbig * PK_BOX_BIG + nsmall * PK_BOX_SMALL) * ROW_BYTES + pk_copy);
           for (int b = 0; b < nbig; ++b)
             tma_load_2d(sx + b * PK_BOX_BIG * ROW_BYTES, &maps.big, bar, it.c0, it.n0 + b * PK_BOX_BIG);
@@ -688,14 +692,15 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       A.it = *reinterpret_cast<const PkItem*>(sbase + off_info);
       A.xb = sbase + lane * 16;
       A.spk = reinterpret_cast<const uint2*>(sbase + off_pk) + (A.it.e0 & 1);  // entry j of the page: spk[j]
+      A.gpk = packed + A.it.e0;
       A.sptr = reinterpret_cast<const int32_t*>(sbase + off_ptr);
       A.snrm = reinterpret_cast<const float*>(sbase + off_nrm);
       A.slow = !A.it.staged || A.it.flag != 0;
       // the last slice of a row may need only the first of the two column chunks (F = 218: 7 of 16 chunks)
       if (V == 2 && A.it.c0 + G * 4 >= f)
-        pk_rows<G, V, 1>(A);
+        pk_rows<G, V, 1, MG>(A);
       else
-        pk_rows<G, V, V>(A);
+        pk_rows<G, V, V, MG>(A);
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(bars + 16 + s * 8);  // this warp is done with stage s
     }
@@ -708,17 +713,29 @@ static size_t pk_smem_bytes(int cs, int32_t np_cap, int32_t ne_cap) {
 
 constexpr size_t PK_SMEM_MAX = 227 * 1024;
 
-// (G, V) for feature width f and page capacity, or G = 0 when two stages do not fit in shared memory
-static void pk_pick(int32_t f, int32_t np_cap, int32_t ne_cap, int* G, int* V) {
+// (G, V, MG) for feature width f and page capacity, or G = 0 when two stages do not fit in shared memory.
+// The slice width follows f; for that width the packed edges are staged when they fit and read through L1
+// otherwise; only then a narrower slice is tried.
+static void pk_pick(int32_t f, int32_t np_cap, int32_t ne_cap, int* G, int* V, int* MG) {
   const int fv = (f + 3) / 4;
   *G = 0;
   *V = 0;
-  if (fv > 8 && pk_smem_bytes(64, np_cap, ne_cap) <= PK_SMEM_MAX) {
-    *G = 8, *V = 2;
-  } else if (fv > 4 && pk_smem_bytes(32, np_cap, ne_cap) <= PK_SMEM_MAX) {
-    *G = 8, *V = 1;
-  } else if (pk_smem_bytes(16, np_cap, ne_cap) <= PK_SMEM_MAX) {
-    *G = 4, *V = 1;
+  *MG = 0;
+  // measured order of preference (conv sweep, F = 218): staged edges beat L1 edges even at half the slice width
+  // (degree 20: 35 % vs 26 % of the HBM roofline); L1 edges are for pages whose edges fit no stage (degree 40)
+  struct Cand { int cs, mg; };
+  const Cand wide[] = {{64, 0}, {32, 0}, {64, 1}, {32, 1}, {16, 0}, {16, 1}};
+  const Cand mid[] = {{32, 0}, {32, 1}, {16, 0}, {16, 1}};
+  const Cand narrow[] = {{16, 0}, {16, 1}};
+  const Cand* c = fv > 8 ? wide : (fv > 4 ? mid : narrow);
+  const int nc = fv > 8 ? 6 : (fv > 4 ? 4 : 2);
+  for (int i = 0; i < nc; ++i) {
+    if (pk_smem_bytes(c[i].cs, np_cap, c[i].mg ? 0 : ne_cap) <= PK_SMEM_MAX) {
+      *G = c[i].cs == 16 ? 4 : 8;
+      *V = c[i].cs == 64 ? 2 : 1;
+      *MG = c[i].mg;
+      return;
+    }
   }
 }
 
@@ -731,24 +748,24 @@ static int pk_dbg() {
   return v;
 }
 
-template <int G, int V>
+template <int G, int V, bool MG>
 static int launch_spmm_paged_pk(const int32_t* indptr, const uint2* packed, const int32_t* page_flag,
                                 const int32_t* indices, const int32_t* eid, const float* w, const float* pre_scale,
                                 const float* row_norm, int mode, const float* x, int64_t ldx, const float* addend,
                                 int64_t ldadd, float* y, int64_t ldy, const int32_t* page_off, int32_t num_pages,
                                 int32_t np_cap, int32_t ne_cap, int32_t n_rows, int32_t f, cudaStream_t st) {
   constexpr int CS = G * V * 4;
-  const size_t smem = pk_smem_bytes(CS, np_cap, ne_cap);
+  const size_t smem = pk_smem_bytes(CS, np_cap, MG ? 0 : ne_cap);
   static size_t configured = 0;
   static int occ_smem = -1, occ = 1;
   if (smem > configured) {
-    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_paged_pk<G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_paged_pk<G, V, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "k_spmm_paged_pk(smem attr)");
     configured = smem;
   }
   if (occ_smem != (int)smem) {
     int o = 1;
-    GTE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_spmm_paged_pk<G, V>, PK_THREADS, smem),
+    GTE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_spmm_paged_pk<G, V, MG>, PK_THREADS, smem),
                    "k_spmm_paged_pk(occupancy)");
     occ = o < 1 ? 1 : o;
     occ_smem = (int)smem;
@@ -766,7 +783,7 @@ static int launch_spmm_paged_pk(const int32_t* indptr, const uint2* packed, cons
   int grid = (int)(items < (int64_t)sm_count() * occ ? items : (int64_t)sm_count() * occ);
   const int per = (int)ceil_div64(items, grid);
   grid = (int)ceil_div64(items, per);
-  k_spmm_paged_pk<G, V><<<grid, PK_THREADS, smem, st>>>(maps, indptr, packed, page_flag, indices, eid, w, pre_scale, row_norm,
+  k_spmm_paged_pk<G, V, MG><<<grid, PK_THREADS, smem, st>>>(maps, indptr, packed, page_flag, indices, eid, w, pre_scale, row_norm,
                                                        mode, x, ldx, addend, ldadd, y, ldy, page_off, f, (int32_t)items,
                                                        nslices, per, np_cap, ne_cap, pk_dbg());
   GTE_CHECK_LAUNCH("k_spmm_paged_pk");
@@ -865,9 +882,9 @@ extern "C" int gte_paged_pack_edges(const int32_t* indptr, const int32_t* indice
 
 extern "C" size_t gte_spmm_paged_packed_smem_bytes(int32_t max_page_nodes, int32_t max_page_edges, int32_t f) {
   if (max_page_nodes < 0 || max_page_edges < 0 || f <= 0) return 0;
-  int G, V;
-  pk_pick(f, max_page_nodes, max_page_edges, &G, &V);
-  return G ? pk_smem_bytes(G * V * 4, max_page_nodes, max_page_edges) : 0;
+  int G, V, MG;
+  pk_pick(f, max_page_nodes, max_page_edges, &G, &V, &MG);
+  return G ? pk_smem_bytes(G * V * 4, max_page_nodes, MG ? 0 : max_page_edges) : 0;
 }
 
 extern "C" int gte_spmm_paged_packed(const int32_t* indptr, const uint64_t* packed, const int32_t* page_flag,
@@ -887,19 +904,23 @@ extern "C" int gte_spmm_paged_packed(const int32_t* indptr, const uint64_t* pack
   GTE_CHECK_ARG(x != y, "gte_spmm_paged_packed: x and y must not alias");
   const bool vec = aligned16(x) && aligned16(y) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
                    (!addend || (aligned16(addend) && ldadd % 4 == 0));
-  int G, V;
-  pk_pick(f, max_page_nodes, max_page_edges, &G, &V);
+  int G, V, MG;
+  pk_pick(f, max_page_nodes, max_page_edges, &G, &V, &MG);
   if (!vec || G == 0)
     return fail(GTE_ERR_UNSUPPORTED,
                 "gte_spmm_paged_packed: operands not 16-byte aligned or pages too large to stage (query "
                 "gte_spmm_paged_packed_smem_bytes first); use gte_spmm_paged");
   cudaStream_t st = as_stream(stream);
   const uint2* pk = reinterpret_cast<const uint2*>(packed);
-#define GTE_PK_GO(GG, VV)                                                                                                  \
-  return launch_spmm_paged_pk<GG, VV>(indptr, pk, page_flag, indices, eid, w, pre_scale, row_norm, mode, x, ldx, addend, \
-                                      ldadd, y, ldy, page_off, num_pages, max_page_nodes, max_page_edges, n_rows, f, st)
-  if (G == 8 && V == 2) GTE_PK_GO(8, 2);
-  if (G == 8) GTE_PK_GO(8, 1);
-  GTE_PK_GO(4, 1);
+#define GTE_PK_GO(GG, VV, MM)                                                                                              \
+  return launch_spmm_paged_pk<GG, VV, MM>(indptr, pk, page_flag, indices, eid, w, pre_scale, row_norm, mode, x, ldx,     \
+                                          addend, ldadd, y, ldy, page_off, num_pages, max_page_nodes, max_page_edges,    \
+                                          n_rows, f, st)
+  if (G == 8 && V == 2 && !MG) GTE_PK_GO(8, 2, false);
+  if (G == 8 && V == 2) GTE_PK_GO(8, 2, true);
+  if (G == 8 && !MG) GTE_PK_GO(8, 1, false);
+  if (G == 8) GTE_PK_GO(8, 1, true);
+  if (!MG) GTE_PK_GO(4, 1, false);
+  GTE_PK_GO(4, 1, true);
 #undef GTE_PK_GO
 }

@@ -92,6 +92,8 @@ def _use_packed(g: PageGraphBatch, x: torch.Tensor, addend: Optional[torch.Tenso
     largest page in shared memory; everything else goes to gte_spmm_paged / gte_spmm."""
     if SPMM_MODE in ("paged", "rows"):
         return False
+    if 16 < x.shape[1] <= 32 and SPMM_MODE != "packed":
+        return False  # 5..8 chunks per row: the one-CTA-per-(page, slice) kernel measures faster (conv sweep, F = 32)
     return (ops.paged_packed_supported(g.pages(), x.shape[1]) and ops._aligned_mat(x)
             and (addend is None or ops._aligned_mat(addend)))
 

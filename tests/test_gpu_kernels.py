@@ -448,6 +448,26 @@ def test_spmm_paged_packed_equals_generic(f, ragged):
     assert torch.equal(ops.spmm(ip, ix, None, x), ops.spmm_packed(ip, pk1, x, pg))
 
 
+@pytest.mark.parametrize("f", [13, 64, 218])
+def test_spmm_paged_packed_high_degree_reads_edges_through_l1(f):
+    """pages whose packed edges do not fit a shared-memory stage next to the x slice (in-degree 45): the kernel
+    variant that reads the edge entries from global memory gives the same bits"""
+    pages = synth.make_pages(6, k=45, n=300)
+    s, d, w, noff, _ = csx.batch_coo(pages)
+    n = int(noff[-1])
+    ip, ix, ei = ops.csx_from_coo(_i32(d), _i32(s), n)
+    wd = _f32(w)
+    w_row = ops.gather_f32(wd, ei)
+    norm = ops.degree_norm(ip)
+    x, add = _padded(torch.randn(n, f)), _padded(torch.randn(n, f))
+    pg = (_i32(noff), len(pages), 300, int(max(p.num_edges for p in pages)))
+    assert pg[3] >= 300 * 45 and ops.paged_packed_supported(pg, f)
+    pk = ops.paged_pack_edges(ip, ix, wd, pg, eid=ei, pre_scale=norm)
+    a = ops.spmm(ip, ix, w_row, x, pre_scale=norm, mode=_lib.GTE_AGG_SUM, addend=add)
+    b = ops.spmm_packed(ip, pk, x, pg, mode=_lib.GTE_AGG_SUM, addend=add)
+    assert torch.equal(a, b)
+
+
 def test_spmm_paged_packed_wrong_page_table_and_small_capacity():
     """a page table that does not describe a block-diagonal graph (edges leave their page), and page
     capacities smaller than the real pages: the slow path keeps the result correct"""
