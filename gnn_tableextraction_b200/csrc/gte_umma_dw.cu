@@ -327,7 +327,19 @@ __global__ void __launch_bounds__(RED_THREADS) k_umma_dw_reduce(const DwReduceAr
   *p = v;
 }
 
-constexpr int DW_CHUNK_ROWS = 512;
+constexpr int DW_CHUNK_ROWS_DEFAULT = 512;
+constexpr int DW_MIN_CHUNK_ROWS = 384;          // smallest chunk dw_launch may choose: bounds the workspace
+// rows per accumulation chunk (GTE_DW_CHUNK overrides for experiments; multiple of 32)
+static int dw_chunk_rows() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("GTE_DW_CHUNK");
+    v = e ? atoi(e) : DW_CHUNK_ROWS_DEFAULT;
+    if (v < 32 || v % 32) v = DW_CHUNK_ROWS_DEFAULT;
+  }
+  return v;
+}
+#define DW_CHUNK_ROWS dw_chunk_rows()
 
 static size_t dw_smem_bytes(int max_boxes) {
   return 1024 + (size_t)DW_STAGES * (2 * 4 * DW_BOX_BYTES + 2 * (size_t)max_boxes * DW_BOX_BYTES) + 4 * 32 * DW_STAGE_LD * 4 +
@@ -349,6 +361,27 @@ static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
     if (atoi(e) == 1) { a.dbg_lbo = 512; a.dbg_sbo = DW_BOX_BYTES; }
     if (atoi(e) == 2) { a.dbg_lbo = DW_BOX_BYTES; a.dbg_sbo = DW_BOX_BYTES; }
     if (atoi(e) == 3) { a.dbg_lbo = DW_BOX_BYTES; a.dbg_sbo = 1024; }
+  }
+  // Rows per accumulation chunk: 12..20 k-blocks (384..640 rows; the accuracy experiments behind the default of 16
+  // hold for this whole range), chosen so that the persistent CTAs finish together: cost = rounds * k-blocks with
+  // rounds = ceil(chunks * items_per_chunk / SMs).  N = 153600, 4 items per chunk: 19 k-blocks -> 7 rounds (133)
+  // instead of 16 -> 9 rounds (144).
+  if (a.n > 0 && a.nchunks > 0 && !getenv("GTE_DW_CHUNK")) {
+    const int sms = sm_count();
+    int best_kb = DW_CHUNK_ROWS_DEFAULT / DW_KB;
+    int64_t best_cost = -1;
+    for (int kb = DW_MIN_CHUNK_ROWS / DW_KB; kb <= 20; ++kb) {
+      const int64_t chunks = ceil_div64(a.n, (int64_t)kb * DW_KB);
+      const int64_t rounds = ceil_div64(chunks * a.items_per_chunk, sms);
+      const int64_t cost = rounds * kb;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_kb = kb;
+      }
+    }
+    a.chunk_rows = best_kb * DW_KB;
+    a.nchunks = (int)ceil_div64(a.n, a.chunk_rows);
+    r.nchunks = a.nchunks;
   }
   const int items = a.nchunks * a.items_per_chunk;
   int grid = sm_count();
@@ -383,7 +416,7 @@ int gte_umma_bwd_weight_supported(int32_t fo, int32_t k1, int32_t k2) {
 
 size_t gte_umma_bwd_weight_workspace_bytes(int32_t n, int32_t fo, int32_t k1, int32_t k2) {
   if (!gte_umma_bwd_weight_supported(fo, k1, k2) || n < 0) return 0;
-  const int64_t nchunks = ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS);
+  const int64_t nchunks = ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS < DW_MIN_CHUNK_ROWS ? DW_CHUNK_ROWS : DW_MIN_CHUNK_ROWS);
   const int64_t rows = ceil_div64(fo, 128) * 128;
   const int64_t ldp = 32 * (boxes_of(k1) + boxes_of(k2));
   return (size_t)(nchunks * rows * ldp * 4 + 256);
@@ -478,7 +511,7 @@ int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const 
 //   dW[:, col1:col1+k] (+)= dz1^T x ; dW[:, col2:col2+k] (+)= dz2^T x ; db (+)= colsum(dz1)
 size_t gte_umma_bwd_weight2_workspace_bytes(int32_t n, int32_t fo, int32_t k) {
   if (n < 0 || fo < 1 || fo > 32 || k < 1 || k > 256) return 0;
-  const int64_t nchunks = ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS);
+  const int64_t nchunks = ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS < DW_MIN_CHUNK_ROWS ? DW_CHUNK_ROWS : DW_MIN_CHUNK_ROWS);
   const int64_t rows = ceil_div64(k + 1, 128) * 128;
   return (size_t)(nchunks * rows * 64 * 4 + 256);
 }
