@@ -338,7 +338,9 @@ static int launch_spmm_paged(const int32_t* indptr, const int32_t* indices, cons
 //     group's metadata loaded ahead, so 8 independent 128-bit shared loads are in flight per lane,
 //   * prefetches the addend rows of the next item into L2 when it stages that item.
 // Sums run in row order exactly like the kernels above (deterministic, same rounding).
-constexpr int PK_CONSUMERS = 512;               // 16 consumer warps
+// 15 consumer warps + 1 producer warp = 16 warps = 4 per SM sub-partition, so each thread may use 128 registers
+// (17 warps put 5 on one sub-partition and cap everybody at 96: the compiler then splits the gather batches)
+constexpr int PK_CONSUMERS = 480;
 constexpr int PK_THREADS = PK_CONSUMERS + 32;   // + 1 producer warp
 constexpr int PK_BOX_BIG = 64;    // rows per large TMA box
 constexpr int PK_BOX_SMALL = 8;   // rows per small TMA box (page tail): at most 7 rows over-read per page
