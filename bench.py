@@ -119,7 +119,7 @@ class ClockSampler:
 class OpTimer:
     """Wraps the tensor-level ops with CUDA events on the launching stream."""
 
-    NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "spmm_packed", "paged_pack_edges", "gram_stream", "wide_out", "linear_fwd", "linear_bwd_data",
+    NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "spmm_packed", "paged_pack_edges", "build_page_formats", "gram_stream", "wide_out", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
              "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2", "umma_linear_fwd_stacked", "umma_linear_bwd_data2"]
 

@@ -134,3 +134,208 @@ extern "C" int gte_bbox_features(const int32_t* boxes, const int32_t* counts, in
   GTE_CHECK_LAUNCH("k_bbox_features");
   return GTE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Batch assembly of a page batch in ONE kernel (replaces `dgl.batch(...)`'s lazy
+// COO -> CSC and COO -> CSR builds of /root/reference/src/models/model_train.py:297 + the per-layer
+// `in_degrees` / `get_norm` of models.py:74-78):  one CTA per page sorts the page's edges by destination (CSC,
+// forward) and by source (CSR, backward) entirely in shared memory -- stable, i.e. bit-identical to
+// gte_csx_from_coo / a stable argsort of the batched COO -- and emits, in the same pass, the degree normaliser
+// and the packed edge entries the conv-layer kernel stages (gte_paged_pack_edges' output for both directions).
+// dgl.batch's contract is assumed: nodes and edges of page p occupy [page_off[p], page_off[p+1]) and
+// [edge_off[p], edge_off[p+1]); an edge with an endpoint outside its page raises *bad (results undefined).
+namespace gte {
+
+constexpr int PF_THREADS = 256;
+
+struct PfOut {
+  int32_t *indptr, *indices, *eid;
+  uint2* packed;
+};
+
+__global__ void __launch_bounds__(PF_THREADS)
+    k_build_page_formats(const int32_t* __restrict__ src, const int32_t* __restrict__ dst, const float* __restrict__ w,
+                         const int32_t* __restrict__ page_off, const int32_t* __restrict__ edge_off, int32_t num_pages,
+                         int32_t np_cap, int32_t ne_cap, PfOut csc, PfOut csr, float* __restrict__ norm,
+                         int* __restrict__ bad) {
+  extern __shared__ __align__(16) int32_t pf_smem[];
+  int32_t* s_src = pf_smem;                 // [ne_cap] page-local source of edge i
+  int32_t* s_dst = s_src + ne_cap;          // [ne_cap]
+  int32_t* slot_in = s_dst + ne_cap;        // [ne_cap] edge index per CSC position
+  int32_t* slot_out = slot_in + ne_cap;     // [ne_cap]
+  int32_t* ptr_in = slot_out + ne_cap;      // [np_cap + 1]
+  int32_t* ptr_out = ptr_in + np_cap + 1;   // [np_cap + 1]
+  int32_t* cur_in = ptr_out + np_cap + 1;   // [np_cap] counts, then fill cursors
+  int32_t* cur_out = cur_in + np_cap;       // [np_cap]
+  float* s_norm = reinterpret_cast<float*>(cur_out + np_cap);  // [np_cap]
+  __shared__ int32_t warp_tot[2][PF_THREADS / 32];
+  __shared__ int32_t carry[2];
+  const int tid = threadIdx.x;
+  const int page = blockIdx.x;
+  const int32_t n0 = page_off[page], np = page_off[page + 1] - n0;
+  const int32_t e0 = edge_off[page], ne = edge_off[page + 1] - e0;
+  if (np > np_cap || ne > ne_cap) {  // cannot happen when the caller's maxima are right
+    if (tid == 0) *bad = 2;
+    return;
+  }
+  for (int i = tid; i < np; i += PF_THREADS) cur_in[i] = cur_out[i] = 0;
+  __syncthreads();
+  // 1. local ids + in/out degree counts
+  for (int i = tid; i < ne; i += PF_THREADS) {
+    const int32_t s = src[e0 + i] - n0, d = dst[e0 + i] - n0;
+    const bool ok = s >= 0 && s < np && d >= 0 && d < np;
+    if (!ok) *bad = 1;
+    s_src[i] = ok ? s : 0;
+    s_dst[i] = ok ? d : 0;
+    if (ok) {
+      atomicAdd(&cur_in[d], 1);
+      atomicAdd(&cur_out[s], 1);
+    }
+  }
+  __syncthreads();
+  // 2. exclusive scans of both degree arrays (block scan, PF_THREADS entries per round)
+  if (tid < 2) carry[tid] = 0;
+  __syncthreads();
+  for (int base = 0; base < np; base += PF_THREADS) {
+    const int i = base + tid;
+    int32_t v[2] = {i < np ? cur_in[i] : 0, i < np ? cur_out[i] : 0};
+    int32_t incl[2] = {v[0], v[1]};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t0 = __shfl_up_sync(0xffffffffu, incl[0], o), t1 = __shfl_up_sync(0xffffffffu, incl[1], o);
+      if ((tid & 31) >= o) {
+        incl[0] += t0;
+        incl[1] += t1;
+      }
+    }
+    if ((tid & 31) == 31) {
+      warp_tot[0][tid >> 5] = incl[0];
+      warp_tot[1][tid >> 5] = incl[1];
+    }
+    __syncthreads();
+    int32_t woff[2] = {0, 0};
+    for (int k = 0; k < (tid >> 5); ++k) {
+      woff[0] += warp_tot[0][k];
+      woff[1] += warp_tot[1][k];
+    }
+    const int32_t ex0 = carry[0] + woff[0] + incl[0] - v[0], ex1 = carry[1] + woff[1] + incl[1] - v[1];
+    if (i < np) {
+      ptr_in[i] = ex0;
+      ptr_out[i] = ex1;
+    }
+    __syncthreads();
+    if (tid == PF_THREADS - 1) {
+      carry[0] = ex0 + v[0];
+      carry[1] = ex1 + v[1];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ptr_in[np] = ne;
+    ptr_out[np] = ne;
+  }
+  // 3. row pointers, normaliser; reset the cursors
+  for (int i = tid; i < np; i += PF_THREADS) {
+    const int32_t deg = cur_in[i];
+    const float nv = deg > 0 ? 1.0f / (float)deg : 0.0f;  // 1./in_degree, inf -> 0 (models.py:75-76)
+    s_norm[i] = nv;
+    norm[n0 + i] = nv;
+    csc.indptr[n0 + i] = e0 + ptr_in[i];
+    csr.indptr[n0 + i] = e0 + ptr_out[i];
+    cur_in[i] = 0;
+    cur_out[i] = 0;
+  }
+  if (page == num_pages - 1 && tid == 0) {
+    csc.indptr[n0 + np] = e0 + ne;
+    csr.indptr[n0 + np] = e0 + ne;
+  }
+  __syncthreads();
+  // 4. scatter edge indices into their rows (any order inside a row) ...
+  for (int i = tid; i < ne; i += PF_THREADS) {
+    const int32_t s = s_src[i], d = s_dst[i];
+    slot_in[ptr_in[d] + atomicAdd(&cur_in[d], 1)] = i;
+    slot_out[ptr_out[s] + atomicAdd(&cur_out[s], 1)] = i;
+  }
+  __syncthreads();
+  // 5. ... then order every row by edge index (= stable sort of the COO): rows are short, one thread per row
+  for (int r = tid; r < 2 * np; r += PF_THREADS) {
+    int32_t* slot = r < np ? slot_in : slot_out;
+    const int32_t* ptr = r < np ? ptr_in : ptr_out;
+    const int rr = r < np ? r : r - np;
+    const int b = ptr[rr], e = ptr[rr + 1];
+    for (int a = b + 1; a < e; ++a) {
+      const int32_t v = slot[a];
+      int c = a - 1;
+      while (c >= b && slot[c] > v) {
+        slot[c + 1] = slot[c];
+        --c;
+      }
+      slot[c + 1] = v;
+    }
+  }
+  __syncthreads();
+  // 6. write both formats and their packed entries
+  for (int j = tid; j < ne; j += PF_THREADS) {
+    const int32_t i = slot_in[j];
+    const float wv = w ? __ldg(w + e0 + i) : 1.0f;
+    csc.indices[e0 + j] = n0 + s_src[i];
+    csc.eid[e0 + j] = e0 + i;
+    csc.packed[e0 + j] = make_uint2((uint32_t)s_src[i], __float_as_uint(wv));
+    const int32_t k = slot_out[j];
+    float wk = w ? __ldg(w + e0 + k) : 1.0f;
+    wk *= s_norm[s_dst[k]];  // source-side scale of the backward aggregation: norm[dst]
+    csr.indices[e0 + j] = n0 + s_dst[k];
+    csr.eid[e0 + j] = e0 + k;
+    csr.packed[e0 + j] = make_uint2((uint32_t)s_dst[k], __float_as_uint(wk));
+  }
+}
+
+static size_t pf_smem_bytes(int32_t np_cap, int32_t ne_cap) {
+  return ((size_t)4 * ne_cap + 2 * ((size_t)np_cap + 1) + 3 * (size_t)np_cap) * 4 + 16;
+}
+
+}  // namespace gte
+
+extern "C" size_t gte_build_page_formats_smem_bytes(int32_t max_page_nodes, int32_t max_page_edges) {
+  if (max_page_nodes < 0 || max_page_edges < 0) return 0;
+  const size_t b = gte::pf_smem_bytes(max_page_nodes, max_page_edges);
+  return b <= 227 * 1024 ? b : 0;
+}
+
+extern "C" int gte_build_page_formats(const int32_t* src, const int32_t* dst, const float* w, const int32_t* page_off,
+                                      const int32_t* edge_off, int32_t num_pages, int32_t n, int64_t e,
+                                      int32_t max_page_nodes, int32_t max_page_edges, int32_t* csc_indptr,
+                                      int32_t* csc_indices, int32_t* csc_eid, uint64_t* csc_packed, int32_t* csr_indptr,
+                                      int32_t* csr_indices, int32_t* csr_eid, uint64_t* csr_packed, float* norm,
+                                      int32_t* page_flag, int32_t* bad, gte_stream_t stream) {
+  GTE_CHECK_ARG(num_pages >= 0 && n >= 0 && e >= 0 && max_page_nodes >= 0 && max_page_edges >= 0,
+                "gte_build_page_formats: negative size");
+  const size_t smem = gte_build_page_formats_smem_bytes(max_page_nodes, max_page_edges);
+  if (smem == 0)
+    return fail(GTE_ERR_UNSUPPORTED, "gte_build_page_formats: a page of %d nodes / %d edges does not fit in shared memory",
+                max_page_nodes, max_page_edges);
+  GTE_CHECK_ARG(page_off && edge_off && csc_indptr && csr_indptr && norm && bad && page_flag,
+                "gte_build_page_formats: null argument");
+  GTE_CHECK_ARG(e == 0 || (src && dst && csc_indices && csc_eid && csc_packed && csr_indices && csr_eid && csr_packed),
+                "gte_build_page_formats: null edge argument");
+  cudaStream_t st = as_stream(stream);
+  GTE_CHECK_CUDA(cudaMemsetAsync(bad, 0, 4, st), "gte_build_page_formats(memset bad)");
+  if (num_pages == 0) {
+    GTE_CHECK_CUDA(cudaMemsetAsync(csc_indptr, 0, 4, st), "gte_build_page_formats(memset)");
+    GTE_CHECK_CUDA(cudaMemsetAsync(csr_indptr, 0, 4, st), "gte_build_page_formats(memset)");
+    return GTE_OK;
+  }
+  GTE_CHECK_CUDA(cudaMemsetAsync(page_flag, 0, (size_t)num_pages * 4, st), "gte_build_page_formats(memset flags)");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_build_page_formats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "k_build_page_formats(smem attr)");
+    configured = smem;
+  }
+  PfOut a{csc_indptr, csc_indices, csc_eid, reinterpret_cast<uint2*>(csc_packed)};
+  PfOut b{csr_indptr, csr_indices, csr_eid, reinterpret_cast<uint2*>(csr_packed)};
+  k_build_page_formats<<<num_pages, PF_THREADS, smem, st>>>(src, dst, w, page_off, edge_off, num_pages, max_page_nodes,
+                                                           max_page_edges, a, b, norm, bad);
+  GTE_CHECK_LAUNCH("k_build_page_formats");
+  return GTE_OK;
+}

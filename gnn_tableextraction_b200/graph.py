@@ -189,6 +189,38 @@ class PageGraphBatch:
         self._cache[which] = (key, out, w)  # holding `w` keeps its address from being recycled
         return out
 
+    def prepare(self, w: Optional[torch.Tensor]) -> bool:
+        """Batch assembly in one kernel (``gte_build_page_formats``): CSC, CSR, the degree normaliser and the packed
+        edges of both directions for the edge weights ``w`` -- everything the layers ask this object for.  Used when
+        the batch has a page table, the largest page fits in shared memory and nothing was built yet; otherwise the
+        individual builders run lazily as before.  Returns True when the formats are in place."""
+        if "csc" in self._cache or "csr" in self._cache:
+            return False
+        pages = self.pages()
+        if w is None or not ops.page_formats_supported(pages) or len(self._be) != pages[1] \
+                or sum(self._be) != self.num_edges():
+            return False
+        w = _edge_weight_1d(w, self.num_edges())
+        if len(pages) < 5:
+            return False
+        eoff = pages[4]
+        csc, csr, norm, pk_csc, pk_csr, bad = ops.build_page_formats(self._src, self._dst, w, pages[0], eoff, pages[1], self._n,
+                                                                     pages[2], pages[3])
+        key = (w.data_ptr(), w._version, int(w.numel()))
+        self._cache["csc"], self._cache["csr"] = csc, csr
+        self._cache[f"norm{_lib.GTE_NORM_INV_DEG_ZERO}"] = norm
+        self._cache["pk_csc"] = (key, pk_csc, w)
+        self._cache["pk_csr"] = (key, pk_csr, w)
+        self._cache["bad"] = bad  # device flag: 1 = an edge leaves its page (check_page_structure() reads it)
+        return True
+
+    def check_page_structure(self) -> None:
+        """Host check (synchronises) that the one-kernel batch assembly saw a truthful page table."""
+        bad = self._cache.get("bad")
+        if bad is not None and int(bad.item()) != 0:
+            raise GteError("PageGraphBatch: an edge leaves its page (batch_num_nodes / batch_num_edges do not describe "
+                           "this graph); build it without page sizes to use the generic kernels")
+
     def packed_edges(self, which: str, w: torch.Tensor) -> "ops.PackedEdges":
         """Edges of the CSC (``which='csc'``, forward) or of the CSR with the source-side scale
         ``norm[dst]`` folded in (``'csr'``, backward), packed once per batch for the page kernel."""
@@ -226,8 +258,8 @@ def _edge_weight_1d(w: torch.Tensor, num_edges: int) -> torch.Tensor:
 
 
 def page_table(batch_num_nodes, batch_num_edges, num_nodes: int, device):
-    """(page_off int32 [P+1] device tensor, P, max page nodes, max page edges) or None (no useful page
-    structure).  Pages are closed under edges, so the per-page edge counts hold for the CSC and the CSR."""
+    """(page_off int32 [P+1] device tensor, P, max page nodes, max page edges, edge_off int32 [P+1] device tensor)
+    or None (no useful page structure).  Pages are closed under edges, so the per-page edge counts hold for the CSC and the CSR."""
     bn = list(batch_num_nodes) if batch_num_nodes is not None else []
     be = list(batch_num_edges) if batch_num_edges is not None else []
     mx = max(bn) if bn else 0
@@ -235,7 +267,12 @@ def page_table(batch_num_nodes, batch_num_edges, num_nodes: int, device):
         return None
     off = np.zeros(len(bn) + 1, dtype=np.int32)
     np.cumsum(np.asarray(bn, dtype=np.int64), out=off[1:])
-    return (torch.from_numpy(off).to(device), len(bn), int(mx), int(max(be)))
+    eoff = np.zeros(len(be) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(be, dtype=np.int64), out=eoff[1:])
+    if eoff[-1] >= 2 ** 31:
+        return None
+    # [4] = edge offsets of the pages (dgl.batch concatenates edges in page order): the one-kernel batch assembly
+    return (torch.from_numpy(off).to(device), len(bn), int(mx), int(max(be)), torch.from_numpy(eoff.astype(np.int32)).to(device))
 
 
 def batch_pages_host(pages, pin: bool = True) -> Dict[str, torch.Tensor]:

@@ -84,6 +84,7 @@ def use_umma_dw(n: int, fo: int, k1: int, k2: int, db_needed: bool, *mats) -> bo
     return GEMM_MODE == "umma" or n >= UMMA_MIN_ROWS
 
 
+PAGE_FORMATS = os.environ.get("GTE_PAGE_FORMATS", "1") != "0"  # one-kernel batch assembly (0: individual builders)
 SPMM_MODE = os.environ.get("GTE_SPMM", "auto")  # auto | packed | paged | rows (diagnostics / A-B runs)
 
 
@@ -105,6 +106,8 @@ def _agg_mode(agg: str) -> int:
 def aggregate_forward(g: PageGraphBatch, h: torch.Tensor, w_edge: torch.Tensor, agg: str = GCN,
                       addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``update_all(u_mul_e, sum|mean)`` (+ ``* norm``): models.py:53-54,69-71,149."""
+    if PAGE_FORMATS:
+        g.prepare(w_edge)  # first call per batch: CSC + CSR + norm + packed edges in one kernel
     indptr, indices, _ = g.csc()
     if _use_packed(g, h, addend):
         return ops.spmm_packed(indptr, g.packed_edges("csc", w_edge), h, g.pages(), mode=_agg_mode(agg),
@@ -116,6 +119,8 @@ def aggregate_forward(g: PageGraphBatch, h: torch.Tensor, w_edge: torch.Tensor, 
 def aggregate_backward(g: PageGraphBatch, d_out: torch.Tensor, w_edge: torch.Tensor,
                        addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     """d h[u] = sum_{u->v} w_e * norm[v] * d_out[v] (+ addend[u]) on the CSR (reverse graph)."""
+    if PAGE_FORMATS:
+        g.prepare(w_edge)
     indptr, indices, _ = g.csr()
     if _use_packed(g, d_out, addend):
         return ops.spmm_packed(indptr, g.packed_edges("csr", w_edge), d_out, g.pages(), mode=_lib.GTE_AGG_SUM,

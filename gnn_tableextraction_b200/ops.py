@@ -162,7 +162,7 @@ def spmm(indptr, indices, w, x, *, mode=_lib.GTE_AGG_SUM, row_norm=None, pre_sca
         if fa != f or addend.shape[0] != n_rows:
             raise GteError("spmm: addend shape mismatch")
     if pages is not None and pages[1] > 0:
-        page_off, num_pages, max_nodes, max_edges = pages
+        page_off, num_pages, max_nodes, max_edges = pages[:4]
         check(
             lib().gte_spmm_paged(_vec(indptr, "indptr", torch.int32), _vec(indices, "indices", torch.int32),
                                  _vec(w, "w", n=indices.numel()), _vec(pre_scale, "pre_scale"),
@@ -231,7 +231,7 @@ def spmm_packed(indptr, pk: PackedEdges, x, pages, *, mode=_lib.GTE_AGG_SUM, row
         ap, lda, fa = _mat(addend, "spmm.addend")
         if fa != f or addend.shape[0] != n_rows:
             raise GteError("spmm: addend shape mismatch")
-    page_off, num_pages, max_nodes, max_edges = pages
+    page_off, num_pages, max_nodes, max_edges = pages[:4]
     check(
         lib().gte_spmm_paged_packed(_vec(indptr, "indptr", torch.int32), pk.packed.data_ptr(), pk.page_flag.data_ptr(),
                                     _vec(pk.indices, "indices", torch.int32), _vec(pk.eid, "eid", torch.int32),
@@ -701,6 +701,35 @@ def page_predictions(logits, page_off, num_pages: int, labels=None):
     check(lib().gte_page_predictions(lp, ld, n, c, labp, ldt, _vec(page_off, "page_off", torch.int32, num_pages + 1), num_pages,
                                      preds.data_ptr(), _ptr(correct), _stream()), "gte_page_predictions")
     return preds, (correct[:num_pages] if correct is not None else None)
+
+
+def page_formats_supported(pages) -> bool:
+    return pages is not None and pages[1] > 0 and lib().gte_build_page_formats_smem_bytes(int(pages[2]), int(pages[3])) > 0
+
+
+def build_page_formats(src, dst, w, page_off, edge_off, num_pages: int, n: int, max_nodes: int, max_edges: int):
+    """One-kernel batch assembly (gte_build_page_formats): returns
+    (csc, csr, norm, pk_csc, pk_csr, bad) with csc/csr = (indptr, indices, eid), pk_* = PackedEdges, bad = device int32
+    flag (1 when an edge leaves its page: the dgl.batch contract is broken and the results are undefined)."""
+    _req_cuda(src, dst, w, page_off, edge_off)
+    e = src.numel()
+    dev = src.device
+    i32 = torch.int32
+    csc = (torch.empty(n + 1, dtype=i32, device=dev), torch.empty(e, dtype=i32, device=dev), torch.empty(e, dtype=i32, device=dev))
+    csr = (torch.empty(n + 1, dtype=i32, device=dev), torch.empty(e, dtype=i32, device=dev), torch.empty(e, dtype=i32, device=dev))
+    pk_in = torch.empty(e + 2, dtype=torch.int64, device=dev)
+    pk_out = torch.empty(e + 2, dtype=torch.int64, device=dev)
+    norm = torch.empty(n, dtype=torch.float32, device=dev)
+    flag = torch.empty(max(num_pages, 1), dtype=i32, device=dev)
+    bad = torch.empty(1, dtype=i32, device=dev)
+    check(lib().gte_build_page_formats(_vec(src, "src", i32), _vec(dst, "dst", i32), _vec(w, "w", n=e),
+                                       _vec(page_off, "page_off", i32, num_pages + 1), _vec(edge_off, "edge_off", i32, num_pages + 1),
+                                       num_pages, n, e, max_nodes, max_edges, csc[0].data_ptr(), csc[1].data_ptr(), csc[2].data_ptr(),
+                                       pk_in.data_ptr(), csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(), pk_out.data_ptr(),
+                                       norm.data_ptr(), flag.data_ptr(), bad.data_ptr(), _stream()), "gte_build_page_formats")
+    pk_csc = PackedEdges(pk_in, flag, csc[1], csc[2], w, None)
+    pk_csr = PackedEdges(pk_out, flag, csr[1], csr[2], w, norm)
+    return csc, csr, norm, pk_csc, pk_csr, bad
 
 
 def bbox_features(boxes: torch.Tensor, counts: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -390,6 +390,25 @@ int gte_page_predictions(const float* logits, int64_t ld, int32_t n, int32_t c, 
                          int32_t* page_correct, gte_stream_t stream);
 
 /*
+ * Batch assembly of a page batch in ONE kernel: everything the layers need from
+ * `dgl.batch(train_batch).to(device)` (model_train.py:297) and `get_norm` (models.py:74-78).  One CTA per page
+ * sorts the page's edges by destination (CSC) and by source (CSR) in shared memory; outputs are bit-identical to
+ * gte_csx_from_coo on the batched COO (stable), gte_degree_norm(INV_DEG_ZERO) and gte_paged_pack_edges
+ * (CSC: weights; CSR: weights * norm[dst]).  Contract of dgl.batch: nodes / edges of page p occupy
+ * [page_off[p], page_off[p+1]) / [edge_off[p], edge_off[p+1]) and no edge leaves its page; *bad (device int) is set to
+ * 1 otherwise (results undefined) -- page_flag[] is cleared (no out-of-page edges by contract).  `w` NULL = all ones.
+ * packed arrays need e + 1 entries (see gte_spmm_paged_packed).  gte_build_page_formats_smem_bytes returns 0 when the
+ * largest page does not fit in shared memory (use gte_csx_from_coo + gte_degree_norm + gte_paged_pack_edges then).
+ */
+size_t gte_build_page_formats_smem_bytes(int32_t max_page_nodes, int32_t max_page_edges);
+int gte_build_page_formats(const int32_t* src, const int32_t* dst, const float* w, const int32_t* page_off,
+                           const int32_t* edge_off, int32_t num_pages, int32_t n, int64_t e,
+                           int32_t max_page_nodes, int32_t max_page_edges,
+                           int32_t* csc_indptr, int32_t* csc_indices, int32_t* csc_eid, uint64_t* csc_packed,
+                           int32_t* csr_indptr, int32_t* csr_indices, int32_t* csr_eid, uint64_t* csr_packed,
+                           float* norm, int32_t* page_flag, int32_t* bad, gte_stream_t stream);
+
+/*
  * BBOX node features on the device (src/components/nlp/bbox.py:49-54 get_shape, :57-111 get_histogram, called
  * per batch at model_train.py:293): boxes [n, 4] int32 = [x0, y0, x1, y1]; counts [n, 3] int32 = (letters,
  * digits, other symbols) of the box text with blanks removed (str.isalpha / str.isdigit are host string

@@ -682,3 +682,30 @@ def test_page_predictions_match_torch_argmax(ldt):
     assert correct.cpu().tolist() == want
     p2, c2 = ops.page_predictions(_padded(logits), off, len(sizes))
     assert torch.equal(p2, preds) and c2 is None
+
+
+@pytest.mark.parametrize("ragged,k,bidir", [(False, 10, False), (True, 7, False), (True, 5, True), (False, 45, False)])
+def test_build_page_formats_bit_exact(ragged, k, bidir):
+    """one-kernel batch assembly == stable argsort oracle (CSC and CSR), == gte_degree_norm, == gte_paged_pack_edges"""
+    pages = synth.make_pages(23, ragged=ragged, k=k, bidirectional=bidir, n=300 if k < 40 else 120)
+    s, d, w, noff, eoff = csx.batch_coo(pages)
+    n = int(noff[-1])
+    mx_n, mx_e = int(max(p.num_nodes for p in pages)), int(max(p.num_edges for p in pages))
+    sd, dd, wd = _i32(s), _i32(d), _f32(w)
+    csc, csr, norm, pk_csc, pk_csr, bad = ops.build_page_formats(sd, dd, wd, _i32(noff), _i32(eoff), len(pages), n, mx_n, mx_e)
+    assert int(bad.item()) == 0
+    for got, (key, other) in ((csc, (d, s)), (csr, (s, d))):
+        ip, ix, ei = csx.csx_from_coo(key, other, n)
+        assert np.array_equal(got[0].cpu().numpy(), ip) and np.array_equal(got[1].cpu().numpy(), ix)
+        assert np.array_equal(got[2].cpu().numpy(), ei)
+    assert torch.equal(norm, ops.degree_norm(csc[0]))
+    pg = (_i32(noff), len(pages), mx_n, mx_e)
+    e = len(s)
+    ref_in = ops.paged_pack_edges(csc[0], csc[1], wd, pg, eid=csc[2])
+    ref_out = ops.paged_pack_edges(csr[0], csr[1], wd, pg, eid=csr[2], pre_scale=norm)
+    assert torch.equal(pk_csc.packed[:e], ref_in.packed[:e]) and torch.equal(pk_csr.packed[:e], ref_out.packed[:e])
+    # broken contract: an edge that leaves its page raises the flag
+    s2 = s.copy()
+    s2[0] = int(noff[-1]) - 1
+    *_, bad2 = ops.build_page_formats(_i32(s2), dd, wd, _i32(noff), _i32(eoff), len(pages), n, mx_n, mx_e)
+    assert int(bad2.item()) == 1
