@@ -307,19 +307,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
         // two passes over TMEM (mean, then centred second moment): exact like nn.LayerNorm; the last chunk
         // is the only one that needs per-column predicates
         const int nfull = P.N / 32, ntail = P.N % 32;
-        // z (pre-activation, saved for backward) does not depend on the statistics: it leaves through TMA stores
-        // already during this first pass, so the store engine is busy across the whole epilogue instead of idling
-        // through the statistics and queueing 2 stores per chunk in the output pass
         float s1 = 0.f;
         for (int c = 0; c < nfull; ++c) {
           load_chunk(c);
-          if (P.tma_store) epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
 #pragma unroll
           for (int j = 0; j < 32; ++j) s1 += x[j];
         }
         if (ntail) {
           load_chunk(nfull);
-          if (P.tma_store) epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], nfull * 32, (int32_t)row0);
 #pragma unroll
           for (int j = 0; j < 32; ++j) s1 += (j < ntail) ? x[j] : 0.f;
         }
@@ -352,9 +347,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
       const int rows_valid = (int)min((int64_t)32, (int64_t)P.M - row0);
       for (int c = 0; c < nchunks; ++c) {
         load_chunk(c);
-        if (P.tma_store) {
-          if (!P.fuse_ln) epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
-        } else if (rows_valid > 0)
+        if (P.tma_store)
+          epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
+        else if (rows_valid > 0)
           epi_store_chunk(st, x, outp + row0 * ldo + c * 32, ldo, rows_valid, P.N - c * 32, vec_out);
         if (P.y != nullptr) {
           const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c * 32);

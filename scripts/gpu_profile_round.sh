@@ -9,4 +9,4 @@ ncu --set full --clock-control none --import-source on -k regex:"k_umma|k_layern
     -o gpurun_out/r01_step_cfg2 -f python scripts/profile_step.py > gpurun_out/ncu_step.log 2>&1
 PAGES=512 REPS=2 ncu --set full --clock-control none --import-source on -k regex:k_spmm_paged_pk --launch-skip 2 --launch-count 2 \
     -o gpurun_out/r01_spmm_cfg2 -f python scripts/profile_spmm.py > gpurun_out/ncu_spmm.log 2>&1
-tail -2 gpurun_out/ncu_step.log gpurun_out/ncu_spmm.log
+tail -n 2 gpurun_out/ncu_step.log; tail -n 2 gpurun_out/ncu_spmm.log
