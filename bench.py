@@ -241,7 +241,7 @@ def ncu_traffic(op_key):
         recs = [r for k, v in m.items() if k.startswith("k_umma_dw grid") for r in v]
         want = max(recs, key=lambda r: r.get("time_us", 0)) if (recs and op_key[3] > 64) else None
     elif name == "spmm":
-        recs = [r for k, v in m.items() if k.startswith("k_spmm_paged_pk<8, 2>") for r in v
+        recs = [r for k, v in m.items() if k.startswith("k_spmm_paged_pk<8, 2") for r in v
                 if r.get("capture", "").startswith("r01_spmm_cfg2")]
         recs = sorted(recs, key=lambda r: r.get("dram_bytes", 0))
         want = (recs[-1] if op_key[4] else recs[0]) if recs else None  # with addend = the larger traffic

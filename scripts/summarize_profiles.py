@@ -97,13 +97,13 @@ for rep in args.reps:
 if metrics:
     out = {}
     md = [f"# {args.tag}: `ncu --set full --clock-control none` captures (per launch)\n",
-          "| kernel | capture | us | DRAM read MB | DRAM write MB | DRAM % | L2 % | LSU wavefront % | issue % | tensor pipe % | regs |",
-          "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+          "| kernel | capture | us | DRAM read MB | DRAM write MB | L2 % | LSU wavefront % | issue % | tensor pipe % | regs |",
+          "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
     for key, recs in metrics.items():
         out[key] = recs
         for rec in recs:
             md.append(f"| `{key}` | {rec['capture']} | {rec.get('time_us', 0):.1f} | {rec.get('dram_read', 0) / 1e6:.1f} | "
-                      f"{rec.get('dram_write', 0) / 1e6:.1f} | {rec.get('dram_pct', 0):.1f} | {rec.get('l2_pct', 0):.1f} | "
+                      f"{rec.get('dram_write', 0) / 1e6:.1f} | {rec.get('l2_pct', 0):.1f} | "
                       f"{rec.get('lsu_wavefronts_pct', 0):.1f} | {rec.get('issue_active_pct', 0):.1f} | "
                       f"{rec.get('tensor_pipe_pct', 0):.1f} | {int(rec.get('regs', 0))} |")
     json.dump(out, open(os.path.join(prof, f"{args.tag}_kernel_metrics.json"), "w"), indent=1)
