@@ -479,6 +479,7 @@ static int setup_output_maps(UmmaArgs& a) {
   bool ok = true;
   for (int g = 0; g < a.ngroups; ++g) ok = ok && aligned16(a.out[g]) && a.ldo[g] % 4 == 0;
   if (a.y) ok = ok && aligned16(a.y) && a.ldy % 4 == 0;
+  if (const char* e = getenv("GTE_UMMA_TMA_STORE")) ok = ok && atoi(e) != 0;  // experiment switch: 0 = transposed st.global path
   a.tma_store = ok ? 1 : 0;
   if (!ok) return GTE_OK;
   for (int g = 0; g < a.ngroups; ++g) {
