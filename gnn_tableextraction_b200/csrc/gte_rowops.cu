@@ -443,8 +443,10 @@ __global__ void k_step_inc(int64_t* step) { *step += 1; }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                        float* __restrict__ v, int64_t count, float lr, float b1, float b2, float eps, float wd,
-                       int64_t step_host, const int64_t* __restrict__ step_dev, float grad_scale) {
+                       int64_t step_host, const int64_t* __restrict__ step_dev, float grad_scale,
+                       const float* __restrict__ grad_den) {
   const int64_t t = step_dev ? *step_dev : step_host;
+  if (grad_den) grad_scale = grad_scale / *grad_den;  // data parallel: gradients were summed un-normalised
   // bias corrections exactly as torch.optim.Adam's single-tensor path (double maths, then fp32 use)
   const double bc1 = 1.0 - pow((double)b1, (double)t);
   const double bc2 = 1.0 - pow((double)b2, (double)t);
@@ -646,7 +648,7 @@ int gte_cross_entropy_bwd(const float* logits, int64_t ld, const void* labels, i
 
 int gte_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int64_t step_host, int64_t* step_dev,
-                  float grad_scale, gte_stream_t stream) {
+                  float grad_scale, const float* grad_den, gte_stream_t stream) {
   GTE_CHECK_ARG(count >= 0, "gte_adam_step: negative count");
   GTE_CHECK_ARG(step_dev != nullptr || step_host >= 1, "gte_adam_step: step must be >= 1");
   if (count == 0) return GTE_OK;
@@ -657,7 +659,7 @@ int gte_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
     GTE_CHECK_LAUNCH("k_step_inc");
   }
   k_adam<<<ew_grid(count), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, weight_decay,
-                                        step_host, step_dev, grad_scale);
+                                        step_host, step_dev, grad_scale, grad_den);
   GTE_CHECK_LAUNCH("k_adam");
   return GTE_OK;
 }

@@ -20,6 +20,7 @@ SUM all-reduce of the flat gradient reproduces the single-GPU result exactly
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -58,8 +59,14 @@ class SageTrainer:
         for p in params:
             offs.append(o)
             o += (p.numel() + 3) // 4 * 4
+        # Data parallel: ONE all-reduce per step.  The loss statistics [sum w*nll, sum w, #correct] live in the tail of
+        # the flat gradient buffer, every rank back-propagates the UN-normalised sum, the single SUM all-reduce carries
+        # gradients and statistics together, and Adam divides by the global label-weight sum it finds in the tail
+        # (gte_adam_step grad_den).  GTE_DP_FUSED=1 forces this path on one GPU (tests).
+        self.dp_fused = self.world > 1 or os.environ.get("GTE_DP_FUSED", "0") == "1"
+        self._flat_len = o
         self.flat_param = torch.zeros(o, dtype=torch.float32, device=self.device)
-        self.flat_grad = torch.zeros(o, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(o + 4, dtype=torch.float32, device=self.device)
         self.exp_avg = torch.zeros(o, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(o, dtype=torch.float32, device=self.device)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -73,7 +80,8 @@ class SageTrainer:
                 gv = self.flat_grad[off:off + p.numel()].view_as(p)
                 p.grad = gv
                 self._grad_views[id(p)] = gv
-        self.stats = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self.stats = self.flat_grad[o:o + 3] if self.dp_fused else torch.zeros(3, dtype=torch.float32, device=self.device)
+        self._one = torch.ones(1, dtype=torch.float32, device=self.device)
         self._graph = None
         self._static: Optional[Dict[str, torch.Tensor]] = None
 
@@ -120,18 +128,19 @@ class SageTrainer:
         return logits, ctxs
 
     def _stage_backward(self, g: PageGraphBatch, labels: torch.Tensor, logits, ctxs):
-        dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, self.stats[1:2])
+        den = self._one if self.dp_fused else self.stats[1:2]
+        dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, den)
         self.backward(g, ctxs, dlogits)
 
     def _stage_update(self):
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
-                      beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step_dev=self.step_dev)
+                      beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step_dev=self.step_dev,
+                      grad_den=self.stats[1:2] if self.dp_fused else None, count=self._flat_len)
 
     def _step_impl(self, g: PageGraphBatch, labels: torch.Tensor):
         logits, ctxs = self._stage_forward(g, labels)
-        self._all_reduce(self.stats)  # global sum w*nll, sum w, #correct
         self._stage_backward(g, labels, logits, ctxs)
-        self._all_reduce(self.flat_grad)
+        self._all_reduce(self.flat_grad)  # dp_fused: gradients + [sum w*nll, sum w, #correct] in one collective
         self._stage_update()
         return logits
 
@@ -181,7 +190,7 @@ class SageTrainer:
         """Capture the whole step (format build + forward + loss + backward +
         optimiser) for batches with exactly this node / edge count.  Later
         batches are fed with ``load_batch`` + ``replay``.  ``split`` (default: data-parallel
-        runs) captures two graphs around the eager collectives instead of one."""
+        runs) captures the kernels in one graph and leaves the all-reduce and Adam outside it."""
         if split is None:
             split = self.world > 1
         dev = self.device
@@ -222,17 +231,16 @@ class SageTrainer:
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         if split:
-            # collectives stay outside the graphs: [graph 1: formats + forward + CE statistics] -> all-reduce(3 floats)
-            # -> [graph 2: CE gradient + backward] -> all-reduce(flat gradient) -> Adam (eager, 2 launches)
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # the collective stays outside the graph: [graph: batch assembly + forward + CE + backward] ->
+            # ONE all-reduce (flat gradient + loss statistics) -> Adam (eager, 2 launches)
+            g1 = torch.cuda.CUDAGraph()
             keep = {}
             with torch.cuda.graph(g1):
                 keep["g"] = make_graph()
                 keep["logits"], keep["ctxs"] = self._stage_forward(keep["g"], st["label"])
-            with torch.cuda.graph(g2, pool=g1.pool()):
                 self._stage_backward(keep["g"], st["label"], keep["logits"], keep["ctxs"])
-            self._graph_keep = keep  # activations live in the graphs' pool: keep their owners alive
-            self._graph = (g1, g2)
+            self._graph_keep = keep  # activations live in the graph's pool: keep their owners alive
+            self._graph = (g1,)
             graph = self._graph
         else:
             graph = torch.cuda.CUDAGraph()
@@ -256,10 +264,7 @@ class SageTrainer:
 
     def _replay_graphs(self):
         if isinstance(self._graph, tuple):
-            g1, g2 = self._graph
-            g1.replay()
-            self._all_reduce(self.stats)
-            g2.replay()
+            self._graph[0].replay()
             self._all_reduce(self.flat_grad)
             self._stage_update()
         else:

@@ -670,8 +670,9 @@ def cross_entropy_bwd(logits, labels, class_w, denominator, out=None):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
-              step: int = 0, step_dev: Optional[torch.Tensor] = None, grad_scale: float = 1.0):
-    count = param.numel()
+              step: int = 0, step_dev: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+              grad_den: Optional[torch.Tensor] = None, count: Optional[int] = None):
+    count = param.numel() if count is None else int(count)
     for t, nm in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _vec(t, nm, n=count)
     if step_dev is not None:
@@ -679,7 +680,7 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, e
     check(
         lib().gte_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), count,
                             float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-                            _ptr(step_dev), float(grad_scale), _stream()),
+                            _ptr(step_dev), float(grad_scale), _vec(grad_den, "grad_den", n=1), _stream()),
         "gte_adam_step",
     )
 

@@ -3,11 +3,10 @@ batched graph, /root/reference/src/models/model_train.py:297 -- no edge crosses 
 feature exchange is ever needed; the reference itself is single device).
 
 Each rank takes a contiguous slice of the global batch's pages, runs the same kernels on its
-own batched graph, and the only exchange per step is
-  * one all-reduce (SUM) of 3 floats  [sum w*nll, sum w, #correct]  -> global loss denominator
-  * one all-reduce (SUM) of the flat fp32 gradient buffer (424 KB for the default model).
-Because the loss is normalised by the GLOBAL label-weight sum before the backward, the summed
-gradients equal the single-GPU gradients exactly (not a mean of per-rank means)."""
+own batched graph, and the only exchange per step is ONE all-reduce (SUM) of the flat fp32 gradient
+buffer (424 KB for the default model) whose tail carries [sum w*nll, sum w, #correct]: every rank
+back-propagates the un-normalised local loss sum and the optimiser divides the summed gradient by the
+GLOBAL label-weight sum, so the result equals the single-GPU gradients (not a mean of per-rank means)."""
 from __future__ import annotations
 
 from typing import List, Sequence, Tuple

@@ -371,12 +371,14 @@ int gte_cross_entropy_bwd(const float* logits, int64_t ld, const void* labels, i
  * a flat parameter buffer (model_train.py:168,332).  The 1-based step count is
  * `step_host`, or -- when `step_dev` is non-NULL -- a device counter that this
  * call increments first and then uses (CUDA-graph replay safe).  grad_scale
- * multiplies the gradient first.
+ * multiplies the gradient first; `grad_den` (device float, may be NULL) divides it:
+ * the data-parallel step sums UN-normalised gradients together with the loss
+ * statistics in ONE all-reduce and normalises here by the global label-weight sum.
  */
 int gte_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   int64_t count, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int64_t step_host, int64_t* step_dev, float grad_scale,
-                  gte_stream_t stream);
+                  const float* grad_den, gte_stream_t stream);
 
 /* ---------------------------------------- either side of the layers ---- */
 /*

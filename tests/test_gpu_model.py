@@ -294,3 +294,32 @@ def test_predict_pages_matches_reference_predict_loop():
     if not diff:
         assert np.allclose(acc.cpu().numpy(), np.asarray(accs), atol=1e-12)
         assert abs(acc.mean().item() - sum(accs) / len(accs)) < 1e-12
+
+
+def test_data_parallel_single_collective_step_equals_plain_step(monkeypatch):
+    """The data-parallel step (un-normalised backward, loss statistics in the tail of the flat gradient buffer, ONE
+    all-reduce, Adam divides by the global label-weight sum) run on one GPU == the plain single-GPU step: same
+    statistics, same normalised gradients (fp32 rounding of one multiply), same parameters after 3 steps; also
+    through the split CUDA-graph capture used under torchrun."""
+    pages = synth.make_pages(6, ragged=True, k=6)
+    hb = batch_pages_host(pages)
+    cw = torch.tensor([1.0] * 6 + [2.5] + [1.0] * 2)
+    _, m1 = _oracle_and_cuda_models(11, (13, 48, 9, 3))
+    _, m2 = _oracle_and_cuda_models(11, (13, 48, 9, 3))
+    _, m3 = _oracle_and_cuda_models(11, (13, 48, 9, 3))
+    t1 = gte.SageTrainer(m1, class_weights=cw)
+    monkeypatch.setenv("GTE_DP_FUSED", "1")
+    t2 = gte.SageTrainer(m2, class_weights=cw)
+    t3 = gte.SageTrainer(m3, class_weights=cw)
+    monkeypatch.delenv("GTE_DP_FUSED")
+    assert t2.dp_fused and not t1.dp_fused and t2.stats.data_ptr() == t2.flat_grad[t2._flat_len:].data_ptr()
+    t3.capture(hb, split=True)
+    for step in range(3):
+        s1 = t1.train_step(gte.PageGraphBatch.from_host(hb, DEV)).clone()
+        s2 = t2.train_step(gte.PageGraphBatch.from_host(hb, DEV)).clone()
+        t3.load_batch(hb)
+        s3 = t3.replay().clone()
+        assert rel_err(s2, s1) < 1e-6 and torch.equal(s2, s3), step
+        n = t1._flat_len
+        assert rel_err(t2.flat_grad[:n] / s2[1], t1.flat_grad[:n]) < 2e-6
+        assert rel_err(t2.flat_param, t1.flat_param) < 2e-6 and torch.equal(t2.flat_param, t3.flat_param)
