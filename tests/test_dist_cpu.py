@@ -1,6 +1,6 @@
 """world_size-2 gloo test (CPU): the data-parallel recipe of gnn_tableextraction_b200.parallel /
-SageTrainer -- shard pages by graph, normalise the loss by the GLOBAL label-weight sum, SUM
-all-reduce the gradients -- reproduces the single-process gradients.  The arithmetic runs on the
+SageTrainer -- shard pages by graph, ONE SUM all-reduce of the un-normalised gradients together with the
+loss statistics, division by the GLOBAL label-weight sum -- reproduces the single-process gradients.  The arithmetic runs on the
 oracle here (no GPU); the same sequence runs on the kernels in SageTrainer._step_impl."""
 import os
 import socket
@@ -43,10 +43,12 @@ def _worker(rank, world, port, q):
     logits = model(g)
     nll = F.cross_entropy(logits, labels, weight=cw, reduction="sum")
     stats = torch.tensor([nll.item(), cw[labels].sum().item(), float((logits.argmax(1) == labels).sum())])
-    all_reduce_sum_(stats)  # global [sum w*nll, sum w, #correct]
-    (nll / stats[1]).backward()  # local loss normalised by the GLOBAL denominator
-    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-    all_reduce_sum_(flat)
+    # the recipe of SageTrainer (dp_fused): back-propagate the UN-normalised local sum, ONE all-reduce of
+    # [gradients | sum w*nll, sum w, #correct], then divide by the global label-weight sum (Adam's grad_den)
+    nll.backward()
+    buf = torch.cat([p.grad.reshape(-1) for p in model.parameters()] + [stats])
+    all_reduce_sum_(buf)
+    flat, stats = buf[:-3] / buf[-2], buf[-3:]
     if rank == 0:
         q.put((stats.numpy(), flat.numpy()))
     dist.barrier()
