@@ -185,12 +185,13 @@ __global__ void __launch_bounds__(PF_THREADS)
     const int32_t s = src[e0 + i] - n0, d = dst[e0 + i] - n0;
     const bool ok = s >= 0 && s < np && d >= 0 && d < np;
     if (!ok) *bad = 1;
-    s_src[i] = ok ? s : 0;
-    s_dst[i] = ok ? d : 0;
-    if (ok) {
-      atomicAdd(&cur_in[d], 1);
-      atomicAdd(&cur_out[s], 1);
-    }
+    // an edge that leaves its page breaks the contract (*bad = 1, results meaningless) but must stay memory safe:
+    // it is kept with its endpoints clamped to local node 0, so every count / cursor / slot below stays consistent
+    const int32_t sl = ok ? s : 0, dl = ok ? d : 0;
+    s_src[i] = sl;
+    s_dst[i] = dl;
+    atomicAdd(&cur_in[dl], 1);
+    atomicAdd(&cur_out[sl], 1);
   }
   __syncthreads();
   // 2. exclusive scans of both degree arrays (block scan, PF_THREADS entries per round)
