@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
       for (int c = 0; c < nchunks; ++c) {
         load_chunk(c);
         if (P.tma_store)
-          epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
+          epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0, P.dbg);
         else if (rows_valid > 0)
           epi_store_chunk(st, x, outp + row0 * ldo + c * 32, ldo, rows_valid, P.N - c * 32, vec_out);
         if (P.y != nullptr) {
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
             }
           }
           if (P.tma_store)
-            epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
+            epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmY, c * 32, (int32_t)row0, P.dbg);
           else if (rows_valid > 0)
             epi_store_chunk(st, x, P.y + row0 * P.ldy + c * 32, P.ldy, rows_valid, P.N - c * 32, vec_y);
         }
@@ -509,7 +509,7 @@ static int launch_umma(UmmaArgs& a, cudaStream_t st) {
     configured = smem;
   }
   a.variant = umma_variant();
-  a.dbg = getenv("GTE_UMMA_DBG") ? 1 : 0;
+  a.dbg = getenv("GTE_UMMA_DBG") ? atoi(getenv("GTE_UMMA_DBG")) : 0;  // bit0: role timestamps; bits1-2: epilogue store experiments
   const int tiles = ((a.M + UM_BM - 1) / UM_BM) * a.ngroups;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;

@@ -177,9 +177,27 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // One 32-row x 32-column accumulator chunk (thread = row) -> dense, 128B-swizzled shared tile [32][32] floats
 // -> one asynchronous TMA store (bounds clipped by the tensor map).  `buf` is 1024-byte aligned and warp private;
 // `seq` counts this warp's stores: with nbuf == 2 two buffers alternate (one older store may still be reading).
+// `dbg` (experiments only): bit1 = do not issue the TMA store, bit2 = do not stage (no shared stores / proxy fence)
 __device__ __forceinline__ void epi_store_chunk_tma(uint8_t* bufs, int nbuf, int& seq, const float (&v)[32],
-                                                    const CUtensorMap* map, int32_t col0, int32_t row0) {
+                                                    const CUtensorMap* map, int32_t col0, int32_t row0, int dbg = 0) {
   const int lane = threadIdx.x & 31;
+  if (dbg & 6) {
+    if (!(dbg & 4)) {
+      float* rowp = reinterpret_cast<float*>(bufs) + lane * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      fence_proxy_async();
+      __syncwarp();
+    }
+    if (!(dbg & 2) && lane == 0) {
+      tma_store_2d(map, smem_u32(bufs), col0, row0);
+      tma_store_commit();
+      tma_store_wait_read<0>();
+    }
+    if (v[0] == 12345.678f) bufs[lane] = 1;  // keep v alive
+    return;
+  }
   uint8_t* buf = bufs + (nbuf == 2 ? (seq & 1) * 4096 : 0);
   if (seq >= nbuf) {
     if (lane == 0) {

@@ -1,6 +1,6 @@
 """Role timeline of the tensor-core projection kernel (GTE_UMMA_DBG=1): where does a tile's time go?"""
 import os, sys
-os.environ["GTE_UMMA_DBG"] = "1"
+os.environ["GTE_UMMA_DBG"] = os.environ.get("GTE_UMMA_DBG", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes, numpy as np, torch
 from gnn_tableextraction_b200 import ops, lib
