@@ -422,10 +422,11 @@ def run_ours(args):
         trainer.prefetch_batch(host_batches[0])
 
         def e2e(i):
-            # every step: H2D of the NEXT batch from pinned memory (side stream, overlaps this step's kernels),
-            # the captured step on the current batch, D2H of [sum w*nll, sum w, #correct]
-            trainer.prefetch_batch(host_batches[(i + 1) % 3])
+            # every step: the captured step on the current batch (launched first, so the GPU never waits for the
+            # host to queue copies), H2D of the NEXT batch from pinned memory (side stream, overlaps this step's
+            # kernels; it lands in the other static input set, no staging copy), D2H of [sum w*nll, sum w, #correct]
             trainer.replay_prefetched()
+            trainer.prefetch_batch(host_batches[(i + 1) % 3])
             stats_host.copy_(trainer.stats, non_blocking=True)
             stream.synchronize()  # the caller reads the loss every step (model_train.py:328 .item())
     else:

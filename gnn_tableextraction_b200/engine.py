@@ -211,47 +211,47 @@ class SageTrainer:
         # replays read it): keep a reference on the trainer
         pages = self._static_pages = page_table(self._static_meta[2], self._static_meta[3], n, dev)
 
-        def make_graph():
-            g = PageGraphBatch(st["src"], st["dst"], n, self._static_meta[2], self._static_meta[3])
-            g._cache["pages"] = pages
-            g.edata["feat"] = st["weight"]
-            g.ndata["feat"] = st["feat"]
-            return g
-
-        def body():
-            self._step_impl(make_graph(), st["label"])
-
+        self._split = split
         # warm-up on a side stream (allocator + lazy module state), restoring the optimiser state afterwards
         snap = (self.flat_param.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone())
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
             for _ in range(2):
-                body()
+                self._step_impl(self._static_graph(st), st["label"])
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        if split:
-            # the collective stays outside the graph: [graph: batch assembly + forward + CE + backward] ->
-            # ONE all-reduce (flat gradient + loss statistics) -> Adam (eager, 2 launches)
-            g1 = torch.cuda.CUDAGraph()
-            keep = {}
-            with torch.cuda.graph(g1):
-                keep["g"] = make_graph()
-                keep["logits"], keep["ctxs"] = self._stage_forward(keep["g"], st["label"])
-                self._stage_backward(keep["g"], st["label"], keep["logits"], keep["ctxs"])
-            self._graph_keep = keep  # activations live in the graph's pool: keep their owners alive
-            self._graph = (g1,)
-            graph = self._graph
-        else:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                body()
-            self._graph = graph
+        self._graph = self._capture_over(st)
+        self._statics, self._graphs = [st], [self._graph]
+        self._stage_sets = None
         self.flat_param.copy_(snap[0])
         self.exp_avg.copy_(snap[1])
         self.exp_avg_sq.copy_(snap[2])
         self.step_dev.copy_(snap[3])
-        return graph
+        return self._graph
+
+    def _static_graph(self, st) -> PageGraphBatch:
+        n = self._static_meta[0]
+        g = PageGraphBatch(st["src"], st["dst"], n, self._static_meta[2], self._static_meta[3])
+        g._cache["pages"] = self._static_pages
+        g.edata["feat"] = st["weight"]
+        g.ndata["feat"] = st["feat"]
+        return g
+
+    def _capture_over(self, st, pool=None):
+        """Capture the step reading the static input set ``st`` (capturing launches nothing).  Under data parallelism
+        the collective stays outside: [graph: batch assembly + forward + CE + backward] -> ONE all-reduce (flat
+        gradient + loss statistics) -> Adam (eager, 2 launches)."""
+        graph = torch.cuda.CUDAGraph()
+        kw = {} if pool is None else {"pool": pool}
+        with torch.cuda.graph(graph, **kw):
+            if self._split:
+                g = self._static_graph(st)
+                logits, ctxs = self._stage_forward(g, st["label"])
+                self._stage_backward(g, st["label"], logits, ctxs)
+            else:
+                self._step_impl(self._static_graph(st), st["label"])
+        return (graph,) if self._split else graph
 
     def load_batch(self, host_batch: Dict[str, torch.Tensor]):
         st = self._static
@@ -262,13 +262,14 @@ class SageTrainer:
         for k in ("src", "dst", "weight", "feat", "label"):
             st[k].copy_(host_batch[k], non_blocking=True)
 
-    def _replay_graphs(self):
-        if isinstance(self._graph, tuple):
-            self._graph[0].replay()
+    def _replay_graphs(self, which: int = 0):
+        graph = self._graphs[which] if getattr(self, "_graphs", None) else self._graph
+        if isinstance(graph, tuple):
+            graph[0].replay()
             self._all_reduce(self.flat_grad)
             self._stage_update()
         else:
-            self._graph.replay()
+            graph.replay()
 
     def replay(self) -> torch.Tensor:
         self._replay_graphs()
@@ -276,27 +277,37 @@ class SageTrainer:
 
     # -- pipelined input: the host->device copy of batch i+1 overlaps the step of batch i ----------------------
     def prefetch_batch(self, host_batch: Dict[str, torch.Tensor]):
-        """Start the H2D copy of the NEXT batch on a side stream into a staging set (double buffered).
-        ``replay_prefetched()`` consumes the staging sets in order."""
+        """Start the H2D copy of the NEXT batch on a side stream.  Two static input sets alternate, each with its own
+        captured graph (sharing one memory pool), so the step reads the batch where the copy engine put it: no
+        device-to-device staging copy.  ``replay_prefetched()`` consumes the sets in order."""
         if self._static is None:
             raise GteError("prefetch_batch: call capture() first")
         if int(host_batch["num_nodes"]) != self._static_meta[0] or int(host_batch["src"].numel()) != self._static_meta[1]:
             raise GteError("prefetch_batch: batch shape differs from the captured one")
         if getattr(self, "_stage_sets", None) is None:
+            torch.cuda.synchronize(self.device)
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._stage_sets = [{k: torch.empty_like(v) for k, v in self._static.items()} for _ in range(2)]
+            second = {k: torch.empty_like(v) for k, v in self._static.items()}
+            for k, v in self._static.items():
+                second[k].copy_(v)  # valid contents for the capture below (capturing runs nothing)
+            pool = (self._graph[0] if isinstance(self._graph, tuple) else self._graph).pool()
+            self._statics = [self._static, second]
+            self._graphs = [self._graph, self._capture_over(second, pool=pool)]
+            self._stage_sets = self._statics
             self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
             self._stage_w = self._stage_r = 0
+            # set 0 may still be read by work queued before this call
+            self._stage_free[0].record(torch.cuda.current_stream(self.device))
+            self._stage_free[1].record(torch.cuda.current_stream(self.device))
         if self._stage_w - self._stage_r >= 2:
-            raise GteError("prefetch_batch: both staging sets hold unconsumed batches; call replay_prefetched() first")
+            raise GteError("prefetch_batch: both input sets hold unconsumed batches; call replay_prefetched() first")
         i = self._stage_w % 2
         cs = self._copy_stream
-        if self._stage_w >= 2:
-            cs.wait_event(self._stage_free[i])  # staging set i was consumed by the step two batches ago
+        cs.wait_event(self._stage_free[i])  # the step that last read input set i has finished
         with torch.cuda.stream(cs):
             for k in ("src", "dst", "weight", "feat", "label"):
-                self._stage_sets[i][k].copy_(host_batch[k], non_blocking=True)
+                self._statics[i][k].copy_(host_batch[k], non_blocking=True)
             self._stage_ready[i].record(cs)
         self._stage_w += 1
 
@@ -307,9 +318,7 @@ class SageTrainer:
         i = self._stage_r % 2
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._stage_ready[i])
-        for k in ("src", "dst", "weight", "feat", "label"):
-            self._static[k].copy_(self._stage_sets[i][k], non_blocking=True)  # device-to-device, ~27 MB
+        self._replay_graphs(i)
         self._stage_free[i].record(cur)
         self._stage_r += 1
-        self._replay_graphs()
         return self.stats
