@@ -311,6 +311,14 @@ class SageTrainer:
             self._stage_ready[i].record(cs)
         self._stage_w += 1
 
+    def replay_set(self, which: int) -> torch.Tensor:
+        """Run one captured step on static input set ``which`` (0 or 1) as it is: inputs resident in HBM, no copy.
+        The sets are filled by ``prefetch_batch`` / ``load_batch``; the caller keeps track of what is in them."""
+        if getattr(self, "_stage_sets", None) is None and which != 0:
+            raise GteError("replay_set: the second input set exists after the first prefetch_batch()")
+        self._replay_graphs(which)
+        return self.stats
+
     def replay_prefetched(self) -> torch.Tensor:
         """Run one captured step on the oldest prefetched batch."""
         if getattr(self, "_stage_sets", None) is None or self._stage_r >= self._stage_w:
