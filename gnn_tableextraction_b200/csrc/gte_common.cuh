@@ -25,6 +25,11 @@ int sm_count();
 // number of kernels launched by this library since load (diagnostic; gte_launch_count())
 void note_launch();
 
+// Opt a kernel into `bytes` of dynamic shared memory on the CURRENT device (cudaFuncAttributeMaxDynamicSharedMemorySize
+// is a per-device attribute).  Remembers the largest size set per (device, kernel); thread safe.  Returns GTE_OK or the
+// failure already recorded with fail().
+int ensure_dynamic_smem(const void* func, size_t bytes, const char* name);
+
 #define GTE_CHECK_ARG(cond, ...)                                  \
   do {                                                            \
     if (!(cond)) return ::gte::fail(GTE_ERR_INVALID, __VA_ARGS__); \

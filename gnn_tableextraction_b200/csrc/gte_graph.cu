@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace gte {
 
@@ -25,6 +26,28 @@ int fail(int code, const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
+int ensure_dynamic_smem(const void* func, size_t bytes, const char* name) {
+  if (bytes <= 48 * 1024) return GTE_OK;
+  struct Entry { int dev; const void* func; size_t bytes; };
+  static std::mutex mu;
+  static std::vector<Entry> seen;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  for (Entry& e : seen)
+    if (e.dev == dev && e.func == func) {
+      if (e.bytes >= bytes) return GTE_OK;
+      cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (err != cudaSuccess) return fail(GTE_ERR_CUDA, "%s(smem attr): %s", name, cudaGetErrorString(err));
+      e.bytes = bytes;
+      return GTE_OK;
+    }
+  cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (err != cudaSuccess) return fail(GTE_ERR_CUDA, "%s(smem attr): %s", name, cudaGetErrorString(err));
+  seen.push_back(Entry{dev, func, bytes});
+  return GTE_OK;
+}
 
 int sm_count() {
   static int cached[64];

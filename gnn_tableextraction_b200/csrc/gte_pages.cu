@@ -327,12 +327,7 @@ extern "C" int gte_build_page_formats(const int32_t* src, const int32_t* dst, co
     return GTE_OK;
   }
   GTE_CHECK_CUDA(cudaMemsetAsync(page_flag, 0, (size_t)num_pages * 4, st), "gte_build_page_formats(memset flags)");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_build_page_formats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                   "k_build_page_formats(smem attr)");
-    configured = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_build_page_formats), smem, "k_build_page_formats")) return rc;
   PfOut a{csc_indptr, csc_indices, csc_eid, reinterpret_cast<uint2*>(csc_packed)};
   PfOut b{csr_indptr, csr_indices, csr_eid, reinterpret_cast<uint2*>(csr_packed)};
   k_build_page_formats<<<num_pages, PF_THREADS, smem, st>>>(src, dst, w, page_off, edge_off, num_pages, max_page_nodes,

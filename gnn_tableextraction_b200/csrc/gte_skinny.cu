@@ -341,12 +341,7 @@ extern "C" int gte_gram_stream(const float* P, int64_t ldp, int32_t wide, const 
   const size_t smem = gs_smem_bytes(wide);
 #define GTE_GS_GO(NBV)                                                                                                    \
   do {                                                                                                                    \
-    static size_t configured = 0;                                                                                         \
-    if (smem > 48 * 1024 && smem > configured) {                                                                          \
-      GTE_CHECK_CUDA(cudaFuncSetAttribute(k_gram_stream<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),    \
-                     "k_gram_stream(smem attr)");                                                                         \
-      configured = smem;                                                                                                  \
-    }                                                                                                                     \
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_gram_stream<NBV>), smem, "k_gram_stream")) return rc; \
     if (grid > 0) {                                                                                                       \
       k_gram_stream<NBV><<<grid, GS_THREADS, smem, st>>>(P, ldp, wide, Q1, ldq1, nq1, Q2, ldq2, nq2, n, rows, partial);  \
       GTE_CHECK_LAUNCH("k_gram_stream");                                                                                  \
@@ -393,16 +388,10 @@ extern "C" int gte_wide_out(const float* A1, int64_t lda1, int32_t k1, const flo
   if (grid > need) grid = need;
 #define GTE_WO_GO(NIV)                                                                                                  \
   do {                                                                                                                  \
-    static size_t configured[2] = {0, 0};                                                                               \
-    if (smem > 48 * 1024 && smem > configured[fuse_ln ? 1 : 0]) {                                                       \
-      if (fuse_ln)                                                                                                      \
-        GTE_CHECK_CUDA(cudaFuncSetAttribute(k_wide_out<NIV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
-                       "k_wide_out(smem attr)");                                                                        \
-      else                                                                                                              \
-        GTE_CHECK_CUDA(cudaFuncSetAttribute(k_wide_out<NIV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
-                       "k_wide_out(smem attr)");                                                                        \
-      configured[fuse_ln ? 1 : 0] = smem;                                                                               \
-    }                                                                                                                   \
+    if (int rc = ensure_dynamic_smem(fuse_ln ? reinterpret_cast<const void*>(&k_wide_out<NIV, true>)                    \
+                                             : reinterpret_cast<const void*>(&k_wide_out<NIV, false>),                  \
+                                     smem, "k_wide_out"))                                                               \
+      return rc;                                                                                                        \
     if (fuse_ln)                                                                                                        \
       k_wide_out<NIV, true><<<(unsigned)grid, WO_THREADS, smem, st>>>(A1, lda1, k1, A2, lda2, k2, B1, B2, sj, sc, bias, gamma, \
                                                                       beta, eps, relu, row_scale, z, ldz, y, ldy, mean, rstd, n, C); \

@@ -307,12 +307,7 @@ static int launch_spmm_paged(const int32_t* indptr, const int32_t* indices, cons
                              int32_t np_cap, int32_t ne_cap, int32_t f, cudaStream_t st) {
   constexpr int CS = G * 4;
   const size_t smem = paged_smem_bytes(G, np_cap, ne_cap);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_paged<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                   "k_spmm_paged(smem attr)");
-    configured = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_spmm_paged<G>), smem, "k_spmm_paged")) return rc;
   dim3 grid((unsigned)ceil_div64(f, CS), (unsigned)num_pages);
   k_spmm_paged<G><<<grid, PAGED_THREADS, smem, st>>>(indptr, indices, w, pre_scale, row_norm, mode, x, ldx, addend, ldadd, y,
                                                     ldy, page_off, f, np_cap, ne_cap);
@@ -758,13 +753,8 @@ static int launch_spmm_paged_pk(const int32_t* indptr, const uint2* packed, cons
                                 int32_t np_cap, int32_t ne_cap, int32_t n_rows, int32_t f, cudaStream_t st) {
   constexpr int CS = G * V * 4;
   const size_t smem = pk_smem_bytes(CS, np_cap, MG ? 0 : ne_cap);
-  static size_t configured = 0;
   static int occ_smem = -1, occ = 1;
-  if (smem > configured) {
-    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_paged_pk<G, V, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                   "k_spmm_paged_pk(smem attr)");
-    configured = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_spmm_paged_pk<G, V, MG>), smem, "k_spmm_paged_pk")) return rc;
   if (occ_smem != (int)smem) {
     int o = 1;
     GTE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_spmm_paged_pk<G, V, MG>, PK_THREADS, smem),

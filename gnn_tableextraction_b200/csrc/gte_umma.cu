@@ -500,14 +500,8 @@ static int launch_umma(UmmaArgs& a, cudaStream_t st) {
   }
   a.epi_bufs = umma_smem_bytes(a.BN, 2) <= 227 * 1024 ? 2 : 1;
   const size_t smem = umma_smem_bytes(a.BN, a.epi_bufs);
-  static size_t configured = 0;
-  if (smem > configured) {
-    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                   "k_umma_gemm(smem attr)");
-    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                   "k_umma_gemm(smem attr)");
-    configured = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_gemm<true>), smem, "k_umma_gemm")) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_gemm<false>), smem, "k_umma_gemm")) return rc;
   a.variant = umma_variant();
   a.dbg = getenv("GTE_UMMA_DBG") ? atoi(getenv("GTE_UMMA_DBG")) : 0;  // bit0: role timestamps; bits1-2: epilogue store experiments
   const int tiles = ((a.M + UM_BM - 1) / UM_BM) * a.ngroups;

@@ -348,11 +348,7 @@ static size_t dw_smem_bytes(int max_boxes) {
 
 static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
   const size_t smem = dw_smem_bytes(a.max_boxes);
-  static size_t configured = 0;
-  if (smem > configured) {
-    GTE_CHECK_CUDA(cudaFuncSetAttribute(k_umma_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "k_umma_dw(smem attr)");
-    configured = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_dw), smem, "k_umma_dw")) return rc;
   a.dbg_lbo = DW_BOX_BYTES;
   a.dbg_sbo = 512;
   a.dbg_mode = 0;
