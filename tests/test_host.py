@@ -102,3 +102,26 @@ def test_strategy_choice():
     assert pick_strategy(218, 218, False) == "agg"
     assert pick_strategy(218, 9, False) == "proj"  # aggregate 9 columns instead of 218
     assert pick_strategy(13, 9, True) == "pp"
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) runs without a GPU and prints ONE JSON
+    line with the agreed keys; under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-pages", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "graphs/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("configs[1]") and d["vs_baseline"] is None and d["dtype"] == "f32"
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out2 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out2.returncode == 0 and not [l for l in out2.stdout.splitlines() if l.startswith("{")]
