@@ -399,6 +399,8 @@ int gte_page_predictions(const float* logits, int64_t ld, int32_t n, int32_t c, 
  * (CSC: weights; CSR: weights * norm[dst]).  Contract of dgl.batch: nodes / edges of page p occupy
  * [page_off[p], page_off[p+1]) / [edge_off[p], edge_off[p+1]) and no edge leaves its page; *bad (device int) is set to
  * 1 otherwise (results undefined) -- page_flag[] is cleared (no out-of-page edges by contract).  `w` NULL = all ones.
+ * Rows are put in edge order by a per-row insertion sort in shared memory (one thread per row): meant for the
+ * bounded degrees of page graphs (k-NN / visibility edges); a hub row of degree d costs O(d^2) steps of one thread.
  * packed arrays need e + 1 entries (see gte_spmm_paged_packed).  gte_build_page_formats_smem_bytes returns 0 when the
  * largest page does not fit in shared memory (use gte_csx_from_coo + gte_degree_norm + gte_paged_pack_edges then).
  */
