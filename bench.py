@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--pages", type=int, default=512, help="page graphs per GPU per step (config 2: 512)")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--cpu-pages", type=int, default=32, help="pages per step of the CPU baseline sample (config 1)")
-    ap.add_argument("--ref-pages", type=int, default=64, help="pages per step of --impl reference (bounded sample)")
+    ap.add_argument("--ref-pages", type=int, default=0,
+                    help="pages per step of --impl reference (0 = the workload's own --pages, i.e. the exact config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-op-profile", action="store_true")
     return ap.parse_args()
@@ -292,14 +293,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_oracle_run(args.ref_pages, args.steps, max(args.warmup, 1), budget_s=150.0)
-    sample = (f"{args.ref_pages} pages/step x {r['steps']} steps of the {args.pages}-page workload, fwd+CE+bwd+Adam, "
-              f"oracle port (DGL not installable: torch-only restatement of the reference CPU path), torch {r['torch']}")
+    ref_pages = args.ref_pages if args.ref_pages > 0 else args.pages
+    r = cpu_oracle_run(ref_pages, args.steps, max(args.warmup, 1), budget_s=150.0)
+    sample = (f"{ref_pages} pages/step x {r['steps']} steps (the workload's batch is {args.pages} pages), fwd+CE+bwd+Adam, "
+              f"oracle PORT, not DGL (DGL is not installable here: torch-only restatement of the reference CPU path -- "
+              f"index_add aggregation + MKL sgemm + autograd + Adam; a DGL OpenMP SpMM would likely be faster than "
+              f"index_add), torch {r['torch']}, {r['cores']} threads of {r['host_cpus']} host cpus")
+    cfg = workload_config(args, 1)
+    cfg["reference_arm"] = {"pages_per_step": ref_pages, "same_batch_as_workload": ref_pages == args.pages,
+                            "kind": "port (torch-only restatement, not DGL)", "torch_threads": r["cores"],
+                            "host_cpus": r["host_cpus"]}
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": cfg,
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

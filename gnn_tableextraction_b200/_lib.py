@@ -11,7 +11,9 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgte_b200.so")
+# GTE_LIB: load another in-tree build of the same ABI (the -DGTE_EXPERIMENTS build used by scripts/); never a fallback
+LIB_PATH = os.environ.get("GTE_LIB") or os.path.join(_HERE, "libgte_b200.so")
+ABI_VERSION = 2
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gte.h")
 
 _lib: Optional[C.CDLL] = None
@@ -26,6 +28,7 @@ SIGNATURES = {
     "gte_device_info": (ci, [C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
     "gte_csx_from_coo_workspace_bytes": (sz, [i32, i64]),
     "gte_csx_from_coo": (ci, [vp, vp, i32, i64, vp, vp, vp, vp, sz, vp]),
+    "gte_csx_from_coo_checked": (ci, [vp, vp, i32, i32, i64, vp, vp, vp, vp, vp, sz, vp]),
     "gte_batch_concat_csx": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     "gte_gather_f32": (ci, [vp, vp, vp, i64, vp]),
     "gte_degree_norm": (ci, [vp, i32, ci, vp, vp]),
@@ -98,8 +101,8 @@ def lib() -> C.CDLL:
         fn = getattr(l, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if l.gte_abi_version() != 1:
-        raise GteError(f"libgte_b200 ABI version {l.gte_abi_version()} != 1")
+    if l.gte_abi_version() != ABI_VERSION:
+        raise GteError(f"libgte_b200 ABI version {l.gte_abi_version()} != {ABI_VERSION}: rebuild with csrc/build.sh")
     _lib = l
     return l
 

@@ -70,12 +70,15 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-__global__ void k_count_keys(const int32_t* __restrict__ key, int64_t e, int32_t n, int32_t* __restrict__ cnt,
-                             int* __restrict__ bad) {
+// `bad` is only ever raised here (the caller clears it), so one flag can collect several builds.
+__global__ void k_count_keys(const int32_t* __restrict__ key, const int32_t* __restrict__ other, int64_t e, int32_t n,
+                             int32_t n_other, int32_t* __restrict__ cnt, int* __restrict__ bad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < e; i += stride) {
     int32_t k = key[i];
+    const int32_t o = other[i];
+    if (o < 0 || o >= n_other) *bad = 1;  // a gather index outside the feature matrix (clamped when stored)
     if (k < 0 || k >= n) {
       *bad = 1;
       continue;
@@ -179,7 +182,7 @@ __global__ void k_scan_apply(int32_t* __restrict__ cnt_cursor, int64_t m, const 
 }
 
 __global__ void k_fill_rows(const int32_t* __restrict__ key, const int32_t* __restrict__ other, int64_t e,
-                            int32_t n, int32_t* __restrict__ cursor, int32_t* __restrict__ tmp_idx,
+                            int32_t n, int32_t n_other, int32_t* __restrict__ cursor, int32_t* __restrict__ tmp_idx,
                             int32_t* __restrict__ tmp_eid) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -187,7 +190,9 @@ __global__ void k_fill_rows(const int32_t* __restrict__ key, const int32_t* __re
     int32_t k = key[i];
     if (k < 0 || k >= n) continue;  // flagged by k_count_keys
     int32_t pos = atomicAdd(&cursor[k], 1);
-    tmp_idx[pos] = other[i];
+    int32_t o = other[i];
+    if (o < 0 || o >= n_other) o = 0;  // flagged by k_count_keys; stored in range so that no later gather leaves the matrix
+    tmp_idx[pos] = o;
     tmp_eid[pos] = (int32_t)i;
   }
 }
@@ -321,7 +326,13 @@ size_t gte_csx_from_coo_workspace_bytes(int32_t n, int64_t e) {
 
 int gte_csx_from_coo(const int32_t* key, const int32_t* other, int32_t n, int64_t e, int32_t* indptr,
                      int32_t* indices, int32_t* eid, void* ws, size_t ws_bytes, gte_stream_t stream) {
-  GTE_CHECK_ARG(n >= 0 && e >= 0, "gte_csx_from_coo: negative size (n=%d, e=%lld)", n, (long long)e);
+  return gte_csx_from_coo_checked(key, other, n, n, e, indptr, indices, eid, nullptr, ws, ws_bytes, stream);
+}
+
+int gte_csx_from_coo_checked(const int32_t* key, const int32_t* other, int32_t n, int32_t n_other, int64_t e,
+                             int32_t* indptr, int32_t* indices, int32_t* eid, int32_t* bad_ids, void* ws,
+                             size_t ws_bytes, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && n_other >= 0 && e >= 0, "gte_csx_from_coo: negative size (n=%d, e=%lld)", n, (long long)e);
   GTE_CHECK_ARG(e < (int64_t)INT32_MAX, "gte_csx_from_coo: e=%lld exceeds int32 edge ids", (long long)e);
   GTE_CHECK_ARG(indptr != nullptr, "gte_csx_from_coo: indptr is null");
   GTE_CHECK_ARG(e == 0 || (key && other && indices && eid), "gte_csx_from_coo: null edge array");
@@ -334,12 +345,12 @@ int gte_csx_from_coo(const int32_t* key, const int32_t* other, int32_t n, int64_
   int32_t* tiles = reinterpret_cast<int32_t*>(base + L.tiles_off);
   int32_t* tmp_idx = reinterpret_cast<int32_t*>(base + L.tmp_idx_off);
   int32_t* tmp_eid = reinterpret_cast<int32_t*>(base + L.tmp_eid_off);
-  int* bad = reinterpret_cast<int*>(base + L.bad_off);
+  int* bad = bad_ids ? bad_ids : reinterpret_cast<int*>(base + L.bad_off);
   int64_t m = (int64_t)n + 1;
   GTE_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)m * 4, st), "gte_csx_from_coo(memset)");
-  GTE_CHECK_CUDA(cudaMemsetAsync(bad, 0, 4, st), "gte_csx_from_coo(memset)");
+  if (!bad_ids) GTE_CHECK_CUDA(cudaMemsetAsync(bad, 0, 4, st), "gte_csx_from_coo(memset)");
   if (e > 0) {
-    k_count_keys<<<grid_for(e, 256), 256, 0, st>>>(key, e, n, cnt, bad);
+    k_count_keys<<<grid_for(e, 256), 256, 0, st>>>(key, other, e, n, n_other, cnt, bad);
     GTE_CHECK_LAUNCH("k_count_keys");
   }
   k_scan_tile_sums<<<L.num_tiles, SCAN_THREADS, 0, st>>>(cnt, m, tiles);
@@ -349,7 +360,7 @@ int gte_csx_from_coo(const int32_t* key, const int32_t* other, int32_t n, int64_
   k_scan_apply<<<L.num_tiles, SCAN_THREADS, 0, st>>>(cnt, m, tiles, indptr);
   GTE_CHECK_LAUNCH("k_scan_apply");
   if (e > 0) {
-    k_fill_rows<<<grid_for(e, 256), 256, 0, st>>>(key, other, e, n, cnt, tmp_idx, tmp_eid);
+    k_fill_rows<<<grid_for(e, 256), 256, 0, st>>>(key, other, e, n, n_other, cnt, tmp_idx, tmp_eid);
     GTE_CHECK_LAUNCH("k_fill_rows");
     constexpr int LPR = 8;
     int64_t threads = (int64_t)n * LPR;

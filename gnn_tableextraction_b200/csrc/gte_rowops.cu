@@ -258,13 +258,9 @@ __global__ void __launch_bounds__(RED_THREADS)
 
 static int ln_bwd_grid(int32_t n) {
   int64_t b = ceil_div64(n, ROW_WARPS);
-  static int cap = 0;
-  if (cap == 0) {
-    const char* e = getenv("GTE_LNBWD_GRID");
-    cap = e ? atoi(e) : 2 * sm_count();  // 128 registers x 256 threads: two CTAs are resident per SM; one wave (measured
-                                         // 90 us vs 99 us with four CTAs per SM queued in two waves at N = 153600, F = 218)
-    if (cap < 1) cap = 2 * sm_count();
-  }
+  // 128 registers x 256 threads: two CTAs are resident per SM; one wave (measured 90 us vs 99 us with four CTAs per SM
+  // queued in two waves at N = 153600, F = 218)
+  const int cap = 2 * sm_count();
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -446,7 +442,14 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
                        int64_t step_host, const int64_t* __restrict__ step_dev, float grad_scale,
                        const float* __restrict__ grad_den) {
   const int64_t t = step_dev ? *step_dev : step_host;
-  if (grad_den) grad_scale = grad_scale / *grad_den;  // data parallel: gradients were summed un-normalised
+  if (grad_den) {
+    // data parallel: gradients were summed un-normalised.  A step without any weighted label (every label out of
+    // range / ignored, or class weight 0) has no defined gradient: leave parameters and moments untouched instead of
+    // dividing by zero (NaN moments would poison every later step).
+    const float den = *grad_den;
+    if (!(den > 0.f)) return;
+    grad_scale = grad_scale / den;
+  }
   // bias corrections exactly as torch.optim.Adam's single-tensor path (double maths, then fp32 use)
   const double bc1 = 1.0 - pow((double)b1, (double)t);
   const double bc2 = 1.0 - pow((double)b2, (double)t);

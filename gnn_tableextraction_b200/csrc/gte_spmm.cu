@@ -420,7 +420,6 @@ struct PkRowArgs {
   float* y;
   int64_t ldy;
   int32_t f;
-  int32_t dbg;  // experiment switches (GTE_SPMM_DBG): 1 = skip the gather loop, 2 = skip the stores, 4 = skip the x staging
 };
 
 // One pass of a row group over R (1 or 2) rows of a staged item: G lanes per row, each lane VV (<= V) 128-bit
@@ -477,7 +476,6 @@ __device__ __forceinline__ void pk_row_pass(const PkRowArgs& A, int32_t rl0) {
   if (cur.staged) {
     int32_t len = end[0] - beg[0];
     if (R == 2) len = max(len, end[R - 1] - beg[R - 1]);
-    if (A.dbg & 1) len = 0;
     auto load_meta = [&](int32_t j, uint2 (&m)[R][U]) {
 #pragma unroll
       for (int q = 0; q < R; ++q)
@@ -552,7 +550,7 @@ __device__ __forceinline__ void pk_row_pass(const PkRowArgs& A, int32_t rl0) {
       if (A.addend) {
         r.x += av[q][v].x; r.y += av[q][v].y; r.z += av[q][v].z; r.w += av[q][v].w;
       }
-      if (!(A.dbg & 2) || r.x == 12345.678f) *reinterpret_cast<float4*>(A.y + row[q] * A.ldy + col[v]) = r;
+      *reinterpret_cast<float4*>(A.y + row[q] * A.ldy + col[v]) = r;
     }
   }
 }
@@ -584,7 +582,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
                     const float* __restrict__ pre_scale, const float* __restrict__ row_norm, int mode,
                     const float* __restrict__ x, int64_t ldx, const float* __restrict__ addend, int64_t ldadd,
                     float* __restrict__ y, int64_t ldy, const int32_t* __restrict__ page_off, int32_t f, int32_t num_items,
-                    int32_t nslices, int32_t items_per_cta, int32_t np_cap, int32_t ne_cap, int32_t dbg) {
+                    int32_t nslices, int32_t items_per_cta, int32_t np_cap, int32_t ne_cap) {
   extern __shared__ __align__(128) uint8_t pk_smem[];
   constexpr int CS = G * V * 4;            // columns per slice
   constexpr int ROW_BYTES = CS * 4;
@@ -641,8 +639,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
       if (pl == 0) {
         *reinterpret_cast<PkItem*>(sbase + off_info) = it;
         if (it.staged) {
-          const int nbig = (dbg & 4) ? 0 : it.np / PK_BOX_BIG;
-          const int nsmall = (dbg & 4) ? 0 : (it.np - nbig * PK_BOX_BIG + PK_BOX_SMALL - 1) / PK_BOX_SMALL;
+          const int nbig = it.np / PK_BOX_BIG;
+          const int nsmall = (it.np - nbig * PK_BOX_BIG + PK_BOX_SMALL - 1) / PK_BOX_SMALL;
           const int e_lo = it.e0 & ~1;  // 16-byte aligned start of the bulk copy
           const uint32_t pk_copy = (!MG && it.ne > 0) ? (uint32_t)((it.e0 + it.ne - e_lo + 1) & ~1) * 8u : 0u;
           mbar_expect_tx(bar, (uint32_t)(nbig * PK_BOX_BIG + nsmall * PK_BOX_SMALL) * ROW_BYTES + pk_copy);
@@ -682,7 +680,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1)
     PkRowArgs A;
     A.zrow = L.x_bytes / ROW_BYTES - 1;
     A.indptr = indptr; A.indices = indices; A.eid = eid; A.w = w; A.pre_scale = pre_scale; A.row_norm = row_norm;
-    A.mode = mode; A.x = x; A.ldx = ldx; A.addend = addend; A.ldadd = ldadd; A.y = y; A.ldy = ldy; A.f = f; A.dbg = dbg;
+    A.mode = mode; A.x = x; A.ldx = ldx; A.addend = addend; A.ldadd = ldadd; A.y = y; A.ldy = ldy; A.f = f;
     for (int item = item_beg, s = 0, k = 0; item < item_end; ++item, s ^= 1, ++k) {
       mbar_wait(bars + s * 8, (uint32_t)(k >> 1) & 1u);
       const uint8_t* sbase = pk_smem + (size_t)s * stage_bytes;
@@ -736,15 +734,6 @@ static void pk_pick(int32_t f, int32_t np_cap, int32_t ne_cap, int* G, int* V, i
   }
 }
 
-static int pk_dbg() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GTE_SPMM_DBG");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 template <int G, int V, bool MG>
 static int launch_spmm_paged_pk(const int32_t* indptr, const uint2* packed, const int32_t* page_flag,
                                 const int32_t* indices, const int32_t* eid, const float* w, const float* pre_scale,
@@ -753,15 +742,13 @@ static int launch_spmm_paged_pk(const int32_t* indptr, const uint2* packed, cons
                                 int32_t np_cap, int32_t ne_cap, int32_t n_rows, int32_t f, cudaStream_t st) {
   constexpr int CS = G * V * 4;
   const size_t smem = pk_smem_bytes(CS, np_cap, MG ? 0 : ne_cap);
-  static int occ_smem = -1, occ = 1;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_spmm_paged_pk<G, V, MG>), smem, "k_spmm_paged_pk")) return rc;
-  if (occ_smem != (int)smem) {
-    int o = 1;
-    GTE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_spmm_paged_pk<G, V, MG>, PK_THREADS, smem),
-                   "k_spmm_paged_pk(occupancy)");
-    occ = o < 1 ? 1 : o;
-    occ_smem = (int)smem;
-  }
+  // resident CTAs per SM for this shared-memory size (a host-side query, no cache: the answer depends on the device
+  // and on smem, and a process-wide static would be wrong for both and racy)
+  int occ = 1;
+  GTE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_paged_pk<G, V, MG>, PK_THREADS, smem),
+                 "k_spmm_paged_pk(occupancy)");
+  if (occ < 1) occ = 1;
   PkMaps maps;
   {
     int rc = make_tmap_2d(&maps.big, x, n_rows, f, ldx, CS, PK_BOX_BIG, CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -777,7 +764,7 @@ static int launch_spmm_paged_pk(const int32_t* indptr, const uint2* packed, cons
   grid = (int)ceil_div64(items, per);
   k_spmm_paged_pk<G, V, MG><<<grid, PK_THREADS, smem, st>>>(maps, indptr, packed, page_flag, indices, eid, w, pre_scale, row_norm,
                                                        mode, x, ldx, addend, ldadd, y, ldy, page_off, f, (int32_t)items,
-                                                       nslices, per, np_cap, ne_cap, pk_dbg());
+                                                       nslices, per, np_cap, ne_cap);
   GTE_CHECK_LAUNCH("k_spmm_paged_pk");
   return GTE_OK;
 }

@@ -14,9 +14,10 @@ Restates the train-step envelope of the reference
 without autograd bookkeeping, without the per-step ``.item()`` sync, and -- for
 fixed-shape batches -- replayed from a CUDA graph.  Data parallel by graph
 (pages are independent): every rank runs the same step on its own pages; the
-loss is normalised by the GLOBAL label-weight sum (all-reduce of 3 floats) so a
-SUM all-reduce of the flat gradient reproduces the single-GPU result exactly
-(not a mean of per-rank means).
+loss statistics ride in the tail of the flat gradient buffer, so ONE SUM
+all-reduce per step carries gradients and statistics; Adam divides by the
+GLOBAL label-weight sum, which reproduces the single-GPU result (not a mean
+of per-rank means).
 """
 from __future__ import annotations
 
@@ -33,6 +34,11 @@ from .graph import PageGraphBatch, page_table
 from .nn import GcnSAGE, _is_relu
 
 
+def _dropout_p(d) -> float:
+    """dropout attribute of the reference modules: nn.Dropout or the float 0. (models.py:30-33)"""
+    return float(d.p) if isinstance(d, nn.Dropout) else float(d or 0.0)
+
+
 class SageTrainer:
     def __init__(self, model: GcnSAGE, lr: float = 0.01, weight_decay: float = 5e-4, betas=(0.9, 0.999),
                  eps: float = 1e-8, class_weights: Optional[torch.Tensor] = None, process_group=None):
@@ -44,6 +50,9 @@ class SageTrainer:
         for layer in model.layers:
             if layer.activation is not None and not _is_relu(layer.activation):
                 raise GteError("SageTrainer: only activation=F.relu/None is fused; use the nn.Module path otherwise")
+        if _dropout_p(model.dropout) > 0 or any(_dropout_p(layer.dropout) > 0 for layer in model.layers):
+            raise GteError("SageTrainer: dropout > 0 is not implemented in the explicit train step (it would silently "
+                           "train without dropout); use the nn.Module path (model(g) + autograd) for dropout > 0")
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.class_w = None if class_weights is None else class_weights.to(self.device, torch.float32).contiguous()
         self.pg = process_group
@@ -82,6 +91,12 @@ class SageTrainer:
                 self._grad_views[id(p)] = gv
         self.stats = self.flat_grad[o:o + 3] if self.dp_fused else torch.zeros(3, dtype=torch.float32, device=self.device)
         self._one = torch.ones(1, dtype=torch.float32, device=self.device)
+        if self.world > 1:
+            # every rank must start from the same parameters / optimiser state (DDP broadcasts from rank 0 too):
+            # do not rely on identical seeding
+            for t in (self.flat_param, self.exp_avg, self.exp_avg_sq, self.step_dev):
+                torch.distributed.broadcast(t, src=torch.distributed.get_global_rank(self.pg, 0) if self.pg is not None else 0,
+                                            group=self.pg)
         self._graph = None
         self._static: Optional[Dict[str, torch.Tensor]] = None
 
@@ -92,7 +107,9 @@ class SageTrainer:
                 layer.lynorm.weight.data if has_ln else None, layer.lynorm.bias.data if has_ln else None, has_ln,
                 layer.lynorm.eps if has_ln else 1e-5, _is_relu(layer.activation))
 
-    def forward(self, g: PageGraphBatch, keep_ctx: bool = True):
+    def forward(self, g: PageGraphBatch, keep_ctx: bool = True, layer_outputs: Optional[list] = None):
+        """Layer loop of ``GcnSAGE.forward`` (models.py:105-116).  ``layer_outputs`` (tests): a list that receives every
+        layer's output tensor (the parity tests read the ReLU on/off patterns from it)."""
         h = g.ndata["feat"]
         w_edge = g.edata["feat"]
         ctxs: List[L.LayerCtx] = []
@@ -101,6 +118,8 @@ class SageTrainer:
             h, ctx = L.sage_layer_forward(g, h, w_edge, W, b, gamma, beta, ln=has_ln, relu=relu, eps=eps, agg=L.GCN,
                                           use_pp=layer.use_pp)
             ctxs.append(ctx if keep_ctx else None)
+            if layer_outputs is not None:
+                layer_outputs.append(h)
         return h, ctxs
 
     def backward(self, g: PageGraphBatch, ctxs: List[L.LayerCtx], dlogits: torch.Tensor):
@@ -204,12 +223,20 @@ class SageTrainer:
             "label": torch.empty(n, dtype=torch.float32, device=dev),
         }
         self._static = st
-        self._static_meta = (n, e, host_batch["batch_num_nodes"], host_batch["batch_num_edges"])
+        bn, be = list(host_batch["batch_num_nodes"]), list(host_batch["batch_num_edges"])
+        self._static_meta = (n, e, bn, be)
+        # The page table (node / edge offsets of the pages) is part of the INPUT: a later batch with the same totals
+        # may order or size its pages differently, so every static input set owns device copies of the two offset
+        # arrays and load_batch / prefetch_batch refresh them.  Only the maxima (shared-memory sizing of the page
+        # kernels) and the page count are fixed at capture time.
+        pages = page_table(bn, be, n, dev)
+        if pages is not None:
+            st["page_off"], st["edge_off"] = pages[0], pages[4]
+            self._static_caps = (pages[1], pages[2], pages[3])  # page count, max page nodes, max page edges
+        else:
+            self._static_caps = None
+        self._loaded_layout = [None, None]
         self.load_batch(host_batch)
-
-        # host->device copy must happen outside the capture, and the tensor must outlive it (the graph
-        # replays read it): keep a reference on the trainer
-        pages = self._static_pages = page_table(self._static_meta[2], self._static_meta[3], n, dev)
 
         self._split = split
         # warm-up on a side stream (allocator + lazy module state), restoring the optimiser state afterwards
@@ -221,6 +248,7 @@ class SageTrainer:
                 self._step_impl(self._static_graph(st), st["label"])
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
+        self._check_static_structure(st)
         self._graph = self._capture_over(st)
         self._statics, self._graphs = [st], [self._graph]
         self._stage_sets = None
@@ -233,10 +261,52 @@ class SageTrainer:
     def _static_graph(self, st) -> PageGraphBatch:
         n = self._static_meta[0]
         g = PageGraphBatch(st["src"], st["dst"], n, self._static_meta[2], self._static_meta[3])
-        g._cache["pages"] = self._static_pages
+        caps = self._static_caps
+        g._cache["pages"] = None if caps is None else (st["page_off"], caps[0], caps[1], caps[2], st["edge_off"])
         g.edata["feat"] = st["weight"]
         g.ndata["feat"] = st["feat"]
         return g
+
+    def _check_static_structure(self, st):
+        """Host check (one synchronisation, capture time only) that the batch in ``st`` honours its page table: the
+        one-kernel batch assembly raises a device flag when an edge leaves its page (results would be undefined)."""
+        g = self._static_graph(st)
+        if g.prepare(st["weight"]):
+            g.check_page_structure()
+
+    def _page_layout(self, host_batch):
+        """Validated (page_off, edge_off) host int32 tensors of a batch fed to a captured step, or None when the
+        captured step has no page table.  Raises when the batch cannot run through the captured kernels."""
+        n, e, bn0, be0 = self._static_meta
+        if int(host_batch["num_nodes"]) != n or int(host_batch["src"].numel()) != e:
+            raise GteError("captured step: batch node / edge totals differ from the captured ones")
+        if self._static_caps is None:
+            return None
+        bn, be = list(host_batch["batch_num_nodes"]), list(host_batch["batch_num_edges"])
+        p, max_n, max_e = self._static_caps
+        if len(bn) != p or len(be) != p or sum(bn) != n or sum(be) != e:
+            raise GteError("captured step: page count / page sizes do not add up to the captured batch shape")
+        if max(bn) > max_n or max(be) > max_e:
+            raise GteError(f"captured step: largest page ({max(bn)} nodes, {max(be)} edges) exceeds the captured maxima "
+                           f"({max_n}, {max_e}) the page kernels were sized for; capture with the largest batch first")
+        if "page_off" in host_batch and "edge_off" in host_batch:
+            return host_batch["page_off"], host_batch["edge_off"], (bn, be)
+        import numpy as np
+        po = np.zeros(p + 1, dtype=np.int32)
+        eo = np.zeros(p + 1, dtype=np.int32)
+        np.cumsum(np.asarray(bn, dtype=np.int64), out=po[1:])
+        np.cumsum(np.asarray(be, dtype=np.int64), out=eo[1:])
+        return torch.from_numpy(po), torch.from_numpy(eo), (bn, be)
+
+    def _copy_inputs(self, st, which: int, host_batch, layout):
+        for k in ("src", "dst", "weight", "feat", "label"):
+            st[k].copy_(host_batch[k], non_blocking=True)
+        if layout is not None:
+            po, eo, key = layout
+            if self._loaded_layout[which] != key:  # fixed-size pages: the offsets never change, skip the copies
+                st["page_off"].copy_(po, non_blocking=True)
+                st["edge_off"].copy_(eo, non_blocking=True)
+                self._loaded_layout[which] = key
 
     def _capture_over(self, st, pool=None):
         """Capture the step reading the static input set ``st`` (capturing launches nothing).  Under data parallelism
@@ -254,13 +324,13 @@ class SageTrainer:
         return (graph,) if self._split else graph
 
     def load_batch(self, host_batch: Dict[str, torch.Tensor]):
+        """Copy a host batch into static input set 0.  The batch must have the captured node / edge totals and page
+        count and no page larger than the captured maxima; page ORDER and SIZES may differ (the page table is
+        refreshed with the batch)."""
         st = self._static
         if st is None:
             raise GteError("load_batch: call capture() first")
-        if int(host_batch["num_nodes"]) != self._static_meta[0] or int(host_batch["src"].numel()) != self._static_meta[1]:
-            raise GteError("load_batch: batch shape differs from the captured one")
-        for k in ("src", "dst", "weight", "feat", "label"):
-            st[k].copy_(host_batch[k], non_blocking=True)
+        self._copy_inputs(st, 0, host_batch, self._page_layout(host_batch))
 
     def _replay_graphs(self, which: int = 0):
         graph = self._graphs[which] if getattr(self, "_graphs", None) else self._graph
@@ -282,14 +352,14 @@ class SageTrainer:
         device-to-device staging copy.  ``replay_prefetched()`` consumes the sets in order."""
         if self._static is None:
             raise GteError("prefetch_batch: call capture() first")
-        if int(host_batch["num_nodes"]) != self._static_meta[0] or int(host_batch["src"].numel()) != self._static_meta[1]:
-            raise GteError("prefetch_batch: batch shape differs from the captured one")
+        layout = self._page_layout(host_batch)
         if getattr(self, "_stage_sets", None) is None:
             torch.cuda.synchronize(self.device)
             self._copy_stream = torch.cuda.Stream(device=self.device)
             second = {k: torch.empty_like(v) for k, v in self._static.items()}
             for k, v in self._static.items():
                 second[k].copy_(v)  # valid contents for the capture below (capturing runs nothing)
+            self._loaded_layout[1] = self._loaded_layout[0]
             pool = (self._graph[0] if isinstance(self._graph, tuple) else self._graph).pool()
             self._statics = [self._static, second]
             self._graphs = [self._graph, self._capture_over(second, pool=pool)]
@@ -306,8 +376,7 @@ class SageTrainer:
         cs = self._copy_stream
         cs.wait_event(self._stage_free[i])  # the step that last read input set i has finished
         with torch.cuda.stream(cs):
-            for k in ("src", "dst", "weight", "feat", "label"):
-                self._statics[i][k].copy_(host_batch[k], non_blocking=True)
+            self._copy_inputs(self._statics[i], i, host_batch, layout)
             self._stage_ready[i].record(cs)
         self._stage_w += 1
 

@@ -135,7 +135,7 @@ class PageGraphBatch:
         """(indptr, indices=src, eid) compressed over destinations -- forward."""
         c = self._cache.get("csc")
         if c is None:
-            c = ops.csx_from_coo(self._dst, self._src, self._n)
+            c = ops.csx_from_coo(self._dst, self._src, self._n, bad=self._bad_ids())
             self._cache["csc"] = c
         return c
 
@@ -143,9 +143,17 @@ class PageGraphBatch:
         """(indptr, indices=dst, eid) compressed over sources -- backward."""
         c = self._cache.get("csr")
         if c is None:
-            c = ops.csx_from_coo(self._src, self._dst, self._n)
+            c = ops.csx_from_coo(self._src, self._dst, self._n, bad=self._bad_ids())
             self._cache["csr"] = c
         return c
+
+    def _bad_ids(self) -> torch.Tensor:
+        """device flag raised by the format builders when a node id lies outside [0, num_nodes)"""
+        f = self._cache.get("bad_ids")
+        if f is None:
+            f = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._cache["bad_ids"] = f
+        return f
 
     def set_formats(self, csc=None, csr=None, w_csc=None, w_csr=None, w_src: Optional[torch.Tensor] = None):
         """Install pre-built formats (``PagePool.batch``)."""
@@ -215,11 +223,19 @@ class PageGraphBatch:
         return True
 
     def check_page_structure(self) -> None:
-        """Host check (synchronises) that the one-kernel batch assembly saw a truthful page table."""
+        """Host check (synchronises) of the flags the format builders raise on the device: node ids outside
+        [0, num_nodes) (DGL raises when such a graph is created; here the offending edges are dropped / clamped so the
+        kernels stay memory safe, and THIS call reports it) and, for the one-kernel batch assembly, an edge that
+        leaves its page (the page table does not describe the graph)."""
+        bad_ids = self._cache.get("bad_ids")
+        if bad_ids is not None and int(bad_ids.item()) != 0:
+            raise GteError(f"PageGraphBatch: edge endpoints outside [0, {self._n}) (num_nodes too small or corrupt ids)")
         bad = self._cache.get("bad")
         if bad is not None and int(bad.item()) != 0:
             raise GteError("PageGraphBatch: an edge leaves its page (batch_num_nodes / batch_num_edges do not describe "
                            "this graph); build it without page sizes to use the generic kernels")
+
+    validate = check_page_structure
 
     def packed_edges(self, which: str, w: torch.Tensor) -> "ops.PackedEdges":
         """Edges of the CSC (``which='csc'``, forward) or of the CSR with the source-side scale
@@ -301,6 +317,12 @@ def batch_pages_host(pages, pin: bool = True) -> Dict[str, torch.Tensor]:
         eo += e
     out = {"src": torch.from_numpy(src), "dst": torch.from_numpy(dst), "weight": torch.from_numpy(w),
            "feat": torch.from_numpy(feat), "label": torch.from_numpy(label)}
+    if e_tot < 2 ** 31:  # the page table travels with the batch (captured steps refresh it per batch)
+        po = np.zeros(len(bn) + 1, dtype=np.int32)
+        eo = np.zeros(len(be) + 1, dtype=np.int32)
+        np.cumsum(np.asarray(bn, dtype=np.int64), out=po[1:])
+        np.cumsum(np.asarray(be, dtype=np.int64), out=eo[1:])
+        out["page_off"], out["edge_off"] = torch.from_numpy(po), torch.from_numpy(eo)
     if pin and torch.cuda.is_available():
         out = {k: v.pin_memory() for k, v in out.items()}
     out["num_nodes"] = n_tot

@@ -256,18 +256,29 @@ def _as_mat(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _no_edge_grad(w_edge):
+    """The reference's edge weights are data (loader.py:332-344): DGL would compute d(edata) through gsddmm only if
+    they required grad.  That kernel is not part of this path, so refuse instead of silently returning None."""
+    if w_edge is not None and w_edge.requires_grad:
+        raise _lib.GteError("edge weights that require grad are not supported (no edge-weight gradient kernel); "
+                            "detach edata['feat'] -- the reference never trains them")
+
+
 class SageLayerFunction(torch.autograd.Function):
     """One fused autograd node per layer (replaces ~10 ATen/DGL nodes of the reference)."""
 
     @staticmethod
     def forward(ctx, h, W, b, gamma, beta, w_edge, g, ln, relu, eps, agg, use_pp):
+        _no_edge_grad(w_edge)
+        ctx.in_dtype = h.dtype
         h = _as_mat(h.detach())
-        out, lctx = sage_layer_forward(g, h, None if w_edge is None else w_edge.detach(), W.detach(),
-                                       None if b is None else b.detach(),
-                                       None if gamma is None else gamma.detach(),
-                                       None if beta is None else beta.detach(),
-                                       ln=ln, relu=relu, eps=eps, agg=agg, use_pp=use_pp)
-        ctx.lctx = lctx
+        with torch.cuda.device(h.device):  # launch on the tensors' device, whatever the caller's current device is
+            out, lctx = sage_layer_forward(g, h, None if w_edge is None else w_edge.detach(), W.detach(),
+                                           None if b is None else b.detach(),
+                                           None if gamma is None else gamma.detach(),
+                                           None if beta is None else beta.detach(),
+                                           ln=ln, relu=relu, eps=eps, agg=agg, use_pp=use_pp)
+        ctx.lctx = lctx  # kept until the node is freed, so backward(retain_graph=True) can run again
         ctx.g = g
         ctx.save_for_backward(W, gamma, beta)
         ctx.has_b = b is not None
@@ -287,7 +298,8 @@ class SageLayerFunction(torch.autograd.Function):
             dh = sage_layer_backward(ctx.g, lctx, dy, W.detach(), None if gamma is None else gamma.detach(),
                                      None if beta is None else beta.detach(), dW, db, dgamma, dbeta,
                                      need_dh=ctx.needs_input_grad[0])
-        ctx.lctx = None
+        if dh is not None and dh.dtype != ctx.in_dtype:
+            dh = dh.to(ctx.in_dtype)
         return dh, dW, db, dgamma, dbeta, None, None, None, None, None, None, None
 
 
@@ -296,16 +308,19 @@ class AggregateFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h, w_edge, g, agg):
+        _no_edge_grad(w_edge)
+        ctx.in_dtype = h.dtype
         h = _as_mat(h.detach())
         ctx.g, ctx.w_edge = g, w_edge.detach()
-        return aggregate_forward(g, h, ctx.w_edge, agg)
+        with torch.cuda.device(h.device):
+            return aggregate_forward(g, h, ctx.w_edge, agg)
 
     @staticmethod
     def backward(ctx, dy):
         dy = _as_mat(dy)
         with torch.cuda.device(dy.device):
             dh = aggregate_backward(ctx.g, dy, ctx.w_edge)
-        return dh, None, None, None
+        return (dh if dh.dtype == ctx.in_dtype else dh.to(ctx.in_dtype)), None, None, None
 
 
 class ReluL2NormFunction(torch.autograd.Function):
@@ -315,7 +330,8 @@ class ReluL2NormFunction(torch.autograd.Function):
     def forward(ctx, z, eps):
         z = _as_mat(z.detach())
         ctx.z, ctx.eps = z, eps
-        return ops.relu_l2norm_fwd(z, eps)
+        with torch.cuda.device(z.device):
+            return ops.relu_l2norm_fwd(z, eps)
 
     @staticmethod
     def backward(ctx, dy):
@@ -330,7 +346,8 @@ class CrossEntropyFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels, class_w):
         logits = _as_mat(logits.detach())
-        stats = ops.cross_entropy_fwd(logits, labels, class_w)
+        with torch.cuda.device(logits.device):
+            stats = ops.cross_entropy_fwd(logits, labels, class_w)
         ctx.logits, ctx.labels, ctx.class_w, ctx.stats = logits, labels, class_w, stats
         return stats[0] / stats[1]
 

@@ -59,8 +59,16 @@ def _vec(t: Optional[torch.Tensor], name: str, dtype=torch.float32, n: Optional[
 
 
 def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """Per-(device, stream) scratch buffer that only ever grows.  Kernels on one
-    stream serialise, so sharing it across calls is safe."""
+    """Scratch buffer for one kernel call.
+
+    Eager calls share a per-(device, stream) buffer that only ever grows (kernels on one stream serialise, so sharing
+    it across calls is safe).  While the stream is being CAPTURED into a CUDA graph the cache is bypassed: a captured
+    kernel keeps the pointer it was recorded with, so the buffer must belong to the graph's own memory pool (torch
+    keeps that pool alive as long as the graph, and re-uses the block for later kernels of the same capture in stream
+    order) -- a cached buffer could be re-allocated by a later, larger eager call and leave the graph with a dangling
+    pointer."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
     key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -83,8 +91,10 @@ def empty_padded(n: int, f: int, device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ graph ---
-def csx_from_coo(key: torch.Tensor, other: torch.Tensor, n: int):
-    """Stable compressed rows over ``key``: (indptr[n+1], indices[E], eid[E]) int32."""
+def csx_from_coo(key: torch.Tensor, other: torch.Tensor, n: int, n_other: Optional[int] = None,
+                 bad: Optional[torch.Tensor] = None):
+    """Stable compressed rows over ``key``: (indptr[n+1], indices[E], eid[E]) int32.  ``bad`` (device int32[1],
+    caller-cleared) is raised when an id lies outside [0, n) / [0, n_other) -- see gte_csx_from_coo_checked."""
     _req_cuda(key, other)
     if key.dtype != torch.int32 or other.dtype != torch.int32:
         raise GteError("csx_from_coo: ids must be int32 (builder.py:425)")
@@ -98,9 +108,10 @@ def csx_from_coo(key: torch.Tensor, other: torch.Tensor, n: int):
     need = l.gte_csx_from_coo_workspace_bytes(n, e)
     ws = workspace(need, dev)
     check(
-        l.gte_csx_from_coo(key.data_ptr(), other.data_ptr(), n, e, indptr.data_ptr(), indices.data_ptr(),
-                           eid.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-        "gte_csx_from_coo",
+        l.gte_csx_from_coo_checked(key.data_ptr(), other.data_ptr(), n, n if n_other is None else int(n_other), e,
+                                   indptr.data_ptr(), indices.data_ptr(), eid.data_ptr(),
+                                   _vec(bad, "bad", torch.int32, 1), ws.data_ptr(), ws.numel(), _stream()),
+        "gte_csx_from_coo_checked",
     )
     return indptr, indices, eid
 

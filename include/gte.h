@@ -40,7 +40,7 @@ extern "C" {
 
 typedef void* gte_stream_t; /* cudaStream_t */
 
-#define GTE_ABI_VERSION 1
+#define GTE_ABI_VERSION 2
 
 #define GTE_OK 0
 #define GTE_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, bad enum) */
@@ -83,6 +83,16 @@ size_t gte_csx_from_coo_workspace_bytes(int32_t n, int64_t e);
 int gte_csx_from_coo(const int32_t* key, const int32_t* other, int32_t n, int64_t e,
                      int32_t* indptr, int32_t* indices, int32_t* eid,
                      void* ws, size_t ws_bytes, gte_stream_t stream);
+/*
+ * Same build with the id check exposed (DGL raises on out-of-range node ids when the graph is created,
+ * builder.py:425): `*bad_ids` (device int32, caller-cleared, only ever raised -- one flag can collect the CSC and the
+ * CSR build) becomes 1 when a `key` lies outside [0, n) (the edge is dropped) or an `other` outside [0, n_other)
+ * (stored as 0, so that no later gather leaves the feature matrix).  The caller reads the flag when it chooses to
+ * synchronise (PageGraphBatch.validate()).  bad_ids NULL = flag kept in the workspace (gte_csx_from_coo).
+ */
+int gte_csx_from_coo_checked(const int32_t* key, const int32_t* other, int32_t n, int32_t n_other, int64_t e,
+                             int32_t* indptr, int32_t* indices, int32_t* eid, int32_t* bad_ids,
+                             void* ws, size_t ws_bytes, gte_stream_t stream);
 
 /*
  * Batch assembly from device-resident per-page compressed rows: replaces

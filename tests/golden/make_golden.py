@@ -158,6 +158,17 @@ def main():
     np.savez_compressed(os.path.join(HERE, "meansage.npz"), **out)
     manifest.append({"file": "meansage.npz", "kind": "MeanSAGE", "nodes": 83, "edges": 600})
 
+    # 6. tensor-core route pin: the repo-default model on 8 pages of 300 nodes (N = 2400 >= 1024 rows, the size from
+    #    which the B200 layers take the tcgen05 3xTF32 kernels), class weights on; reference-produced logits/gradients
+    pages = [synth.make_page(1000 + i, n=300) for i in range(8)]
+    cw = torch.tensor([1.0] * 6 + [2.0] + [1.0] * 2)
+    manifest.append(run_gcnsage(ref, "gcnsage_default_2400", shim_batch(pages), 13, 218, 9, 3, seed=5, class_w=cw))
+
+    # 7. same size, ragged pages (40..900 nodes) and the symmetrised k=5 variant: 4 layers, hidden 96
+    sizes = (900, 40, 333, 128, 517, 77, 260, 145)
+    pages = [synth.make_page(2000 + i, n=n, k=5, bidirectional=True) for i, n in enumerate(sizes)]
+    manifest.append(run_gcnsage(ref, "gcnsage_ragged_2400", shim_batch(pages), 13, 96, 9, 4, seed=6))
+
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
         json.dump({"generator": "tests/golden/make_golden.py", "reference": REF_MODELS,
                    "dgl": "oracle/dgl_shim.py (DGL not installable; see oracle/__init__.py)",

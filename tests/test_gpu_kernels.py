@@ -709,3 +709,91 @@ def test_build_page_formats_bit_exact(ragged, k, bidir):
     s2[0] = int(noff[-1]) - 1
     *_, bad2 = ops.build_page_formats(_i32(s2), dd, wd, _i32(noff), _i32(eoff), len(pages), n, mx_n, mx_e)
     assert int(bad2.item()) == 1
+
+
+# ------------------------------- config-5 sizes: 64-bit row offsets, F = 512, edges-through-L1 at 512 pages -----
+def _oracle_rows_for_pages(pages, page_ids, noff, x_dev, f, mode_norm=True, addend_dev=None):
+    """so.u_mul_e_sum on the sub-batch made of the sampled pages (pages are independent), rows in batch order"""
+    outs = []
+    for p_id in page_ids:
+        pg = pages[p_id]
+        lo = int(noff[p_id])
+        xs = x_dev[lo:lo + pg.num_nodes, :f].cpu()
+        ah = so.u_mul_e_sum(torch.from_numpy(pg.src), torch.from_numpy(pg.dst), torch.from_numpy(pg.weight), xs, pg.num_nodes)
+        if mode_norm:
+            deg = so.in_degrees(torch.from_numpy(pg.dst), pg.num_nodes).float().unsqueeze(1)
+            norm = 1.0 / deg
+            norm[torch.isinf(norm)] = 0
+            ah = ah * norm
+        if addend_dev is not None:
+            ah = ah + addend_dev[lo:lo + pg.num_nodes, :f].cpu()
+        outs.append(ah)
+    return outs
+
+
+def test_spmm_paged_packed_row_offsets_beyond_2_31_bytes_f512():
+    """3600 pages x 300 nodes x F = 512: N * ld * 4 = 2.2e9 > 2^31 bytes, so every row offset of the last pages needs
+    64-bit arithmetic (config 5 reaches 10 M x 512).  Sampled pages (first, around the 2^31-byte mark, last) against
+    so.u_mul_e_sum; whole output against the generic row kernel on 8 random column probes."""
+    num_pages, f = 3600, 512
+    pages = synth.make_pages(num_pages, distinct=24)
+    s, d, w, noff, _ = csx.batch_coo(pages)
+    n = int(noff[-1])
+    assert n * f * 4 > 2 ** 31
+    ip, ix, ei = ops.csx_from_coo(_i32(d), _i32(s), n)
+    wd = _f32(w)
+    norm = ops.degree_norm(ip)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    x = ops.empty_padded(n, f, DEV)
+    x.normal_(generator=gen)
+    pg = (_i32(noff), num_pages, 300, int(max(p.num_edges for p in pages)))
+    assert ops.paged_packed_supported(pg, f)
+    pk = ops.paged_pack_edges(ip, ix, wd, pg, eid=ei)
+    y = ops.spmm_packed(ip, pk, x, pg, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
+    mark = (2 ** 31) // (f * 4 * 300)
+    sample = [0, 1, mark - 1, mark, mark + 1, num_pages // 2, num_pages - 2, num_pages - 1]
+    for p_id, ref in zip(sample, _oracle_rows_for_pages(pages, sample, noff, x, f)):
+        lo = int(noff[p_id])
+        assert rel_err(y[lo:lo + 300], ref) < 2e-6, p_id
+    # generic kernel (global gathers, 64-bit offsets as well) agrees bit for bit on the last 1000 pages
+    y2 = ops.spmm(ip, ix, ops.gather_f32(wd, ei), x, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
+    lo = int(noff[num_pages - 1000])
+    assert torch.equal(y[lo:], y2[lo:])
+    del y2
+    # backward form (CSR, norm[dst] folded in, addend) on the same sizes
+    ipr, ixr, eir = ops.csx_from_coo(_i32(s), _i32(d), n)
+    pkr = ops.paged_pack_edges(ipr, ixr, wd, pg, eid=eir, pre_scale=norm)
+    dh = ops.spmm_packed(ipr, pkr, x, pg, mode=_lib.GTE_AGG_SUM, addend=y)
+    for p_id in (0, mark, num_pages - 1):
+        pgp = pages[p_id]
+        lo = int(noff[p_id])
+        xs = x[lo:lo + 300].cpu()
+        deg = so.in_degrees(torch.from_numpy(pgp.dst), 300).float().unsqueeze(1)
+        nrm = 1.0 / deg
+        nrm[torch.isinf(nrm)] = 0
+        ref = so.u_mul_e_sum(torch.from_numpy(pgp.dst), torch.from_numpy(pgp.src), torch.from_numpy(pgp.weight), xs * nrm, 300)
+        assert rel_err(dh[lo:lo + 300], ref + y[lo:lo + 300].cpu()) < 2e-6, p_id
+
+
+@pytest.mark.parametrize("f", [218, 512])
+def test_spmm_paged_packed_edges_through_l1_at_512_pages(f):
+    """in-degree 40 (config 5's densest point) on 512 pages: the page's packed edges do not fit a stage next to the x
+    slice, the kernel reads them through L1 -- same bits as the generic kernel, sampled pages against the oracle"""
+    num_pages = 512
+    pages = synth.make_pages(num_pages, k=40, distinct=12)
+    s, d, w, noff, _ = csx.batch_coo(pages)
+    n = int(noff[-1])
+    ip, ix, ei = ops.csx_from_coo(_i32(d), _i32(s), n)
+    wd = _f32(w)
+    norm = ops.degree_norm(ip)
+    x = ops.empty_padded(n, f, DEV)
+    x.normal_(generator=torch.Generator(device=DEV).manual_seed(f))
+    pg = (_i32(noff), num_pages, 300, int(max(p.num_edges for p in pages)))
+    assert pg[3] == 300 * 40 and ops.paged_packed_supported(pg, f)
+    pk = ops.paged_pack_edges(ip, ix, wd, pg, eid=ei)
+    y = ops.spmm_packed(ip, pk, x, pg, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm)
+    assert torch.equal(y, ops.spmm(ip, ix, ops.gather_f32(wd, ei), x, mode=_lib.GTE_AGG_SUM_NORM, row_norm=norm))
+    sample = [0, 137, 511]
+    for p_id, ref in zip(sample, _oracle_rows_for_pages(pages, sample, noff, x, f)):
+        lo = int(noff[p_id])
+        assert rel_err(y[lo:lo + 300], ref) < 2e-6, p_id

@@ -323,3 +323,178 @@ def test_data_parallel_single_collective_step_equals_plain_step(monkeypatch):
         n = t1._flat_len
         assert rel_err(t2.flat_grad[:n] / s2[1], t1.flat_grad[:n]) < 2e-6
         assert rel_err(t2.flat_param, t1.flat_param) < 2e-6 and torch.equal(t2.flat_param, t3.flat_param)
+
+
+# ------------------------------------- tensor-core route at the benchmarked sizes (parity gaps) -----
+def _page_counts(d):
+    """per-page node / edge counts of a golden batch (dgl.batch keeps the edges of a page contiguous)"""
+    bn = [int(v) for v in d["batch_num_nodes"]]
+    off = np.concatenate([[0], np.cumsum(bn)])
+    page_of_edge = np.searchsorted(off, d["src"], side="right") - 1
+    assert (np.diff(page_of_edge) >= 0).all()
+    return bn, [int(v) for v in np.bincount(page_of_edge, minlength=len(bn))]
+
+
+def _spy(monkeypatch, names):
+    from gnn_tableextraction_b200 import ops
+
+    calls = {n: 0 for n in names}
+    for n in names:
+        f = getattr(ops, n)
+
+        def wrap(*a, _f=f, _n=n, **kw):
+            calls[_n] += 1
+            return _f(*a, **kw)
+
+        monkeypatch.setattr(ops, n, wrap)
+    return calls
+
+
+@pytest.mark.parametrize("name", ["gcnsage_default_2400", "gcnsage_ragged_2400"])
+@pytest.mark.parametrize("paged", [True, False])
+def test_tensor_core_route_matches_reference_golden(name, paged, monkeypatch):
+    """N = 2400 >= 1024 rows: the layers take the tcgen05 3xTF32 kernels (checked by counting their calls), and the
+    vectors they are compared with were produced by the reference's own models.py (tests/golden/make_golden.py)."""
+    d = load_golden(name)
+    inf, hid, ncls, nl = (int(v) for v in d["config"])
+    model = gte.GcnSAGE(inf, hid, ncls, nl, F.relu, 0)
+    model.load_state_dict(sub(d, "state"))
+    model = model.to(DEV)
+    if paged:
+        bn, be = _page_counts(d)
+        t = lambda a, dt: torch.as_tensor(np.asarray(a)).to(dt).to(DEV)
+        g = gte.PageGraphBatch(t(d["src"], torch.int32), t(d["dst"], torch.int32), int(d["num_nodes"]), bn, be)
+        g.edata["feat"], g.ndata["feat"] = t(d["weight"], torch.float32), t(d["feat"], torch.float32)
+        g.ndata["label"] = t(d["label"], torch.float32)
+    else:
+        g = _cuda_graph(d)
+    calls = _spy(monkeypatch, ["umma_linear_fwd", "umma_linear_bwd_data", "umma_linear_bwd_weight", "spmm_packed"])
+    logits, masks = cuda_forward_with_masks(model, g)
+    assert rel_err(logits, d["logits"]) < TOL
+    cw = torch.from_numpy(d["class_w"]).to(DEV) if "class_w" in d else None
+    loss = gte.CrossEntropyLoss(weight=cw)(logits, g.ndata["label"])
+    assert abs(loss.item() - float(d["loss"])) < TOL * max(1.0, abs(float(d["loss"])))
+    loss.backward()
+    assert calls["umma_linear_fwd"] >= nl - 1 and calls["umma_linear_bwd_weight"] >= nl - 1 and calls["umma_linear_bwd_data"] >= 1
+    assert (calls["spmm_packed"] > 0) == paged
+    if paged:
+        g.check_page_structure()
+    # ReLU patterns may differ from the reference's only at pre-activations within fp32 noise of 0 (DESIGN.md c)
+    om = so.OracleGcnSAGE(inf, hid, ncls, nl, F.relu, 0)
+    om.load_state_dict(sub(d, "state"))
+    og = oracle_graph_from_golden(d)
+    om(og)
+    flips = check_relu_patterns(om, masks)
+    grads = sub(d, "grad")
+    if flips == 0:  # same pattern as the reference run: compare with the reference-produced gradients directly
+        for k, p in model.named_parameters():
+            assert rel_err(p.grad, grads[k]) < TOL, k
+    else:  # same comparison under the CUDA pattern (the oracle equals the golden vectors to 1e-6, tests/test_oracle.py)
+        assert flips <= 3
+        ref = om(og, relu_masks=masks)
+        torch.nn.CrossEntropyLoss(weight=None if cw is None else cw.cpu())(ref, og.ndata["label"].long()).backward()
+        for (k, p), (_, q) in zip(model.named_parameters(), om.named_parameters()):
+            assert rel_err(p.grad, q.grad) < TOL, k
+            assert rel_err(p.grad, grads[k]) < 20 * TOL, k  # one flipped unit moves a bias gradient by O(1/N)
+
+
+def test_config2_full_step_every_gradient_matches_oracle():
+    """One full config-2 train step (512 pages, N = 153600, E = 1.536 M; tcgen05 route, page kernels, one-kernel batch
+    assembly) replayed from the captured CUDA graph: loss, logits and EVERY gradient against the CPU oracle at 1e-5."""
+    pages = synth.make_pages(512, distinct=48)
+    hb = batch_pages_host(pages)
+    om, cm = _oracle_and_cuda_models(21)
+    tr = gte.SageTrainer(cm)
+    g = gte.PageGraphBatch.from_host(hb, DEV)
+    outs = []
+    logits, _ = tr.forward(g, keep_ctx=False, layer_outputs=outs)
+    g.check_page_structure()
+    masks = [(o > 0).cpu() if layer.activation is not None else None for o, layer in zip(outs, cm.layers)]
+    logits = logits.cpu()
+    del outs
+    og = oracle_graph_from_pages(pages)
+    ref = om(og)
+    assert rel_err(logits, ref) < TOL
+    flips = check_relu_patterns(om, masks)
+    assert flips <= 1e-5 * sum(m.numel() for m in masks if m is not None) + 2
+    ref = om(og, relu_masks=masks)
+    oloss = torch.nn.CrossEntropyLoss()(ref, og.ndata["label"].long())
+    oloss.backward()
+    # the product path: captured graph, replayed on the same batch
+    tr.capture(hb)
+    tr.load_batch(hb)
+    st = tr.replay().cpu()
+    assert abs(st[0].item() / st[1].item() - oloss.item()) < TOL * max(1.0, abs(oloss.item()))
+    assert abs(st[2].item() - (ref.argmax(1) == og.ndata["label"].long()).sum().item()) <= 2  # near-tied logits may flip
+    worst = 0.0
+    for (k, p), (_, q) in zip(cm.named_parameters(), om.named_parameters()):
+        e = rel_err(p.grad, q.grad)
+        worst = max(worst, e)
+        assert e < TOL, (k, e)
+    print(f"config-2 full step: worst gradient error {worst:.2e}, {flips} ReLU flips")
+
+
+# ------------------------------------------------ ADVICE r1: captured steps, bad ids, dropout in the trainer -----
+def test_captured_step_follows_the_page_table_of_every_batch():
+    """Batches with the captured totals but a different page order / different page sizes run through the captured
+    graph with THEIR page table (it is an input, refreshed per batch): bit-equal to the eager step.  A batch whose
+    largest page exceeds the captured maxima is refused instead of silently mis-assigned."""
+    pages = synth.make_pages(6, ragged=True, k=6)
+    perm = [3, 0, 5, 1, 4, 2]
+    ha, hb = batch_pages_host(pages), batch_pages_host([pages[i] for i in perm])
+    assert ha["batch_num_nodes"] != hb["batch_num_nodes"] and ha["num_nodes"] == hb["num_nodes"]
+    _, m1 = _oracle_and_cuda_models(31, (13, 40, 9, 3))
+    _, m2 = _oracle_and_cuda_models(31, (13, 40, 9, 3))
+    _, m3 = _oracle_and_cuda_models(31, (13, 40, 9, 3))
+    t1, t2, t3 = gte.SageTrainer(m1), gte.SageTrainer(m2), gte.SageTrainer(m3)
+    t2.capture(ha)
+    t3.capture(ha)
+    t3.prefetch_batch(ha)
+    seq = (ha, hb, hb, ha, hb)
+    for i, hbatch in enumerate(seq):
+        s1 = t1.train_step(gte.PageGraphBatch.from_host(hbatch, DEV)).clone()
+        t2.load_batch(hbatch)
+        s2 = t2.replay().clone()
+        if i + 1 < len(seq):
+            t3.prefetch_batch(seq[i + 1])
+        s3 = t3.replay_prefetched().clone()
+        assert torch.equal(s1, s2) and torch.equal(s1, s3), i
+    assert torch.equal(t1.flat_param, t2.flat_param) and torch.equal(t1.flat_param, t3.flat_param)
+    # same totals, one page larger than anything the capture saw
+    small = synth.make_pages(2, n=100, k=6)
+    big = [synth.make_page(5, n=150, k=6), synth.make_page(6, n=50, k=6)]
+    _, m4 = _oracle_and_cuda_models(32, (13, 24, 9, 3))
+    t4 = gte.SageTrainer(m4)
+    t4.capture(batch_pages_host(small))
+    with pytest.raises(gte.GteError, match="exceeds the captured maxima"):
+        t4.load_batch(batch_pages_host(big))
+    with pytest.raises(gte.GteError):
+        t4.load_batch(batch_pages_host(synth.make_pages(3, n=100, k=4)))  # different totals
+
+
+def test_bad_node_ids_are_flagged_and_memory_safe():
+    """num_nodes too small for the edge list (DGL raises at graph construction): the builders drop / clamp the
+    offending edges so the kernels stay in bounds, and validate() reports it."""
+    p = synth.make_page(3, n=50, k=4)
+    t = lambda a, dt: torch.as_tensor(a).to(dt).to(DEV)
+    g = gte.PageGraphBatch(t(p.src, torch.int32), t(p.dst, torch.int32), 40)  # ids up to 49, 40 nodes declared
+    g.edata["feat"] = t(p.weight, torch.float32)
+    g.ndata["feat"] = t(p.feat[:40], torch.float32)
+    _, cm = _oracle_and_cuda_models(33, (13, 16, 9, 3))
+    out = cm(g)  # must not fault
+    torch.cuda.synchronize()
+    assert out.shape == (40, 9)
+    with pytest.raises(gte.GteError, match="outside"):
+        g.validate()
+    ok = gte.PageGraphBatch.from_pages([p], DEV)
+    cm(ok)
+    ok.validate()
+    # broken page table on the one-kernel batch assembly path
+    two = synth.make_pages(2, n=60, k=4)
+    hb = batch_pages_host(two)
+    gb = gte.PageGraphBatch(hb["src"].to(DEV), hb["dst"].to(DEV), 120, [70, 50], [hb["batch_num_edges"][0], hb["batch_num_edges"][1]])
+    gb.edata["feat"], gb.ndata["feat"] = hb["weight"].to(DEV), hb["feat"].to(DEV)
+    cm(gb)
+    torch.cuda.synchronize()
+    with pytest.raises(gte.GteError, match="leaves its page"):
+        gb.validate()

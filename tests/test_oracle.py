@@ -18,7 +18,8 @@ from oracle import sage_oracle as so
 
 
 # ---------------------------------------------------------------- golden ----
-@pytest.mark.parametrize("name", ["gcnsage_default_knn", "gcnsage_bidir_classw", "gcnsage_multigraph"])
+@pytest.mark.parametrize("name", ["gcnsage_default_knn", "gcnsage_bidir_classw", "gcnsage_multigraph",
+                                  "gcnsage_default_2400", "gcnsage_ragged_2400"])
 def test_oracle_matches_reference_gcnsage(name):
     d = load_golden(name)
     inf, hid, ncls, nl = (int(v) for v in d["config"])
