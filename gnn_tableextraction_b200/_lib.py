@@ -25,6 +25,8 @@ SIGNATURES = {
     "gte_abi_version": (ci, []),
     "gte_last_error_string": (C.c_char_p, []),
     "gte_launch_count": (i64, []),
+    "gte_set_tuning": (ci, [ci, ci]),
+    "gte_get_tuning": (ci, [ci]),
     "gte_device_info": (ci, [C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
     "gte_csx_from_coo_workspace_bytes": (sz, [i32, i64]),
     "gte_csx_from_coo": (ci, [vp, vp, i32, i64, vp, vp, vp, vp, sz, vp]),
@@ -52,7 +54,7 @@ SIGNATURES = {
     "gte_umma_pack_weights": (ci, [vp, i64, i32, i32, i32, vp, vp]),
     "gte_umma_linear_fwd": (ci, [vp, i64, vp, i64, i32, vp, vp, vp, vp, f32, ci, ci, vp, i64, vp, i64, vp, vp, i32, i32, vp]),
     "gte_umma_linear_bwd_data": (ci, [vp, i64, i32, vp, i32, vp, i64, vp, i64, i32, i32, vp]),
-    "gte_umma_debug_times": (ci, [vp, i32]),
+    "gte_umma_debug_times": (ci, [i32, vp, i32]),
     "gte_umma_linear_fwd_stacked": (ci, [vp, i64, i32, vp, vp, i32, vp, i64, i32, vp]),
     "gte_umma_linear_bwd_data2": (ci, [vp, i64, vp, i64, i32, vp, vp, i64, i32, i32, vp]),
     "gte_umma_bwd_weight_supported": (ci, [i32, i32, i32]),
@@ -77,6 +79,7 @@ SIGNATURES = {
     "gte_adam_step": (ci, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, f32, vp, vp]),
 }
 
+GTE_TUNE_UMMA_PAIR, GTE_TUNE_DW_PAIR = 0, 1
 GTE_AGG_SUM, GTE_AGG_SUM_NORM, GTE_AGG_MEAN = 0, 1, 2
 GTE_NORM_INV_DEG_ZERO, GTE_NORM_INV_DEG_CLAMP = 0, 1
 GTE_LABEL_I64, GTE_LABEL_I32, GTE_LABEL_F32 = 0, 1, 2

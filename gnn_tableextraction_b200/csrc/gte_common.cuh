@@ -22,6 +22,9 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // SM count of the current device (cached per device; immutable after first query)
 int sm_count();
 
+// process-wide A/B switches behind gte_set_tuning() (defaults = the product path)
+int tuning(int key);
+
 // number of kernels launched by this library since load (diagnostic; gte_launch_count())
 void note_launch();
 

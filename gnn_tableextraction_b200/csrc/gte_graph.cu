@@ -49,6 +49,10 @@ int ensure_dynamic_smem(const void* func, size_t bytes, const char* name) {
   return GTE_OK;
 }
 
+// process-wide A/B switches (gte_set_tuning); defaults = the product path
+static std::atomic<int> g_tuning[GTE_TUNE_COUNT] = {{1}, {1}};
+int tuning(int key) { return (key >= 0 && key < GTE_TUNE_COUNT) ? g_tuning[key].load(std::memory_order_relaxed) : 0; }
+
 int sm_count() {
   static int cached[64];
   static std::once_flag once;
@@ -305,6 +309,14 @@ int gte_abi_version(void) { return GTE_ABI_VERSION; }
 int64_t gte_launch_count(void) { return (int64_t)launches(); }
 
 const char* gte_last_error_string(void) { return err_buf(); }
+
+int gte_set_tuning(int key, int value) {
+  GTE_CHECK_ARG(key >= 0 && key < GTE_TUNE_COUNT, "gte_set_tuning: unknown key %d", key);
+  g_tuning[key].store(value, std::memory_order_relaxed);
+  return GTE_OK;
+}
+
+int gte_get_tuning(int key) { return tuning(key); }
 
 int gte_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host) {
   int dev = 0;

@@ -25,81 +25,25 @@
 // Roofline: tensor pipe (3 * 2*M*N*K flops at the TF32 rate) vs. L2->SM operand
 // traffic (W tiles are re-read per 128-row tile); HBM traffic is compulsory
 // (read A once, write z and y once).
-#include "gte_common.cuh"
-#include "gte_umma_ptx.cuh"
+#include "gte_umma_args.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
 
 namespace gte {
 
+#ifdef GTE_EXPERIMENTS
 // diagnostic: per-CTA, per-tile role timestamps (clock64) when UmmaArgs::dbg != 0; read with gte_umma_debug_times()
 __device__ long long g_umma_dbg[148 * 16 * 8];
+#endif
 
 constexpr int UM_THREADS = 384;
-constexpr int UM_BM = 128;
-constexpr int UM_BK = 32;               // floats per k block = one 128-byte swizzle row
 constexpr int UM_STAGES = 2;
 constexpr int UM_SPLIT_THREADS = 192;     // warps 2..7 split the A operand
 constexpr int UM_PREFETCH = 8;            // k-blocks of L2 prefetch lookahead for the activation tiles
-constexpr int UM_A_BYTES = UM_BM * 128;  // 16 KB
-constexpr int UM_MAX_BN = 256;
-constexpr int UM_ACC_STRIDE = 256;       // TMEM columns per accumulator stage
 // per epilogue warp: one or two 32x32 fp32 store tiles (TMA store, 1024-byte aligned); the legacy
 // [32][36] transposition tile (4608 B) must fit as well
 __host__ __device__ constexpr int um_epi_bytes(int nbuf) { return nbuf == 2 ? 8192 : 5120; }
-
-struct UmmaArgs {
-  CUtensorMap tmA[2];       // per K segment: activations [M, K_s], box 32 x 128
-  CUtensorMap tmBhi[2][2];  // [group][segment]: packed weights hi [BN, Kpad], box 32 x BN
-  CUtensorMap tmBlo[2][2];
-  CUtensorMap tmOut[2];     // per group: z / dx, box 32 x 32 (TMA store)
-  CUtensorMap tmY;          // y (TMA store)
-  int32_t nseg, ngroups;
-  int32_t kblocks[2];
-  int32_t M, N, BN;
-  float* out[2];            // per group: pre-activation output (z / dx)
-  int64_t ldo[2];
-  float* y;                 // LayerNorm/ReLU output (forward only), may be null
-  int64_t ldy;
-  const float* bias;
-  const float* gamma;
-  const float* beta;
-  float* mean;
-  float* rstd;
-  float eps;
-  int32_t fuse_ln, relu;
-  int32_t dbg;
-  int32_t tma_store;  // outputs are TMA-store compatible (16-byte aligned, ld % 4 == 0)
-  int32_t epi_bufs;   // store tiles per epilogue warp (2 unless shared memory is tight)
-  int32_t bias_n;  // number of valid bias entries (the stacked class-layer output is wider than its bias)
-  int32_t variant;  // bit0: round-to-nearest hi/lo split, bit1: cross terms in their own accumulator
-};
-
-// x[j] = accumulator (main [+ cross-term accumulator]) + bias for the 32 columns of one chunk of this thread's row.
-// Everything is compile-time indexed so the 32-register TMEM load windows stay in registers (no local memory).
-template <bool SPLIT>
-__device__ __forceinline__ void epi_load_chunk(uint32_t taddr, const float* bias_c, float (&x)[32]) {
-  uint32_t v[32];
-  tmem_ld_32x32b_x32_nowait(taddr, v);
-  if constexpr (SPLIT) {
-    uint32_t v2[32];
-    tmem_ld_32x32b_x32_nowait(taddr + UM_ACC_STRIDE, v2);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-  } else {
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-  }
-  const float4* b4 = reinterpret_cast<const float4*>(bias_c);
-#pragma unroll
-  for (int qd = 0; qd < 8; ++qd) {
-    const float4 b = b4[qd];
-    x[4 * qd] += b.x; x[4 * qd + 1] += b.y; x[4 * qd + 2] += b.z; x[4 * qd + 3] += b.w;
-  }
-}
 
 // ------------------------------------------------------------ the kernel ---
 template <bool SPLIT>
@@ -133,12 +77,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
   const int m_tiles = (P.M + UM_BM - 1) / UM_BM;
   const int total_tiles = m_tiles * P.ngroups;
   const int kb_total = P.kblocks[0] + (P.nseg > 1 ? P.kblocks[1] : 0);
+#ifdef GTE_EXPERIMENTS
   auto stamp = [&](int tile, int slot) {
     if (P.dbg && blockIdx.x < 148) {
       const int t = (tile - blockIdx.x) / gridDim.x;
       if (t < 16) g_umma_dbg[(blockIdx.x * 16 + t) * 8 + slot] = clock64();
     }
   };
+#else
+  auto stamp = [](int, int) {};
+#endif
 
   for (int i = threadIdx.x; i < UM_MAX_BN; i += UM_THREADS) {
     s_bias[i] = (P.bias && i < P.bias_n) ? P.bias[i] : 0.f;
@@ -260,16 +208,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
         for (int i = 0; i < (UM_A_BYTES / 16 + UM_SPLIT_THREADS - 1) / UM_SPLIT_THREADS; ++i) {
           const int idx = t + UM_SPLIT_THREADS * i;
           if (idx >= UM_A_BYTES / 16) break;
+          // hi stays as TMA wrote it: kind::tf32 reads the top 19 bits of the fp32 word, i.e. a_hi = trunc(a);
+          // only the remainder a - trunc(a) (exact in fp32, rounded to tf32) is written
           const float4 v = hi[idx];
-          float4 h, l;
-          if (P.variant & 1) {
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-            l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-          } else {
-            h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          }
-          hi[idx] = h;
+          float4 l;
+          l.x = tf32_rna(v.x - tf32_hi(v.x)); l.y = tf32_rna(v.y - tf32_hi(v.y));
+          l.z = tf32_rna(v.z - tf32_hi(v.z)); l.w = tf32_rna(v.w - tf32_hi(v.w));
           lo[idx] = l;
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
@@ -347,27 +291,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
       const int rows_valid = (int)min((int64_t)32, (int64_t)P.M - row0);
       for (int c = 0; c < nchunks; ++c) {
         load_chunk(c);
-        if (P.tma_store)
-          epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0, P.dbg);
-        else if (rows_valid > 0)
-          epi_store_chunk(st, x, outp + row0 * ldo + c * 32, ldo, rows_valid, P.N - c * 32, vec_out);
-        if (P.y != nullptr) {
-          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c * 32);
-          const float4* e4 = reinterpret_cast<const float4*>(s_beta + c * 32);
-#pragma unroll
-          for (int qd = 0; qd < 8; ++qd) {
-            const float4 gm = g4[qd], bt = e4[qd];
-            const float gv[4] = {gm.x, gm.y, gm.z, gm.w}, bv[4] = {bt.x, bt.y, bt.z, bt.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float o = x[4 * qd + e];
-              if (P.fuse_ln) o = (o - mean) * rstd * gv[e] + bv[e];
-              if (P.relu) o = fmaxf(o, 0.f);
-              x[4 * qd + e] = o;
-            }
-          }
+        if (outp != nullptr) {  // z / dx (not wanted by inference-only callers)
           if (P.tma_store)
-            epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmY, c * 32, (int32_t)row0, P.dbg);
+            epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
+          else if (rows_valid > 0)
+            epi_store_chunk(st, x, outp + row0 * ldo + c * 32, ldo, rows_valid, P.N - c * 32, vec_out);
+        }
+        if (P.y != nullptr) {
+          epi_norm_act(x, s_gamma + c * 32, s_beta + c * 32, P.fuse_ln != 0, P.relu != 0, mean, rstd);
+          if (P.tma_store)
+            epi_store_chunk_tma(stb, P.epi_bufs, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
           else if (rows_valid > 0)
             epi_store_chunk(st, x, P.y + row0 * P.ldy + c * 32, P.ldy, rows_valid, P.N - c * 32, vec_y);
         }
@@ -396,7 +329,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
 //            row 16+o = W[o, fin:2fin] (neighbour block): ONE pass over x gives [x Ws^T | x Wn^T] side by side.
 __global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
                             float* __restrict__ Pf, int32_t BN, int32_t Kp, float* __restrict__ Pb, int32_t BNb,
-                            int32_t Kpb, float* __restrict__ Ps, int32_t variant) {
+                            int32_t Kpb, float* __restrict__ Ps) {
   const int64_t per_f = (int64_t)BN * Kp, per_b = (int64_t)BNb * Kpb;
   const int64_t total_f = (int64_t)nseg * per_f, total_b = (int64_t)nseg * per_b;
   const int64_t total_s = Ps ? (int64_t)32 * Kp : 0;
@@ -429,9 +362,9 @@ __global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo
       dst = Pb + (int64_t)grp * 2 * per_b + r;
       half_stride = per_b;
     }
-    const float h = (variant & 1) ? tf32_rna(w) : tf32_hi(w);
+    const float h = tf32_rna(w);  // round-to-nearest split of the (small, packed once per step) weight operand
     dst[0] = h;
-    dst[half_stride] = (variant & 1) ? tf32_rna(w - h) : tf32_hi(w - h);
+    dst[half_stride] = tf32_rna(w - h);
   }
 }
 
@@ -442,16 +375,6 @@ static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-// experiment switch (GTE_UMMA_VARIANT): bit0 = round-to-nearest split, bit1 = separate cross-term accumulator
-static int umma_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GTE_UMMA_VARIANT");
-    v = e ? atoi(e) : 3;
-  }
-  return v;
-}
 
 struct PackDims {
   int BN, Kp, BNb, Kpb;
@@ -477,12 +400,12 @@ static size_t umma_smem_bytes(int BN, int epi_bufs) {
 // TMA-store descriptors for the outputs (used when every output is 16-byte aligned with ld % 4 == 0)
 static int setup_output_maps(UmmaArgs& a) {
   bool ok = true;
-  for (int g = 0; g < a.ngroups; ++g) ok = ok && aligned16(a.out[g]) && a.ldo[g] % 4 == 0;
+  for (int g = 0; g < a.ngroups; ++g) ok = ok && (a.out[g] == nullptr || (aligned16(a.out[g]) && a.ldo[g] % 4 == 0));
   if (a.y) ok = ok && aligned16(a.y) && a.ldy % 4 == 0;
-  if (const char* e = getenv("GTE_UMMA_TMA_STORE")) ok = ok && atoi(e) != 0;  // experiment switch: 0 = transposed st.global path
   a.tma_store = ok ? 1 : 0;
   if (!ok) return GTE_OK;
   for (int g = 0; g < a.ngroups; ++g) {
+    if (a.out[g] == nullptr) continue;
     int rc = make_tmap_2d(&a.tmOut[g], a.out[g], a.M, a.N, a.ldo[g], 32, 32);
     if (rc) return rc;
   }
@@ -493,17 +416,25 @@ static int setup_output_maps(UmmaArgs& a) {
   return GTE_OK;
 }
 
-static int launch_umma(UmmaArgs& a, cudaStream_t st) {
-  {
-    int rc = setup_output_maps(a);
-    if (rc) return rc;
-  }
+// weight-tile maps with the box of the kernel that will run: BN rows (single CTA) or BN/2 rows (each CTA of a pair
+// stages half of the B rows)
+int setup_weight_maps(UmmaArgs& a, int box_rows) {
+  for (int g = 0; g < a.ngroups; ++g)
+    for (int s = 0; s < a.nseg; ++s) {
+      int rc = make_map(&a.tmBhi[g][s], a.bhi[g][s], a.BN, a.b_cols, a.b_cols, box_rows);
+      if (rc) return rc;
+      rc = make_map(&a.tmBlo[g][s], a.blo[g][s], a.BN, a.b_cols, a.b_cols, box_rows);
+      if (rc) return rc;
+    }
+  return GTE_OK;
+}
+
+int launch_umma_single(UmmaArgs& a, cudaStream_t st) {
+  if (int rc = setup_weight_maps(a, a.BN)) return rc;
   a.epi_bufs = umma_smem_bytes(a.BN, 2) <= 227 * 1024 ? 2 : 1;
   const size_t smem = umma_smem_bytes(a.BN, a.epi_bufs);
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_gemm<true>), smem, "k_umma_gemm")) return rc;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_gemm<false>), smem, "k_umma_gemm")) return rc;
-  a.variant = umma_variant();
-  a.dbg = getenv("GTE_UMMA_DBG") ? atoi(getenv("GTE_UMMA_DBG")) : 0;  // bit0: role timestamps; bits1-2: epilogue store experiments
   const int tiles = ((a.M + UM_BM - 1) / UM_BM) * a.ngroups;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
@@ -514,12 +445,23 @@ static int launch_umma(UmmaArgs& a, cudaStream_t st) {
   // TMEM for a second accumulator stage (epilogue of tile i overlaps the MMAs of tile i+1) and halves the
   // epilogue's TMEM reads.
   const int kb_total = a.kblocks[0] + (a.nseg > 1 ? a.kblocks[1] : 0);
-  if ((a.variant & 2) && kb_total > 2)
+  if (kb_total > 2)
     k_umma_gemm<true><<<grid, UM_THREADS, smem, st>>>(a);
   else
     k_umma_gemm<false><<<grid, UM_THREADS, smem, st>>>(a);
   GTE_CHECK_LAUNCH("k_umma_gemm");
   return GTE_OK;
+}
+
+// CTA pairs (cta_group::2) whenever the shape allows it: the pair halves the weight-tile traffic per SM, which is what
+// bounds the 3xTF32 contraction (see gte_umma2.cu); gte_set_tuning(GTE_TUNE_UMMA_PAIR, 0) forces the single-CTA kernel.
+static int launch_umma(UmmaArgs& a, cudaStream_t st) {
+  if (int rc = setup_output_maps(a)) return rc;
+#ifdef GTE_EXPERIMENTS
+  a.dbg = getenv("GTE_UMMA_DBG") ? atoi(getenv("GTE_UMMA_DBG")) : 0;  // role timestamps
+#endif
+  if (tuning(GTE_TUNE_UMMA_PAIR) != 0 && umma_pair_supported(a)) return launch_umma_pair(a, st);
+  return launch_umma_single(a, st);
 }
 
 }  // namespace gte
@@ -548,7 +490,7 @@ int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, 
   const int64_t total = (int64_t)nseg * ((int64_t)d.BN * d.Kp + (int64_t)d.BNb * d.Kpb) + (int64_t)d.stacked_floats / 2;
   k_umma_pack<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
       W, ldw, fo, fin, nseg, pack, d.BN, d.Kp, pack + d.fwd_floats, d.BNb, d.Kpb,
-      d.stacked_floats ? pack + d.fwd_floats + d.bwd_floats : nullptr, umma_variant());
+      d.stacked_floats ? pack + d.fwd_floats + d.bwd_floats : nullptr);
   GTE_CHECK_LAUNCH("k_umma_pack");
   return GTE_OK;
 }
@@ -560,11 +502,11 @@ int gte_umma_linear_fwd(const float* x1, int64_t ldx1, const float* x2, int64_t 
   GTE_CHECK_ARG(n >= 0, "gte_umma_linear_fwd: negative n");
   if (!gte_umma_supported(fo, fin)) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_fwd: fo=%d fin=%d unsupported", fo, fin);
   if (n == 0) return GTE_OK;
-  GTE_CHECK_ARG(x1 && pack && z, "gte_umma_linear_fwd: null argument");
+  GTE_CHECK_ARG(x1 && pack && (z || y), "gte_umma_linear_fwd: null argument (z may be NULL only when y is given)");
   GTE_CHECK_ARG(!fuse_ln || (gamma && beta && mean && rstd && y), "gte_umma_linear_fwd: fused LayerNorm needs gamma/beta/mean/rstd/y");
   GTE_CHECK_ARG(aligned16(x1) && ldx1 % 4 == 0 && ldx1 >= fin, "gte_umma_linear_fwd: x1 must be 16-byte aligned with ld %% 4 == 0");
   GTE_CHECK_ARG(!x2 || (aligned16(x2) && ldx2 % 4 == 0 && ldx2 >= fin), "gte_umma_linear_fwd: x2 must be 16-byte aligned with ld %% 4 == 0");
-  GTE_CHECK_ARG(ldz >= fo && (!y || ldy >= fo), "gte_umma_linear_fwd: output leading dimension < fo");
+  GTE_CHECK_ARG((!z || ldz >= fo) && (!y || ldy >= fo), "gte_umma_linear_fwd: output leading dimension < fo");
   const int nseg = x2 ? 2 : 1;
   PackDims d = pack_dims(fo, fin, nseg);
   UmmaArgs a{};
@@ -580,11 +522,10 @@ int gte_umma_linear_fwd(const float* x1, int64_t ldx1, const float* x2, int64_t 
     a.kblocks[s] = d.Kp / UM_BK;
     int rc = make_map(&a.tmA[s], xs[s], n, fin, lds[s], UM_BM);
     if (rc) return rc;
-    rc = make_map(&a.tmBhi[0][s], pack + (size_t)s * 2 * per, d.BN, d.Kp, d.Kp, d.BN);
-    if (rc) return rc;
-    rc = make_map(&a.tmBlo[0][s], pack + (size_t)s * 2 * per + per, d.BN, d.Kp, d.Kp, d.BN);
-    if (rc) return rc;
+    a.bhi[0][s] = pack + (size_t)s * 2 * per;
+    a.blo[0][s] = pack + (size_t)s * 2 * per + per;
   }
+  a.b_cols = d.Kp;
   a.out[0] = z;
   a.ldo[0] = ldz;
   a.y = y;
@@ -622,11 +563,10 @@ int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const fl
   if (rc) return rc;
   const size_t per = (size_t)d.BNb * d.Kpb;
   for (int gq = 0; gq < nseg; ++gq) {
-    rc = make_map(&a.tmBhi[gq][0], pb + (size_t)gq * 2 * per, d.BNb, d.Kpb, d.Kpb, d.BNb);
-    if (rc) return rc;
-    rc = make_map(&a.tmBlo[gq][0], pb + (size_t)gq * 2 * per + per, d.BNb, d.Kpb, d.Kpb, d.BNb);
-    if (rc) return rc;
+    a.bhi[gq][0] = pb + (size_t)gq * 2 * per;
+    a.blo[gq][0] = pb + (size_t)gq * 2 * per + per;
   }
+  a.b_cols = d.Kpb;
   a.out[0] = dx1;
   a.ldo[0] = lddx1;
   a.out[1] = dx2;
@@ -656,10 +596,9 @@ int gte_umma_linear_fwd_stacked(const float* x, int64_t ldx, int32_t fin, const 
   a.kblocks[0] = d.Kp / UM_BK;
   int rc = make_map(&a.tmA[0], x, n, fin, ldx, UM_BM);
   if (rc) return rc;
-  rc = make_map(&a.tmBhi[0][0], ps, 32, d.Kp, d.Kp, 32);
-  if (rc) return rc;
-  rc = make_map(&a.tmBlo[0][0], ps + (size_t)32 * d.Kp, 32, d.Kp, d.Kp, 32);
-  if (rc) return rc;
+  a.bhi[0][0] = ps;
+  a.blo[0][0] = ps + (size_t)32 * d.Kp;
+  a.b_cols = d.Kp;
   a.out[0] = out;
   a.ldo[0] = ldo;
   a.bias = bias;
@@ -692,21 +631,27 @@ int gte_umma_linear_bwd_data2(const float* dz1, int64_t lddz1, const float* dz2,
     a.kblocks[s] = d.Kpb / UM_BK;
     int rc = make_map(&a.tmA[s], dzs[s], n, fo, lds[s], UM_BM);
     if (rc) return rc;
-    rc = make_map(&a.tmBhi[0][s], pb + (size_t)s * 2 * per, d.BNb, d.Kpb, d.Kpb, d.BNb);
-    if (rc) return rc;
-    rc = make_map(&a.tmBlo[0][s], pb + (size_t)s * 2 * per + per, d.BNb, d.Kpb, d.Kpb, d.BNb);
-    if (rc) return rc;
+    a.bhi[0][s] = pb + (size_t)s * 2 * per;
+    a.blo[0][s] = pb + (size_t)s * 2 * per + per;
   }
+  a.b_cols = d.Kpb;
   a.out[0] = dx;
   a.ldo[0] = lddx;
   return launch_umma(a, as_stream(stream));
 }
 
-// diagnostic only: copy the role timestamps of the last k_umma_gemm launch run with GTE_UMMA_DBG=1 (148 x 16 x 8 int64)
-int gte_umma_debug_times(int64_t* out_host, int32_t count) {
+// diagnostic only (-DGTE_EXPERIMENTS builds): copy the role timestamps of the last tensor-core projection launched with
+// GTE_UMMA_DBG=1 (148 x 16 x 8 int64); `which` 0 = single-CTA kernel, 1 = CTA-pair kernel
+int gte_umma_debug_times(int32_t which, int64_t* out_host, int32_t count) {
   if (!out_host || count <= 0 || count > 148 * 16 * 8) return fail(GTE_ERR_INVALID, "gte_umma_debug_times: bad argument");
+#ifdef GTE_EXPERIMENTS
+  if (which == 1) return umma_pair_debug_times(out_host, count);
   GTE_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_umma_dbg, (size_t)count * 8), "gte_umma_debug_times");
   return GTE_OK;
+#else
+  (void)which;
+  return fail(GTE_ERR_UNSUPPORTED, "gte_umma_debug_times: library built without -DGTE_EXPERIMENTS");
+#endif
 }
 
 }  // extern "C"

@@ -137,6 +137,95 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------ CTA pairs (cta_group::2) ----
+// Two CTAs of one cluster (two SMs of a TPC) run ONE tcgen05.mma: each holds 128 rows of A and half of the B rows in
+// its own shared memory, and its own 128 TMEM lanes of the accumulator.  The leader CTA (cluster rank 0) issues.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on a barrier that may live in the peer CTA (address from mapa_shared), release at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier whose arrivals may come from the peer CTA: acquire at cluster scope
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// same, with nanosleep backoff, for roles that routinely wait a long time
+__device__ __forceinline__ void mbar_wait_cluster_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done, ns = 32;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+    if (ns < 512) ns <<= 1;
+  }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// D[tmem, 2 x 128 lanes] (+)= A[2 x 128 rows, smem of each CTA] * B[N rows: N/2 in each CTA], kind::tf32
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// smem tile -> global, element-wise fp32 ADD performed by the memory system (L2): partial accumulation without
+// reading the old value into the SM
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src_smem, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t r;
@@ -175,29 +264,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // One 32-row x 32-column accumulator chunk (thread = row) -> dense, 128B-swizzled shared tile [32][32] floats
-// -> one asynchronous TMA store (bounds clipped by the tensor map).  `buf` is 1024-byte aligned and warp private;
+// -> one asynchronous TMA store (bounds clipped by the tensor map).  `bufs` is 1024-byte aligned and warp private;
 // `seq` counts this warp's stores: with nbuf == 2 two buffers alternate (one older store may still be reading).
-// `dbg` (experiments only): bit1 = do not issue the TMA store, bit2 = do not stage (no shared stores / proxy fence)
 __device__ __forceinline__ void epi_store_chunk_tma(uint8_t* bufs, int nbuf, int& seq, const float (&v)[32],
-                                                    const CUtensorMap* map, int32_t col0, int32_t row0, int dbg = 0) {
+                                                    const CUtensorMap* map, int32_t col0, int32_t row0) {
   const int lane = threadIdx.x & 31;
-  if (dbg & 6) {
-    if (!(dbg & 4)) {
-      float* rowp = reinterpret_cast<float*>(bufs) + lane * 32;
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      fence_proxy_async();
-      __syncwarp();
-    }
-    if (!(dbg & 2) && lane == 0) {
-      tma_store_2d(map, smem_u32(bufs), col0, row0);
-      tma_store_commit();
-      tma_store_wait_read<0>();
-    }
-    if (v[0] == 12345.678f) bufs[lane] = 1;  // keep v alive
-    return;
-  }
   uint8_t* buf = bufs + (nbuf == 2 ? (seq & 1) * 4096 : 0);
   if (seq >= nbuf) {
     if (lane == 0) {

@@ -116,7 +116,7 @@ class SageTrainer:
         for layer in self.model.layers:
             W, b, gamma, beta, has_ln, eps, relu = self._layer_args(layer)
             h, ctx = L.sage_layer_forward(g, h, w_edge, W, b, gamma, beta, ln=has_ln, relu=relu, eps=eps, agg=L.GCN,
-                                          use_pp=layer.use_pp)
+                                          use_pp=layer.use_pp, save_for_backward=keep_ctx)
             ctxs.append(ctx if keep_ctx else None)
             if layer_outputs is not None:
                 layer_outputs.append(h)

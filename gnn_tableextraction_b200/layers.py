@@ -132,8 +132,9 @@ def aggregate_backward(g: PageGraphBatch, d_out: torch.Tensor, w_edge: torch.Ten
 def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Optional[torch.Tensor],
                        W: torch.Tensor, b: Optional[torch.Tensor], gamma: Optional[torch.Tensor],
                        beta: Optional[torch.Tensor], *, ln: bool, relu: bool, eps: float = 1e-5, agg: str = GCN,
-                       use_pp: bool = False, strategy: Optional[str] = None):
-    """Returns (out [N, Fout], LayerCtx)."""
+                       use_pp: bool = False, strategy: Optional[str] = None, save_for_backward: bool = True):
+    """Returns (out [N, Fout], LayerCtx).  ``save_for_backward=False`` (inference): the fused tensor-core epilogue does not
+    write the pre-activation z (it only exists for the backward pass)."""
     fout = W.shape[0]
     fin = W.shape[1] if use_pp else W.shape[1] // 2
     if h.shape[1] != (W.shape[1] if use_pp else fin):
@@ -154,7 +155,7 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
             # tensor cores: projection + bias + LayerNorm + ReLU in one kernel
             ctx.pack = ops.umma_pack_weights(W, fin, 2)
             z, y, ctx.mean, ctx.rstd = ops.umma_linear_fwd(h, ah, fin, ctx.pack, b, fout, gamma=gamma, beta=beta,
-                                                           eps=eps, relu=relu, fuse_ln=ln)
+                                                           eps=eps, relu=relu, fuse_ln=ln, want_z=save_for_backward)
             ctx.z = z
             return (y if y is not None else z), ctx
         if (ln or not relu) and ops.wide_out_supported(fin, fin, fout, h, ah) and h.shape[0] >= SKINNY_MIN_ROWS:

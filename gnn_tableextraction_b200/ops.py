@@ -443,9 +443,19 @@ def umma_pack_weights(W: torch.Tensor, fin: int, nseg: int, out: Optional[torch.
     return out
 
 
+def set_tuning(key: int, value: int) -> None:
+    """Process-wide A/B switch of the native library (tests / measurements; see gte.h gte_set_tuning)."""
+    check(lib().gte_set_tuning(int(key), int(value)), "gte_set_tuning")
+
+
+def get_tuning(key: int) -> int:
+    return int(lib().gte_get_tuning(int(key)))
+
+
 def umma_linear_fwd(x1, x2, fin: int, pack, bias, fo: int, *, gamma=None, beta=None, eps: float = 1e-5,
-                    relu: bool = False, fuse_ln: bool = False, want_y: bool = False):
-    """(z, y, mean, rstd): z = [x1 | x2] W^T + b ; y = act(LN(z)) / act(z) (None unless requested)."""
+                    relu: bool = False, fuse_ln: bool = False, want_y: bool = False, want_z: bool = True):
+    """(z, y, mean, rstd): z = [x1 | x2] W^T + b ; y = act(LN(z)) / act(z) (None unless requested).
+    ``want_z=False`` (inference: nothing is saved for a backward pass) skips the z stores when y exists."""
     x1p, ld1, k1 = _mat(x1, "umma.x1")
     n = x1.shape[0]
     x2p, ld2 = None, 0
@@ -456,9 +466,9 @@ def umma_linear_fwd(x1, x2, fin: int, pack, bias, fo: int, *, gamma=None, beta=N
     if k1 != fin:
         raise GteError("umma_linear_fwd: x1 shape mismatch")
     dev = x1.device
-    z = empty_padded(n, fo, dev)
-    zp, ldz, _ = _mat(z, "umma.z")
     need_y = fuse_ln or want_y or relu
+    z = empty_padded(n, fo, dev) if (want_z or not need_y) else None
+    zp, ldz = (None, 0) if z is None else _mat(z, "umma.z")[:2]
     y = empty_padded(n, fo, dev) if need_y else None
     yp, ldy = (None, 0) if y is None else _mat(y, "umma.y")[:2]
     mean = torch.empty(n, dtype=torch.float32, device=dev) if fuse_ln else None

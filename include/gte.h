@@ -67,6 +67,19 @@ int gte_abi_version(void);
 const char* gte_last_error_string(void);
 /* Kernels launched by this library since it was loaded (process-wide diagnostic counter). */
 int64_t gte_launch_count(void);
+
+/*
+ * Process-wide A/B switches for tests and measurements (NOT a configuration surface: the defaults are the product
+ * path; every value computes the same results through a different kernel).
+ *   GTE_TUNE_UMMA_PAIR   1 (default): tensor-core projections run on CTA pairs (tcgen05 cta_group::2) when the shape
+ *                        allows it; 0: always the single-CTA kernel
+ *   GTE_TUNE_DW_PAIR     same for the tensor-core weight gradients
+ */
+#define GTE_TUNE_UMMA_PAIR 0
+#define GTE_TUNE_DW_PAIR 1
+#define GTE_TUNE_COUNT 2
+int gte_set_tuning(int key, int value);
+int gte_get_tuning(int key);
 /* SM count and compute capability of the current device. */
 int gte_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 
@@ -295,8 +308,9 @@ int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const fl
                              float* dx1, int64_t lddx1, float* dx2, int64_t lddx2, int32_t n, int32_t fin,
                              gte_stream_t stream);
 
-/* Diagnostic: role timestamps (clock64) of the last tensor-core projection launched with GTE_UMMA_DBG=1. */
-int gte_umma_debug_times(int64_t* out_host, int32_t count);
+/* Diagnostic (-DGTE_EXPERIMENTS builds; GTE_ERR_UNSUPPORTED otherwise): role timestamps (clock64) of the last tensor-core
+ * projection launched with GTE_UMMA_DBG=1; which: 0 = single-CTA kernel, 1 = CTA-pair kernel. */
+int gte_umma_debug_times(int32_t which, int64_t* out_host, int32_t count);
 
 /*
  * Class-layer (fo <= 16) forms of the project-then-aggregate strategy.  `pack` from

@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes, numpy as np, torch
 from gnn_tableextraction_b200 import ops, lib
 DEV = "cuda"
+WHICH = int(os.environ.get("GTE_UMMA_PAIR", "1"))  # 1 = CTA-pair kernel, 0 = single-CTA kernel
+ops.set_tuning(0, WHICH)
 def run(tag, fn):
     for _ in range(3): fn()
     torch.cuda.synchronize()
@@ -12,7 +14,7 @@ def run(tag, fn):
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     print("   event ms", e0.elapsed_time(e1))
     buf = np.zeros(148 * 16 * 8, dtype=np.int64)
-    lib().gte_umma_debug_times(buf.ctypes.data_as(ctypes.c_void_p), buf.size)
+    lib().gte_umma_debug_times(WHICH, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
     t = buf.reshape(148, 16, 8)
     print("==", tag)
     span = (t[:, :, 3].max(axis=1) - t[:, 0, 7])

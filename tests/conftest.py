@@ -50,3 +50,17 @@ def rel_err(a, b):
 
 # fp32 tolerance of the path (BASELINE.json north_star: logits and gradients within 1e-5 relative)
 TOL = 1e-5
+
+
+@pytest.fixture(params=["pair", "single"])
+def umma_kernel(request):
+    """Runs a tensor-core test twice: on the CTA-pair kernels (tcgen05 cta_group::2, the product path) and on the
+    single-CTA kernels (kept for batches of one row tile and as the A/B reference)."""
+    from gnn_tableextraction_b200 import _lib, ops
+
+    v = 1 if request.param == "pair" else 0
+    ops.set_tuning(_lib.GTE_TUNE_UMMA_PAIR, v)
+    ops.set_tuning(_lib.GTE_TUNE_DW_PAIR, v)
+    yield request.param
+    ops.set_tuning(_lib.GTE_TUNE_UMMA_PAIR, 1)
+    ops.set_tuning(_lib.GTE_TUNE_DW_PAIR, 1)

@@ -327,7 +327,7 @@ def _log_err(tag, err):
 @pytest.mark.parametrize("n,fin,fo,ln,relu,two", [(1000, 218, 218, True, True, True), (129, 64, 64, False, False, True),
                                                   (5000, 100, 130, True, False, True), (128, 32, 16, False, True, False),
                                                   (3001, 256, 256, True, True, True), (40000, 218, 218, True, True, True)])
-def test_umma_linear_fwd_3xtf32(n, fin, fo, ln, relu, two):
+def test_umma_linear_fwd_3xtf32(n, fin, fo, ln, relu, two, umma_kernel):
     gen = torch.Generator().manual_seed(n)
     x1 = torch.randn(n, fin, generator=gen)
     x2 = torch.randn(n, fin, generator=gen) * 3 if two else None
@@ -349,13 +349,17 @@ def test_umma_linear_fwd_3xtf32(n, fin, fo, ln, relu, two):
     zf = ops.linear_fwd(_padded(x1), _padded(x2) if two else None, W.to(DEV), b.to(DEV))
     _log_err(f"fwd n={n} fin={fin} fo={fo} ln={ln}: umma_z={ez:.2e} umma_y={ey:.2e} ffma_z", rel_err(zf, z64))
     assert ez < 3e-6 and ey < 5e-6
+    if ln or relu:  # inference form: no z stores, same y bits
+        z2, y2, _, _ = ops.umma_linear_fwd(_padded(x1), _padded(x2) if two else None, fin, pack, b.to(DEV), fo,
+                                           gamma=gamma.to(DEV), beta=beta.to(DEV), relu=relu, fuse_ln=ln, want_z=False)
+        assert z2 is None and torch.equal(y2, y)
     if ln:
         assert rel_err(mean, z64.mean(1)) < 3e-6
         assert rel_err(rstd, 1.0 / torch.sqrt(z64.var(1, unbiased=False) + 1e-5)) < 3e-6
 
 
 @pytest.mark.parametrize("n,fin,fo", [(1000, 218, 218), (4097, 64, 96), (257, 256, 16)])
-def test_umma_linear_bwd_data_3xtf32(n, fin, fo):
+def test_umma_linear_bwd_data_3xtf32(n, fin, fo, umma_kernel):
     gen = torch.Generator().manual_seed(n + 1)
     dz = torch.randn(n, fo, generator=gen)
     W = (torch.rand(fo, 2 * fin, generator=gen) - 0.5) * 0.2
@@ -503,7 +507,7 @@ def test_spmm_paged_packed_wrong_page_table_and_small_capacity():
 
 @pytest.mark.parametrize("n,fo,k1,k2,with_db", [(5000, 218, 218, 218, False), (2000, 218, 13, 13, True), (1000, 64, 100, 0, True),
                                                 (513, 256, 256, 256, False), (40000, 218, 218, 218, False), (7, 9, 20, 0, True)])
-def test_umma_linear_bwd_weight_3xtf32(n, fo, k1, k2, with_db):
+def test_umma_linear_bwd_weight_3xtf32(n, fo, k1, k2, with_db, umma_kernel):
     gen = torch.Generator().manual_seed(n + fo)
     dz = torch.randn(n, fo, generator=gen)
     x1 = torch.randn(n, k1, generator=gen)
@@ -527,7 +531,7 @@ def test_umma_linear_bwd_weight_3xtf32(n, fo, k1, k2, with_db):
 
 
 @pytest.mark.parametrize("n,fo,k", [(3000, 9, 218), (1025, 32, 100), (200, 5, 256 - 1)])
-def test_umma_linear_bwd_weight2_3xtf32(n, fo, k):
+def test_umma_linear_bwd_weight2_3xtf32(n, fo, k, umma_kernel):
     gen = torch.Generator().manual_seed(n)
     x = torch.randn(n, k, generator=gen)
     dz1, dz2 = torch.randn(n, fo, generator=gen), torch.randn(n, fo, generator=gen)
@@ -540,7 +544,7 @@ def test_umma_linear_bwd_weight2_3xtf32(n, fo, k):
     assert rel_err(db, dz1.double().sum(0)) < 3e-6
 
 
-def test_umma_class_layer_forms():
+def test_umma_class_layer_forms(umma_kernel):
     """stacked forward + two-segment input gradient of the project-then-aggregate class layer"""
     n, fin, fo = 3000, 218, 9
     gen = torch.Generator().manual_seed(5)
@@ -558,7 +562,7 @@ def test_umma_class_layer_forms():
     assert rel_err(dx, dz1.double() @ W.double()[:, :fin] + dz2.double() @ W.double()[:, fin:]) < 3e-6
 
 
-def test_umma_input_layer_narrow_k():
+def test_umma_input_layer_narrow_k(umma_kernel):
     """input layer on tensor cores: K = 13 + 13 (raw BBOX magnitudes up to 5e3), fused LayerNorm + ReLU"""
     pages = synth.make_pages(5)
     n = 1500

@@ -352,7 +352,7 @@ def _spy(monkeypatch, names):
 
 @pytest.mark.parametrize("name", ["gcnsage_default_2400", "gcnsage_ragged_2400"])
 @pytest.mark.parametrize("paged", [True, False])
-def test_tensor_core_route_matches_reference_golden(name, paged, monkeypatch):
+def test_tensor_core_route_matches_reference_golden(name, paged, monkeypatch, umma_kernel):
     """N = 2400 >= 1024 rows: the layers take the tcgen05 3xTF32 kernels (checked by counting their calls), and the
     vectors they are compared with were produced by the reference's own models.py (tests/golden/make_golden.py)."""
     d = load_golden(name)
@@ -398,7 +398,7 @@ def test_tensor_core_route_matches_reference_golden(name, paged, monkeypatch):
             assert rel_err(p.grad, grads[k]) < 20 * TOL, k  # one flipped unit moves a bias gradient by O(1/N)
 
 
-def test_config2_full_step_every_gradient_matches_oracle():
+def test_config2_full_step_every_gradient_matches_oracle(umma_kernel):
     """One full config-2 train step (512 pages, N = 153600, E = 1.536 M; tcgen05 route, page kernels, one-kernel batch
     assembly) replayed from the captured CUDA graph: loss, logits and EVERY gradient against the CPU oracle at 1e-5."""
     pages = synth.make_pages(512, distinct=48)
