@@ -37,6 +37,7 @@ namespace gte {
 __device__ long long g_umma_dbg[148 * 16 * 8];
 #endif
 
+constexpr int PK_PLANES = 2;  // packed weight tiles: tf32 hi, tf32 lo
 constexpr int UM_THREADS = 384;
 constexpr int UM_STAGES = 2;
 constexpr int UM_SPLIT_THREADS = 192;     // warps 2..7 split the A operand
@@ -351,7 +352,7 @@ __global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo
       const int64_t r = i % per_f;
       const int o = (int)(r / Kp), k = (int)(r % Kp);
       if (o < fo && k < fin) w = W[(int64_t)o * ldw + (int64_t)seg * fin + k];
-      dst = Pf + (int64_t)seg * 2 * per_f + r;
+      dst = Pf + (int64_t)seg * PK_PLANES * per_f + r;
       half_stride = per_f;
     } else {
       const int64_t ib = i - total_f;
@@ -359,7 +360,7 @@ __global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo
       const int64_t r = ib % per_b;
       const int j = (int)(r / Kpb), o = (int)(r % Kpb);
       if (o < fo && j < fin) w = W[(int64_t)o * ldw + (int64_t)grp * fin + j];
-      dst = Pb + (int64_t)grp * 2 * per_b + r;
+      dst = Pb + (int64_t)grp * PK_PLANES * per_b + r;
       half_stride = per_b;
     }
     const float h = tf32_rna(w);  // round-to-nearest split of the (small, packed once per step) weight operand
@@ -386,9 +387,9 @@ static PackDims pack_dims(int fo, int fin, int nseg) {
   d.Kp = round_up(fin, UM_BK);
   d.BNb = round_up(fin, 16);
   d.Kpb = round_up(fo, UM_BK);
-  d.fwd_floats = (size_t)nseg * 2 * d.BN * d.Kp;
-  d.bwd_floats = (size_t)nseg * 2 * d.BNb * d.Kpb;
-  d.stacked_floats = (fo <= 16 && nseg == 2) ? (size_t)2 * 32 * d.Kp : 0;
+  d.fwd_floats = (size_t)nseg * PK_PLANES * d.BN * d.Kp;
+  d.bwd_floats = (size_t)nseg * PK_PLANES * d.BNb * d.Kpb;
+  d.stacked_floats = (fo <= 16 && nseg == 2) ? (size_t)PK_PLANES * 32 * d.Kp : 0;
   return d;
 }
 
@@ -487,7 +488,7 @@ int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, 
   if (!gte_umma_supported(fo, fin)) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_pack_weights: fo=%d fin=%d unsupported", fo, fin);
   GTE_CHECK_ARG(aligned16(pack), "gte_umma_pack_weights: pack buffer must be 16-byte aligned");
   PackDims d = pack_dims(fo, fin, nseg);
-  const int64_t total = (int64_t)nseg * ((int64_t)d.BN * d.Kp + (int64_t)d.BNb * d.Kpb) + (int64_t)d.stacked_floats / 2;
+  const int64_t total = (int64_t)nseg * ((int64_t)d.BN * d.Kp + (int64_t)d.BNb * d.Kpb) + (int64_t)d.stacked_floats / PK_PLANES;
   k_umma_pack<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
       W, ldw, fo, fin, nseg, pack, d.BN, d.Kp, pack + d.fwd_floats, d.BNb, d.Kpb,
       d.stacked_floats ? pack + d.fwd_floats + d.bwd_floats : nullptr);
@@ -522,8 +523,8 @@ int gte_umma_linear_fwd(const float* x1, int64_t ldx1, const float* x2, int64_t 
     a.kblocks[s] = d.Kp / UM_BK;
     int rc = make_map(&a.tmA[s], xs[s], n, fin, lds[s], UM_BM);
     if (rc) return rc;
-    a.bhi[0][s] = pack + (size_t)s * 2 * per;
-    a.blo[0][s] = pack + (size_t)s * 2 * per + per;
+    a.bhi[0][s] = pack + (size_t)s * PK_PLANES * per;
+    a.blo[0][s] = a.bhi[0][s] + per;
   }
   a.b_cols = d.Kp;
   a.out[0] = z;
@@ -563,8 +564,8 @@ int gte_umma_linear_bwd_data(const float* dz, int64_t lddz, int32_t fo, const fl
   if (rc) return rc;
   const size_t per = (size_t)d.BNb * d.Kpb;
   for (int gq = 0; gq < nseg; ++gq) {
-    a.bhi[gq][0] = pb + (size_t)gq * 2 * per;
-    a.blo[gq][0] = pb + (size_t)gq * 2 * per + per;
+    a.bhi[gq][0] = pb + (size_t)gq * PK_PLANES * per;
+    a.blo[gq][0] = a.bhi[gq][0] + per;
   }
   a.b_cols = d.Kpb;
   a.out[0] = dx1;
@@ -631,8 +632,8 @@ int gte_umma_linear_bwd_data2(const float* dz1, int64_t lddz1, const float* dz2,
     a.kblocks[s] = d.Kpb / UM_BK;
     int rc = make_map(&a.tmA[s], dzs[s], n, fo, lds[s], UM_BM);
     if (rc) return rc;
-    a.bhi[0][s] = pb + (size_t)s * 2 * per;
-    a.blo[0][s] = pb + (size_t)s * 2 * per + per;
+    a.bhi[0][s] = pb + (size_t)s * PK_PLANES * per;
+    a.blo[0][s] = a.bhi[0][s] + per;
   }
   a.b_cols = d.Kpb;
   a.out[0] = dx;

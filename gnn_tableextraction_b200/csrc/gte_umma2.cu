@@ -1,14 +1,19 @@
 // Tensor-core projection on CTA PAIRS (tcgen05 cta_group::2) -- the product path of gte_umma_linear_fwd /
 // _bwd_data / _fwd_stacked / _bwd_data2 whenever the batch has at least two 128-row tiles.
 //
-// Why pairs.  The 3xTF32 contraction issues three tcgen05.mma per K = 8 step, and every one of them reads its A
-// (128 x 8) and B (N x 8) operands from shared memory: 12 x (4 KB + 7 KB) = 132 KB per 32-wide k-block at N = 224,
-// on top of the TMA writes (72 KB) and the operand split (48 KB) -- 252 KB per k-block against a shared-memory
-// pipe of 128 B/clk, i.e. ~1970 clocks for 1344 clocks of tensor work.  The single-CTA kernel (gte_umma.cu) measured
-// ~2140 clocks per k-block: it is bound by shared-memory bandwidth, not by the tensor pipe.  A CTA pair runs ONE
-// M = 256 MMA on two SMs; each SM stages only HALF of the weight tile (the hardware shares the halves), and the
-// operand split writes only the low part (the tensor core truncates the raw fp32 word to tf32 by itself):
-//     TMA 44 KB + split 32 KB + MMA reads 12 x 7.5 KB = 166 KB  ->  ~1300 clocks per k-block  <  1344 (tensor pipe).
+// Why pairs: each SM stages only HALF of the weight tile (the hardware shares the halves of a cta_group::2 MMA), and the
+// operand split writes only the low part (the tensor core truncates the raw fp32 word to tf32 by itself).
+//
+// What bounds it (role timestamps, scripts/umma_trace.py, profiles/r02_umma_pair_experiments.md): NOT the tensor pipe
+// (issuing one of the three MMAs changes nothing; the 3x pattern alone runs at 1350-1500 clocks per k-block) but the
+// SM <-> L2 traffic: per 128-row tile 616 KB of operand tiles come in (224 KB activations + 392 KB weight tiles, which do
+// not fit in shared memory next to the operand ring and are re-read per tile) and 229 KB of z / y go out, ~1 GB per
+// launch at config 2 against ~550 MB of HBM traffic.  Variants measured and NOT kept (same results, slower or equal):
+// weight tile staged as one fp32 plane with the low part derived on chip (-23 % bytes, but the split then sits on the
+// critical path of a 3-stage ring: 1100 clocks per k-block); epilogue draining its row slice into registers
+// (setmaxnreg 56/200) to overlap the next tile's MMAs (the stores then contend with the operand loads: +8 k clocks on
+// the MMA phase for 11 k saved); thread-per-row 256-bit global stores instead of TMA stores (2x slower: every warp
+// instruction touches 32 lines).
 //
 // Per CTA, 14 warps:
 //   warp 0          TMA producer: raw A tile [128 x 32] of its own row tile + its half of W_hi / W_lo

@@ -135,7 +135,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Warp-group register re-allocation (all four warps of a warp group execute it together)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ------------------------------------------------------------ CTA pairs (cta_group::2) ----
 // Two CTAs of one cluster (two SMs of a TPC) run ONE tcgen05.mma: each holds 128 rows of A and half of the B rows in
@@ -227,6 +242,15 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
 }
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// round-to-nearest (ties away from zero) to tf32 with two integer ops: adds half an ulp of the 10-bit mantissa and
+// clears the 13 low bits -- same result as cvt.rna.tf32.f32 for finite values, at full ALU rate
+__device__ __forceinline__ float tf32_rna_fast(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+// 256-bit global store (one full 32-byte sector per thread)
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));

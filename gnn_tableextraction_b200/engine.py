@@ -181,6 +181,14 @@ class SageTrainer:
             logits, _ = self.forward(g, keep_ctx=False)
         return logits
 
+    def _predict_impl(self, g: PageGraphBatch, labels: Optional[torch.Tensor]):
+        """forward (nothing saved for a backward pass) + argmax + per-page correct counts, all on the device"""
+        pages = g.pages()
+        if pages is None:
+            raise GteError("captured predict pass needs a page table (batch_num_nodes / batch_num_edges)")
+        logits, _ = self.forward(g, keep_ctx=False)
+        return ops.page_predictions(logits, pages[0], pages[1], labels)
+
     @torch.no_grad()
     def predict_pages(self, g: PageGraphBatch, labels: Optional[torch.Tensor] = None):
         """The predict loop of model_predict.py:130-154 for a whole batch of pages in one pass:
@@ -205,13 +213,23 @@ class SageTrainer:
         return preds, acc
 
     # ----------------------------------------------------- CUDA graphs -----
-    def capture(self, host_batch: Dict[str, torch.Tensor], split: Optional[bool] = None):
+    def capture_predict(self, host_batch: Dict[str, torch.Tensor]):
+        """Capture the batched predict pass of model_predict.py:130-154 (format build + forward without saved
+        activations + argmax + per-page correct counts) for batches of this shape.  Feed batches with ``load_batch`` /
+        ``prefetch_batch``; ``replay()`` / ``replay_prefetched()`` then return ``(preds int32 [N], page_correct int32 [P])``
+        -- static device tensors of the input set that ran, valid until that set runs again."""
+        return self.capture(host_batch, split=False, mode="predict")
+
+    def capture(self, host_batch: Dict[str, torch.Tensor], split: Optional[bool] = None, mode: str = "train"):
         """Capture the whole step (format build + forward + loss + backward +
         optimiser) for batches with exactly this node / edge count.  Later
         batches are fed with ``load_batch`` + ``replay``.  ``split`` (default: data-parallel
         runs) captures the kernels in one graph and leaves the all-reduce and Adam outside it."""
         if split is None:
             split = self.world > 1
+        if mode not in ("train", "predict"):
+            raise GteError(f"capture: unknown mode {mode}")
+        self._mode = mode
         dev = self.device
         n, e = int(host_batch["num_nodes"]), int(host_batch["src"].numel())
         f = int(host_batch["feat"].shape[1])
@@ -245,7 +263,10 @@ class SageTrainer:
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
             for _ in range(2):
-                self._step_impl(self._static_graph(st), st["label"])
+                if mode == "train":
+                    self._step_impl(self._static_graph(st), st["label"])
+                else:
+                    self._predict_impl(self._static_graph(st), st["label"])
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self._check_static_structure(st)
@@ -315,7 +336,9 @@ class SageTrainer:
         graph = torch.cuda.CUDAGraph()
         kw = {} if pool is None else {"pool": pool}
         with torch.cuda.graph(graph, **kw):
-            if self._split:
+            if getattr(self, "_mode", "train") == "predict":
+                st["preds"], st["correct"] = self._predict_impl(self._static_graph(st), st["label"])
+            elif self._split:
                 g = self._static_graph(st)
                 logits, ctxs = self._stage_forward(g, st["label"])
                 self._stage_backward(g, st["label"], logits, ctxs)
@@ -341,9 +364,15 @@ class SageTrainer:
         else:
             graph.replay()
 
-    def replay(self) -> torch.Tensor:
-        self._replay_graphs()
+    def _outputs(self, which: int):
+        if getattr(self, "_mode", "train") == "predict":
+            st = self._statics[which]
+            return st["preds"], st["correct"]
         return self.stats
+
+    def replay(self):
+        self._replay_graphs()
+        return self._outputs(0)
 
     # -- pipelined input: the host->device copy of batch i+1 overlaps the step of batch i ----------------------
     def prefetch_batch(self, host_batch: Dict[str, torch.Tensor]):
@@ -356,8 +385,9 @@ class SageTrainer:
         if getattr(self, "_stage_sets", None) is None:
             torch.cuda.synchronize(self.device)
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            second = {k: torch.empty_like(v) for k, v in self._static.items()}
-            for k, v in self._static.items():
+            inputs = {k: v for k, v in self._static.items() if k not in ("preds", "correct")}
+            second = {k: torch.empty_like(v) for k, v in inputs.items()}
+            for k, v in inputs.items():
                 second[k].copy_(v)  # valid contents for the capture below (capturing runs nothing)
             self._loaded_layout[1] = self._loaded_layout[0]
             pool = (self._graph[0] if isinstance(self._graph, tuple) else self._graph).pool()
@@ -386,9 +416,9 @@ class SageTrainer:
         if getattr(self, "_stage_sets", None) is None and which != 0:
             raise GteError("replay_set: the second input set exists after the first prefetch_batch()")
         self._replay_graphs(which)
-        return self.stats
+        return self._outputs(which)
 
-    def replay_prefetched(self) -> torch.Tensor:
+    def replay_prefetched(self):
         """Run one captured step on the oldest prefetched batch."""
         if getattr(self, "_stage_sets", None) is None or self._stage_r >= self._stage_w:
             raise GteError("replay_prefetched: no prefetched batch")
@@ -398,4 +428,4 @@ class SageTrainer:
         self._replay_graphs(i)
         self._stage_free[i].record(cur)
         self._stage_r += 1
-        return self.stats
+        return self._outputs(i)

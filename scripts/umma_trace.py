@@ -13,9 +13,10 @@ def run(tag, fn):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     print("   event ms", e0.elapsed_time(e1))
-    buf = np.zeros(148 * 16 * 8, dtype=np.int64)
+    slots = 8
+    buf = np.zeros(148 * 16 * slots, dtype=np.int64)
     lib().gte_umma_debug_times(WHICH, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
-    t = buf.reshape(148, 16, 8)
+    t = buf.reshape(148, 16, slots)
     print("==", tag)
     span = (t[:, :, 3].max(axis=1) - t[:, 0, 7])
     print("   per-CTA span cycles: median", int(np.median(span)), "max", int(span.max()), " tile period (cta0):", [int(t[0, i + 1, 3] - t[0, i, 3]) for i in range(6)])
@@ -24,7 +25,8 @@ def run(tag, fn):
         for tile in range(1, 5):
             r = t[cta, tile] - base
             print(f" cta {cta} tile {tile}: prod_first_tma {r[7]:7d} | mma wait_tempty {r[4]:7d}->{r[5]:7d} issued {r[6]:7d} | epi wait {r[0]:7d} tfull {r[1]:7d} stats {r[2]:7d} done {r[3]:7d}"
-                  f"   [mma {r[6]-r[5]:6d}  epi_stats {r[2]-r[1]:6d} epi_store {r[3]-r[2]:6d}]")
+                  f"   [mma {r[6]-r[5]:6d}  epi_stats {r[2]-r[1]:6d} epi_store {r[3]-r[2]:6d}]"
+                  + (f" [sums {r[8]-r[2]:6d} bar {r[9]-r[8]:6d} merge {r[10]-r[9]:6d} norm+store {r[3]-r[10]:6d}]" if slots == 16 and r[8] > 0 else ""))
 n = 153600
 h = ops.empty_padded(n, 218, DEV); h.normal_()
 ah = ops.empty_padded(n, 218, DEV); ah.normal_()

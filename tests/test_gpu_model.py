@@ -395,7 +395,9 @@ def test_tensor_core_route_matches_reference_golden(name, paged, monkeypatch, um
         torch.nn.CrossEntropyLoss(weight=None if cw is None else cw.cpu())(ref, og.ndata["label"].long()).backward()
         for (k, p), (_, q) in zip(model.named_parameters(), om.named_parameters()):
             assert rel_err(p.grad, q.grad) < TOL, k
-            assert rel_err(p.grad, grads[k]) < 20 * TOL, k  # one flipped unit moves a bias gradient by O(1/N)
+            # sanity only: one flipped unit switches that node's contribution to its column of the weight gradients
+            # on or off, i.e. moves them by O(1/N) of the batch sum (N = 2400) -- far above TOL, far below a real error
+            assert rel_err(p.grad, grads[k]) < 1e-2, k
 
 
 def test_config2_full_step_every_gradient_matches_oracle(umma_kernel):
@@ -484,8 +486,12 @@ def test_bad_node_ids_are_flagged_and_memory_safe():
     out = cm(g)  # must not fault
     torch.cuda.synchronize()
     assert out.shape == (40, 9)
-    with pytest.raises(gte.GteError, match="outside"):
+    with pytest.raises(gte.GteError, match="outside|leaves its page"):  # one "page" of 40 nodes: either builder reports it
         g.validate()
+    from gnn_tableextraction_b200 import ops
+    bad = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.csx_from_coo(t(p.dst, torch.int32), t(p.src, torch.int32), 40, bad=bad)  # the generic builder's own flag
+    assert int(bad.item()) == 1
     ok = gte.PageGraphBatch.from_pages([p], DEV)
     cm(ok)
     ok.validate()
@@ -498,3 +504,26 @@ def test_bad_node_ids_are_flagged_and_memory_safe():
     torch.cuda.synchronize()
     with pytest.raises(gte.GteError, match="leaves its page"):
         gb.validate()
+
+
+def test_captured_predict_pass_equals_eager_predict_pages():
+    """config 3's pipeline: the captured predict pass (two static input sets, H2D of the next batch overlapping) returns
+    the predictions / per-page correct counts of SageTrainer.predict_pages for every batch, ragged pages included"""
+    pages = synth.make_pages(6, ragged=True, k=6)
+    ha, hb = batch_pages_host(pages), batch_pages_host([pages[i] for i in (2, 5, 0, 3, 1, 4)])
+    _, cm = _oracle_and_cuda_models(41, (13, 64, 9, 3))
+    cm.eval()
+    tr = gte.SageTrainer(cm)
+    tr.capture_predict(ha)
+    tr.prefetch_batch(ha)
+    seq = (ha, hb, ha, hb)
+    for i, hbatch in enumerate(seq):
+        preds, corr = tr.replay_prefetched()
+        preds, corr = preds.clone(), corr.clone()
+        if i + 1 < len(seq):
+            tr.prefetch_batch(seq[i + 1])
+        g = gte.PageGraphBatch.from_host(hbatch, DEV)
+        p2, acc = tr.predict_pages(g, g.ndata["label"])  # eager pass of the same trainer
+        assert torch.equal(preds, p2), i
+        sizes = torch.tensor(hbatch["batch_num_nodes"], dtype=torch.float64, device=DEV)
+        assert torch.equal(corr[:6].to(torch.float64) / sizes, acc), i
