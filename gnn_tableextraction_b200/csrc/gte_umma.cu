@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
           }
         }
       };
+#ifdef GTE_EXPERIMENTS
+      if (P.dbg & 32) pf_tile = total_tiles;  // timing experiment: no L2 prefetch
+#endif
       for (int i = 0; i < UM_PREFETCH; ++i) pf_step();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / P.ngroups, grp = tile % P.ngroups;
@@ -647,6 +650,7 @@ int gte_umma_debug_times(int32_t which, int64_t* out_host, int32_t count) {
   if (!out_host || count <= 0 || count > 148 * 16 * 8) return fail(GTE_ERR_INVALID, "gte_umma_debug_times: bad argument");
 #ifdef GTE_EXPERIMENTS
   if (which == 1) return umma_pair_debug_times(out_host, count);
+  if (which == 2) return umma_dw_debug_times(out_host, count);
   GTE_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_umma_dbg, (size_t)count * 8), "gte_umma_debug_times");
   return GTE_OK;
 #else

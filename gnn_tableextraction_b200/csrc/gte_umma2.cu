@@ -158,6 +158,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
           }
         }
       };
+#ifdef GTE_EXPERIMENTS
+      if (P.dbg & 32) pf_t = total;  // timing experiment: no L2 prefetch
+#endif
       for (int i = 0; i < U2_PREFETCH; ++i) pf_step();
       for (int t = cluster_id; t < total; t += nclusters) {
         const int mt = 2 * (t / P.ngroups) + (int)rank, grp = t % P.ngroups;

@@ -49,6 +49,7 @@ int launch_umma_pair(UmmaArgs& a, cudaStream_t st);
 bool umma_pair_supported(const UmmaArgs& a);
 int setup_weight_maps(UmmaArgs& a, int box_rows);  // tmBhi / tmBlo with the box the chosen kernel stages
 int umma_pair_debug_times(int64_t* out_host, int32_t count);  // GTE_EXPERIMENTS builds
+int umma_dw_debug_times(int64_t* out_host, int32_t count);    // GTE_EXPERIMENTS builds (gte_umma_dw.cu)
 
 // process-wide A/B switches behind gte_set_tuning() (gte_graph.cu)
 int tuning(int key);

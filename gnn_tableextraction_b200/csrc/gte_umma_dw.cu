@@ -11,11 +11,21 @@
 // hi = rna(x), lo = rna(x - hi)); the small cross terms (a_lo*b_hi + a_hi*b_lo) accumulate in
 // their own TMEM accumulator so that the long main chain sees as few round-toward-zero steps as possible.
 //
-// Rows are processed in chunks (512 rows = 64 MMA K-steps per accumulator) whose fp32 partial
-// tiles are written to a workspace and summed afterwards in a fixed order -- deterministic, no
-// atomics, and the in-TMEM chain stays short (tensor-core accumulation truncates).
+// Rows are processed in chunks (~512 rows = 64 MMA K-steps per accumulator, the in-TMEM chain stays short because
+// tensor-core accumulation truncates).  Every persistent CTA owns ONE (group, m-tile) output tile and walks its share
+// of the chunks in a fixed order; after each chunk it adds the accumulator to its private fp32 partial tile (plain
+// coalesced read-modify-write, L2 resident: 148 tiles of 112 KB), so a launch writes one partial per CTA instead of one
+// per chunk (r01: 145 MB of chunk partials written and read back).  A second kernel sums the <= 148 partials in a fixed
+// order -- deterministic, no atomics.
 // An all-ones column (B side) or row (A side) can be injected to obtain column sums (bias gradient)
 // from the same pass.
+//
+// Pipeline: 4 stages of 16 contraction rows (r01: 2 stages of 32 rows -- the ring was latency bound: TMA + split + MMA
+// of a stage ran almost back to back); every operand tile arrives as ONE TMA request through a 3-D blocked view of the
+// row-major matrix (r01: one request per 32-column box, 11 per stage -- the TMA unit's request rate was a bound); the
+// operand split writes only the low parts (hi = the raw fp32 word, which kind::tf32 truncates by itself) with batched
+// shared-memory loads, on twelve worker warps that also run the per-chunk epilogue (role accounting,
+// scripts/dw_trace.py: with six split warps the MMA issuer waited 40 % of the time for split operands).
 //
 // Roofline: HBM (each activation byte is read once per use) -- the MMA work is 3*2*n*M*N flops.
 #include "gte_common.cuh"
@@ -25,23 +35,36 @@
 
 namespace gte {
 
-constexpr int DW_THREADS = 384;
-constexpr int DW_KB = 32;                      // contraction rows per pipeline stage
-constexpr int DW_BOX_BYTES = DW_KB * 128;      // one TMA box: 32 rows x 32 floats
-constexpr int DW_STAGES = 2;
-constexpr int DW_SPLIT_THREADS = 192;           // warps 2..7 split the operands
-constexpr int DW_PREFETCH = 6;                 // k-blocks of L2 prefetch lookahead
+constexpr int DW_THREADS = 448;                // producer, MMA issuer, 12 worker warps
+constexpr int DW_KB = 16;                      // contraction rows per pipeline stage (two K = 8 MMA steps)
+constexpr int DW_BOX_BYTES = DW_KB * 128;      // one TMA box: 16 rows x 32 floats
+constexpr int DW_MAX_STAGES = 8;
+constexpr int DW_WORKERS = 12;                 // warps 2..13: operand split per stage + epilogue per chunk
+constexpr int DW_SPLIT_THREADS = DW_WORKERS * 32;
 constexpr int DW_MAX_BOXES = 8;
-constexpr int DW_STAGE_LD = EPI_LD;
 
-struct DwBox {
-  int32_t map;  // index into tmB
-  int32_t col;  // first column of the box in that tensor
+#ifdef GTE_EXPERIMENTS
+// per-CTA role accounting (clock64 cycles): 0 span, 1 producer waits on empty, 2 split waits on full, 3 split work,
+// 4 MMA waits on ready, 5 MMA waits on tempty, 6 epilogue waits on tfull, 7 epilogue work, 8 stages
+__device__ long long g_dw_dbg[148 * 16];
+#define DW_T0() const long long t0__ = clock64()
+#define DW_ACC(var) var += clock64() - t0__
+#else
+#define DW_T0()
+#define DW_ACC(var)
+#endif
+
+struct DwRun {      // consecutive 32-column blocks of one B tensor, consecutive boxes of the shared-memory tile
+  int32_t map;      // index into tmB
+  int32_t blk0;     // first 32-column block
+  int32_t nblk;
+  int32_t blocked;  // 1: tmB[map] is a 3-D blocked map (one request for the run), 0: 2-D boxes, one request per block
 };
 struct DwGroup {
   int32_t a;       // index into tmA
   int32_t nboxes;  // N = 32 * nboxes
-  DwBox box[DW_MAX_BOXES];
+  int32_t nruns;
+  DwRun run[2];
   int32_t pcol0;   // first column of this group's tile in the partial matrix
   int32_t ones_b_col;  // >= 0: tile column of B forced to 1 (column sums of A); -1: none
   int32_t ones_a_col;  // >= 0: column of A forced to 1 (column sums of B); -1: none
@@ -54,10 +77,11 @@ struct DwArgs {
   int32_t items_per_chunk;
   int32_t n, chunk_rows, nchunks;
   int32_t max_boxes;
-  float* partial;
-  int64_t ldp, chunk_stride;
-  int32_t dbg_lbo, dbg_sbo;  // descriptor experiment (GTE_DW_DESC)
-  int32_t dbg_mode;
+  int32_t a_blocked[2];  // tmA[i] is a 3-D blocked map (box = 4 blocks = one m-tile)
+  int32_t stages;        // operand ring depth (as many stages as fit: narrow operands get a deeper ring)
+  int32_t dbg;           // GTE_EXPERIMENTS builds
+  float* partial;        // [gridDim.x] tiles of [32 * max_boxes columns][128 rows] floats (column-major: row fastest)
+  int64_t tile_stride;   // floats per partial tile
 };
 
 __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant__ DwArgs P) {
@@ -72,31 +96,38 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
   auto sA_lo = [&](int s) { return tiles + s * stage_bytes + a_bytes; };
   auto sB_hi = [&](int s) { return tiles + s * stage_bytes + 2 * a_bytes; };
   auto sB_lo = [&](int s) { return tiles + s * stage_bytes + 2 * a_bytes + b_bytes; };
-  float* s_stage = reinterpret_cast<float*>(tiles + DW_STAGES * stage_bytes);  // [4][32][33]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * 32 * DW_STAGE_LD);
+  const int DW_STAGES = P.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + DW_STAGES * stage_bytes);
   uint64_t* bar_full = bars;
-  uint64_t* bar_ready = bars + DW_STAGES;
-  uint64_t* bar_empty = bars + 2 * DW_STAGES;
-  uint64_t* bar_tfull = bars + 3 * DW_STAGES;
+  uint64_t* bar_ready = bars + DW_MAX_STAGES;
+  uint64_t* bar_empty = bars + 2 * DW_MAX_STAGES;
+  uint64_t* bar_tfull = bars + 3 * DW_MAX_STAGES;
   uint64_t* bar_tempty = bar_tfull + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_items = P.nchunks * P.items_per_chunk;
   const int kb_per_chunk = P.chunk_rows / DW_KB;
+  // this CTA's output tile and its chunks: CTAs b, b + ipc, b + 2 ipc, ... share sub-item b % ipc and deal the chunks
+  // round robin (fixed order => reproducible partials)
+  const int ipc = P.items_per_chunk;
+  const int sub = blockIdx.x % ipc;
+  const int peers = ((int)gridDim.x - sub + ipc - 1) / ipc;  // CTAs working on this sub-item
+  const int first_chunk = blockIdx.x / ipc;
+  const DwGroup& G = P.grp[P.item_g[sub]];
+  const int mt = P.item_mt[sub];
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < DW_STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_ready[s]), DW_SPLIT_THREADS);
+      mbar_init(smem_u32(&bar_ready[s]), DW_WORKERS);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(bar_tfull), 1);
-    mbar_init(smem_u32(bar_tempty), 128);
+    mbar_init(smem_u32(bar_tempty), DW_WORKERS);
     fence_barrier_init();
-    tma_prefetch_desc(&P.tmA[0]);
-    tma_prefetch_desc(&P.tmB[0]);
+    tma_prefetch_desc(&P.tmA[G.a]);
+    for (int r = 0; r < G.nruns; ++r) tma_prefetch_desc(&P.tmB[G.run[r].map]);
   }
   if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
   tc_fence_before();
@@ -114,72 +145,83 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
 
   if (warp == 0) {
     // ================================ TMA producer ================================
+    // No L2 prefetch: both ways of doing it were measured to SLOW the kernel down at config 2 (hidden-layer dW 0.23 ms
+    // without; 0.28 ms with cp.async.bulk.prefetch requests 12 stages ahead -- they queue in the TMA unit in front of the
+    // real loads; 0.47 ms with prefetch.global.L2 from the producer warp's spare lanes).
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // L2 prefetch cursor running DW_PREFETCH k-blocks ahead of the loads
-      int pf_item = blockIdx.x, pf_kb = 0, pf_left = 0;
-      auto pf_step = [&]() {
-        if (pf_item >= total_items) return;
-        const int chunk = pf_item / P.items_per_chunk, sub = pf_item % P.items_per_chunk;
-        const DwGroup& G = P.grp[P.item_g[sub]];
-        const int mt = P.item_mt[sub];
-        const int row = chunk * P.chunk_rows + pf_kb * DW_KB;
-        for (int b = 0; b < 4; ++b) tma_prefetch_2d(&P.tmA[G.a], mt * 128 + b * 32, row);
-        for (int b = 0; b < G.nboxes; ++b) tma_prefetch_2d(&P.tmB[G.box[b].map], G.box[b].col, row);
-        if (++pf_kb >= chunk_kblocks(chunk)) {
-          pf_kb = 0;
-          pf_item += gridDim.x;
-        }
-      };
-      for (pf_left = 0; pf_left < DW_PREFETCH; ++pf_left) pf_step();
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
-        const DwGroup& G = P.grp[P.item_g[sub]];
-        const int mt = P.item_mt[sub];
+      long long w_acc = 0, n_st = 0;
+      const long long t_begin = clock64();
+      (void)w_acc; (void)n_st; (void)t_begin;
+      for (int chunk = first_chunk; chunk < P.nchunks; chunk += peers) {
         const int r0 = chunk * P.chunk_rows;
         const int nkb = chunk_kblocks(chunk);
         for (int kb = 0; kb < nkb; ++kb) {
-          pf_step();
-          mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
+          ++n_st;
+          {
+            DW_T0();
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+            DW_ACC(w_acc);
+          }
           const uint32_t fb = smem_u32(&bar_full[stage]);
           mbar_expect_tx(fb, (uint32_t)((4 + G.nboxes) * DW_BOX_BYTES));
           const int row = r0 + kb * DW_KB;
-          for (int b = 0; b < 4; ++b)
+          if (P.a_blocked[G.a]) tma_load_3d(smem_u32(sA_hi(stage)), &P.tmA[G.a], fb, 0, row, mt * 4);
+          else for (int b = 0; b < 4; ++b)
             tma_load_2d(smem_u32(sA_hi(stage) + b * DW_BOX_BYTES), &P.tmA[G.a], fb, mt * 128 + b * 32, row);
-          for (int b = 0; b < G.nboxes; ++b)
-            tma_load_2d(smem_u32(sB_hi(stage) + b * DW_BOX_BYTES), &P.tmB[G.box[b].map], fb, G.box[b].col, row);
+          int box = 0;
+          for (int r = 0; r < G.nruns; ++r) {
+            const DwRun& R = G.run[r];
+            if (R.blocked) tma_load_3d(smem_u32(sB_hi(stage) + box * DW_BOX_BYTES), &P.tmB[R.map], fb, 0, row, R.blk0);
+            else for (int b = 0; b < R.nblk; ++b)
+              tma_load_2d(smem_u32(sB_hi(stage) + (box + b) * DW_BOX_BYTES), &P.tmB[R.map], fb, (R.blk0 + b) * 32, row);
+            box += R.nblk;
+          }
           if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
         }
       }
+#ifdef GTE_EXPERIMENTS
+      if (blockIdx.x < 148) {
+        g_dw_dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
+        g_dw_dbg[blockIdx.x * 16 + 1] = w_acc;
+        g_dw_dbg[blockIdx.x * 16 + 8] = n_st;
+      }
+#endif
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
-        const DwGroup& G = P.grp[P.item_g[sub]];
-        const int BN = G.nboxes * 32;
-        // D=f32, A=B=tf32, both MN-major, N=BN, M=128
-        uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        if (P.dbg_mode == 13) idesc &= ~((1u << 15) | (1u << 16));
-        mbar_wait_backoff(smem_u32(bar_tempty), acc_phase ^ 1);
+      const int BN = G.nboxes * 32;
+      // D=f32, A=B=tf32, both MN-major, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t d_main = tmem_base, d_cross = tmem_base + 256;
+      long long w_ready = 0, w_tempty = 0;
+      (void)w_ready; (void)w_tempty;
+      for (int chunk = first_chunk; chunk < P.nchunks; chunk += peers) {
+        {
+          DW_T0();
+          mbar_wait_backoff(smem_u32(bar_tempty), acc_phase ^ 1);
+          DW_ACC(w_tempty);
+        }
         tc_fence_after();
-        const uint32_t d_main = tmem_base, d_cross = tmem_base + 256;
         const int nkb = chunk_kblocks(chunk);
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          mbar_wait(smem_u32(&bar_ready[stage]), phase);
+          {
+            DW_T0();
+            mbar_wait(smem_u32(&bar_ready[stage]), phase);
+            DW_ACC(w_ready);
+          }
           tc_fence_after();
-          const uint64_t dah = make_desc_mn_sw128_32b(smem_u32(sA_hi(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
-          const uint64_t dal = make_desc_mn_sw128_32b(smem_u32(sA_lo(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
-          const uint64_t dbh = make_desc_mn_sw128_32b(smem_u32(sB_hi(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
-          const uint64_t dbl = make_desc_mn_sw128_32b(smem_u32(sB_lo(stage)), (uint32_t)P.dbg_lbo, (uint32_t)P.dbg_sbo);
+          const uint64_t dah = make_desc_mn_sw128_32b(smem_u32(sA_hi(stage)), DW_BOX_BYTES);
+          const uint64_t dal = make_desc_mn_sw128_32b(smem_u32(sA_lo(stage)), DW_BOX_BYTES);
+          const uint64_t dbh = make_desc_mn_sw128_32b(smem_u32(sB_hi(stage)), DW_BOX_BYTES);
+          const uint64_t dbl = make_desc_mn_sw128_32b(smem_u32(sB_lo(stage)), DW_BOX_BYTES);
 #pragma unroll
-          for (int k = 0; k < (P.dbg_mode == 22 ? 0 : DW_KB / 8); ++k) {
+          for (int k = 0; k < DW_KB / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 1024) >> 4);  // next 8-row atom inside every box
             const uint32_t first = (kb | k) == 0 ? 0u : 1u;
             umma_tf32(d_cross, dal + adv, dbh + adv, idesc, first);
@@ -192,90 +234,129 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
         umma_commit(smem_u32(bar_tfull));
         acc_phase ^= 1;
       }
+#ifdef GTE_EXPERIMENTS
+      if (blockIdx.x < 148) {
+        g_dw_dbg[blockIdx.x * 16 + 4] = w_ready;
+        g_dw_dbg[blockIdx.x * 16 + 5] = w_tempty;
+      }
+#endif
     }
-  } else if (warp >= 2 && warp < 8) {
-    // ================================ operand split (6 warps: 2..7) ================
+  } else {
+    // ================================ worker warps (2..13) ========================
+    // Per stage: the operand split.  hi stays as TMA wrote it (kind::tf32 truncates the raw fp32 word by itself); only
+    // lo = rna(v - trunc(v)) is written, position preserving, so the swizzle does not matter.
+    // Per chunk: the epilogue.  The same warps add the accumulator (main + cross) to this CTA's partial tile -- the MMA
+    // issuer and the ring are idle then anyway (one accumulator pair fills TMEM), so twelve warps instead of four
+    // shorten exactly the part that cannot overlap.  Warp w may touch TMEM lanes 32 (w % 4) ..: three warps per lane
+    // quarter, which take the 32-column chunks c = j, j + 3, j + 6.  The partial tile is column major, so a warp's 32
+    // rows of one column are one 128-byte line.
     const int t = threadIdx.x - 64;
+    const int q = warp & 3, third = (warp - 2) >> 2;
     int stage = 0;
-    uint32_t phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
-      const DwGroup& G = P.grp[P.item_g[sub]];
-      const int mt = P.item_mt[sub];
+    uint32_t phase = 0, acc_phase = 0;
+    const int na4 = a_bytes / 16, nb4 = G.nboxes * DW_BOX_BYTES / 16;
+    const int ones_col = G.ones_b_col >= 0 ? G.ones_b_col : ((G.ones_a_col >= 0 && G.ones_a_col / 128 == mt) ? G.ones_a_col % 128 : -1);
+    float* const ptile = P.partial + (int64_t)blockIdx.x * P.tile_stride + q * 32 + lane;
+    bool first = true;
+    long long w_full = 0, w_work = 0, w_tfull = 0, w_epi = 0;
+    (void)w_full; (void)w_work; (void)w_tfull; (void)w_epi;
+    for (int chunk = first_chunk; chunk < P.nchunks; chunk += peers) {
       const int r0 = chunk * P.chunk_rows;
       const int nkb = chunk_kblocks(chunk);
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
-        auto split = [&](uint8_t* hi_p, uint8_t* lo_p, int nf4) {
-          float4* hi = reinterpret_cast<float4*>(hi_p);
-          float4* lo = reinterpret_cast<float4*>(lo_p);
-          if (P.dbg_mode == 20) return;  // timing experiment: no split at all
-          for (int idx = t; idx < nf4; idx += DW_SPLIT_THREADS) {
-            const float4 v = hi[idx];
-            float4 h, l;
-            if (P.dbg_mode == 21) {  // timing experiment: truncation masks instead of cvt.rna
-              h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-              l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-            } else {
-              h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-              l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-            }
-            hi[idx] = h;
-            lo[idx] = l;
-          }
-        };
-        split(sA_hi(stage), sA_lo(stage), 4 * DW_BOX_BYTES / 16);
-        split(sB_hi(stage), sB_lo(stage), G.nboxes * DW_BOX_BYTES / 16);
-        // all-ones column: element (row kk, tile column c) of an MN-major SW128 box tile
-        const int ones_col = G.ones_b_col >= 0 ? G.ones_b_col : ((G.ones_a_col >= 0 && G.ones_a_col / 128 == mt) ? G.ones_a_col % 128 : -1);
+        {
+          DW_T0();
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          DW_ACC(w_full);
+        }
+        DW_T0();
+        constexpr int PER = ((4 + DW_MAX_BOXES) * DW_BOX_BYTES / 16 + DW_SPLIT_THREADS - 1) / DW_SPLIT_THREADS;  // 4
+        float4 v[PER];
+        const float4* a_hi = reinterpret_cast<const float4*>(sA_hi(stage));
+        const float4* b_hi = reinterpret_cast<const float4*>(sB_hi(stage));
+        float4* a_lo = reinterpret_cast<float4*>(sA_lo(stage));
+        float4* b_lo = reinterpret_cast<float4*>(sB_lo(stage));
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {  // all loads first: one shared-memory round trip
+          const int idx = t + i * DW_SPLIT_THREADS;
+          if (idx < na4) v[i] = a_hi[idx];
+          else if (idx - na4 < nb4) v[i] = b_hi[idx - na4];
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int idx = t + i * DW_SPLIT_THREADS;
+          float4 l;
+          l.x = tf32_rna_fast(v[i].x - tf32_hi(v[i].x)); l.y = tf32_rna_fast(v[i].y - tf32_hi(v[i].y));
+          l.z = tf32_rna_fast(v[i].z - tf32_hi(v[i].z)); l.w = tf32_rna_fast(v[i].w - tf32_hi(v[i].w));
+          if (idx < na4) a_lo[idx] = l;
+          else if (idx - na4 < nb4) b_lo[idx - na4] = l;
+        }
         if (ones_col >= 0) {
-          asm volatile("bar.sync 1, %0;" ::"n"(DW_SPLIT_THREADS) : "memory");  // the splits above wrote the same words
+          // all-ones column: element (row kk, tile column c) of an MN-major SW128 box tile.  It is a padding column: zero
+          // filled by the 2-D maps, but whatever the row's padding holds with the 3-D blocked maps -- so hi := 1 and
+          // lo := 0 are both patched, after every splitting thread wrote its low parts.  Rows past the end of the batch are
+          // zero filled by either map and stay 0.
+          asm volatile("bar.sync 1, %0;" ::"n"(DW_SPLIT_THREADS) : "memory");
           if (t < DW_KB) {
             const int kk = t;
             if (r0 + kb * DW_KB + kk < P.n) {
-              uint8_t* tile = G.ones_b_col >= 0 ? sB_hi(stage) : sA_hi(stage);
               const int box = ones_col / 32, cin = ones_col % 32;
               const int off = box * DW_BOX_BYTES + kk * 128 + (((cin >> 3) ^ (kk & 3)) << 5) + (cin & 7) * 4;  // 32-byte chunk swizzle
-              *reinterpret_cast<float*>(tile + off) = 1.0f;
+              *reinterpret_cast<float*>((G.ones_b_col >= 0 ? sB_hi(stage) : sA_hi(stage)) + off) = 1.0f;
+              *reinterpret_cast<float*>((G.ones_b_col >= 0 ? sB_lo(stage) : sA_lo(stage)) + off) = 0.0f;
             }
           }
         }
         fence_proxy_async();
-        mbar_arrive(smem_u32(&bar_ready[stage]));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_ready[stage]));
+        DW_ACC(w_work);
         if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
       }
-    }
-  } else if (warp >= 8) {
-    // ================================ epilogue ====================================
-    const int q = warp & 3;
-    float* st = s_stage + q * 32 * DW_STAGE_LD;
-    uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int chunk = item / P.items_per_chunk, sub = item % P.items_per_chunk;
-      const DwGroup& G = P.grp[P.item_g[sub]];
-      const int mt = P.item_mt[sub];
-      mbar_wait(smem_u32(bar_tfull), acc_phase);
+      // ---- epilogue of this chunk
+      {
+        DW_T0();
+        mbar_wait(smem_u32(bar_tfull), acc_phase);
+        DW_ACC(w_tfull);
+      }
+      DW_T0();
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
-      float* outp = P.partial + (int64_t)chunk * P.chunk_stride + (int64_t)(mt * 128 + q * 32) * P.ldp + G.pcol0;
-      for (int c = 0; c < G.nboxes; ++c) {
+      for (int c = third; c < G.nboxes; c += 3) {
         uint32_t v[32], v2[32];
         tmem_ld_32x32b_x32_nowait(t_base + c * 32, v);
         tmem_ld_32x32b_x32_nowait(t_base + 256 + c * 32, v2);
+        float old[32];
+        float* const pc = ptile + (int64_t)(c * 32) * 128;
+        if (!first) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) old[j] = pc[j * 128];
+        }
         tmem_wait_ld();
-        float val[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          val[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-          if (P.dbg_mode == 10) val[j] = 1.0f;
-          if (P.dbg_mode == 11) val[j] = __uint_as_float(v[j]);
-          if (P.dbg_mode == 12) val[j] = __uint_as_float(v2[j]);
+          const float val = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+          pc[j * 128] = first ? val : old[j] + val;
         }
-        epi_store_chunk(st, val, outp + c * 32, P.ldp, 32, 32, true);  // partial tiles are 128-byte aligned
       }
+      first = false;
       tc_fence_before();
-      mbar_arrive(smem_u32(bar_tempty));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_tempty));
       acc_phase ^= 1;
+      DW_ACC(w_epi);
+    }
+#ifdef GTE_EXPERIMENTS
+    if (blockIdx.x < 148 && threadIdx.x == 64) {
+      g_dw_dbg[blockIdx.x * 16 + 2] = w_full;
+      g_dw_dbg[blockIdx.x * 16 + 3] = w_work;
+      g_dw_dbg[blockIdx.x * 16 + 6] = w_tfull;
+      g_dw_dbg[blockIdx.x * 16 + 7] = w_epi;
+    }
+#endif
+    if (first) {  // a CTA without any chunk still owns a partial tile: it must read as zero
+      for (int c = third; c < G.nboxes; c += 3)
+        for (int j = 0; j < 32; ++j) ptile[(int64_t)(c * 32 + j) * 128] = 0.f;
     }
   }
   tc_fence_before();
@@ -286,9 +367,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
   }
 }
 
-// ---- fixed-order reduction of the chunk partials into up to four rectangular destinations -------------------
+// ---- fixed-order reduction of the per-CTA partial tiles into up to four rectangular destinations ----------------
 struct DwSeg {
-  int32_t prow0, nrows, pcol0, ncols;  // rectangle of the partial matrix
+  int32_t prow0, nrows, pcol0, ncols;  // rectangle of the conceptual [m-tiles * 128, sum of group widths] result
   float* dst;
   int64_t stride_row, stride_col;      // dst[row*stride_row + col*stride_col]
 };
@@ -296,8 +377,11 @@ struct DwReduceArgs {
   DwSeg seg[4];
   int32_t nseg;
   const float* partial;
-  int64_t ldp, chunk_stride;
-  int32_t nchunks, accumulate;
+  int64_t tile_stride;
+  int32_t grid, ipc;                   // CTAs of the k_umma_dw launch, sub-items per chunk
+  int32_t item_g[4], item_mt[4];
+  int32_t grp_pcol0[2], grp_ncols[2];
+  int32_t accumulate;
 };
 
 __global__ void __launch_bounds__(RED_THREADS) k_umma_dw_reduce(const DwReduceArgs R) {
@@ -313,14 +397,25 @@ __global__ void __launch_bounds__(RED_THREADS) k_umma_dw_reduce(const DwReduceAr
     }
     i -= cnt;
   }
-  int row = 0, col = 0;
-  int64_t pidx = 0;
+  int row = 0, col = 0, nb = 0;
+  int64_t pidx = 0, stride = 0;
   if (valid) {
-    row = (int)(i / R.seg[s].ncols);
-    col = (int)(i % R.seg[s].ncols);
-    pidx = (int64_t)(R.seg[s].prow0 + row) * R.ldp + R.seg[s].pcol0 + col;
+    // rows fastest: consecutive threads read consecutive floats of the column-major partial tiles
+    col = (int)(i / R.seg[s].nrows);
+    row = (int)(i % R.seg[s].nrows);
+    const int prow = R.seg[s].prow0 + row, pcol = R.seg[s].pcol0 + col;
+    const int mt = prow >> 7, r = prow & 127;
+    int g = 0;
+    if (pcol >= R.grp_pcol0[1] && R.grp_ncols[1] > 0) g = 1;
+    const int c = pcol - R.grp_pcol0[g];
+    int sub = 0;
+    for (int k = 0; k < R.ipc; ++k)
+      if (R.item_g[k] == g && R.item_mt[k] == mt) sub = k;
+    nb = (R.grid - sub + R.ipc - 1) / R.ipc;  // CTAs sub, sub + ipc, ... hold the partials of this output tile
+    pidx = (int64_t)sub * R.tile_stride + (int64_t)c * 128 + r;
+    stride = (int64_t)R.ipc * R.tile_stride;
   }
-  float v = reduce_partials_block(R.partial, R.nchunks, R.chunk_stride, pidx, valid, red);
+  float v = reduce_partials_block(R.partial, nb, stride, pidx, valid, red);
   if ((threadIdx.x >> 5) != 0 || !valid) return;
   float* p = R.seg[s].dst + row * R.seg[s].stride_row + col * R.seg[s].stride_col;
   if (R.accumulate) v += *p;
@@ -328,47 +423,31 @@ __global__ void __launch_bounds__(RED_THREADS) k_umma_dw_reduce(const DwReduceAr
 }
 
 constexpr int DW_CHUNK_ROWS_DEFAULT = 512;
-constexpr int DW_MIN_CHUNK_ROWS = 384;          // smallest chunk dw_launch may choose: bounds the workspace
-// rows per accumulation chunk (GTE_DW_CHUNK overrides for experiments; multiple of 32)
-static int dw_chunk_rows() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("GTE_DW_CHUNK");
-    v = e ? atoi(e) : DW_CHUNK_ROWS_DEFAULT;
-    if (v < 32 || v % 32) v = DW_CHUNK_ROWS_DEFAULT;
-  }
-  return v;
-}
-#define DW_CHUNK_ROWS dw_chunk_rows()
 
-static size_t dw_smem_bytes(int max_boxes) {
-  return 1024 + (size_t)DW_STAGES * (2 * 4 * DW_BOX_BYTES + 2 * (size_t)max_boxes * DW_BOX_BYTES) + 4 * 32 * DW_STAGE_LD * 4 +
-         (3 * DW_STAGES + 2) * 8 + 16;
+static size_t dw_smem_bytes(int max_boxes, int stages) {
+  return 1024 + (size_t)stages * (2 * 4 * DW_BOX_BYTES + 2 * (size_t)max_boxes * DW_BOX_BYTES) + (3 * DW_MAX_STAGES + 2) * 8 + 16;
 }
+
+// partial tiles: one per CTA of the (at most sm_count) persistent grid
+static size_t dw_workspace_bytes(int max_boxes) { return (size_t)sm_count() * 32 * max_boxes * 128 * 4 + 256; }
 
 static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
-  const size_t smem = dw_smem_bytes(a.max_boxes);
+  a.stages = DW_MAX_STAGES;
+  while (a.stages > 2 && dw_smem_bytes(a.max_boxes, a.stages) > 227 * 1024) --a.stages;
+  const size_t smem = dw_smem_bytes(a.max_boxes, a.stages);
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_dw), smem, "k_umma_dw")) return rc;
-  a.dbg_lbo = DW_BOX_BYTES;
-  a.dbg_sbo = 512;
-  a.dbg_mode = 0;
-  if (const char* e = getenv("GTE_DW_MODE")) a.dbg_mode = atoi(e);
-  if (const char* e = getenv("GTE_DW_DESC")) {
-    if (atoi(e) == 1) { a.dbg_lbo = 512; a.dbg_sbo = DW_BOX_BYTES; }
-    if (atoi(e) == 2) { a.dbg_lbo = DW_BOX_BYTES; a.dbg_sbo = DW_BOX_BYTES; }
-    if (atoi(e) == 3) { a.dbg_lbo = DW_BOX_BYTES; a.dbg_sbo = 1024; }
-  }
-  // Rows per accumulation chunk: 12..20 k-blocks (384..640 rows; the accuracy experiments behind the default of 16
-  // hold for this whole range), chosen so that the persistent CTAs finish together: cost = rounds * k-blocks with
-  // rounds = ceil(chunks * items_per_chunk / SMs).  N = 153600, 4 items per chunk: 19 k-blocks -> 7 rounds (133)
-  // instead of 16 -> 9 rounds (144).
-  if (a.n > 0 && a.nchunks > 0 && !getenv("GTE_DW_CHUNK")) {
-    const int sms = sm_count();
+  // Rows per accumulation chunk: 384..640 rows (the accuracy experiments behind the default of 512 hold for this whole
+  // range), chosen so that the persistent CTAs finish together: every sub-item is shared by grid / ipc CTAs that deal
+  // its chunks round robin, cost = rounds * k-blocks with rounds = ceil(chunks / (grid / ipc)).
+  const int sms = sm_count();
+  int grid = sms;
+  if (a.n > 0) {
+    const int lanes = sms / a.items_per_chunk > 0 ? sms / a.items_per_chunk : 1;
     int best_kb = DW_CHUNK_ROWS_DEFAULT / DW_KB;
     int64_t best_cost = -1;
-    for (int kb = DW_MIN_CHUNK_ROWS / DW_KB; kb <= 20; ++kb) {
+    for (int kb = 384 / DW_KB; kb <= 640 / DW_KB; ++kb) {
       const int64_t chunks = ceil_div64(a.n, (int64_t)kb * DW_KB);
-      const int64_t rounds = ceil_div64(chunks * a.items_per_chunk, sms);
+      const int64_t rounds = ceil_div64(chunks, lanes);
       const int64_t cost = rounds * kb;
       if (best_cost < 0 || cost < best_cost) {
         best_cost = cost;
@@ -377,11 +456,27 @@ static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
     }
     a.chunk_rows = best_kb * DW_KB;
     a.nchunks = (int)ceil_div64(a.n, a.chunk_rows);
-    r.nchunks = a.nchunks;
+    const int64_t items = (int64_t)a.nchunks * a.items_per_chunk;
+    if (grid > items) grid = (int)items;
+  } else {
+    a.nchunks = 0;
+    grid = 0;
   }
-  const int items = a.nchunks * a.items_per_chunk;
-  int grid = sm_count();
-  if (grid > items) grid = items;
+#ifdef GTE_EXPERIMENTS
+  if (const char* e = getenv("GTE_DW_DBG")) a.dbg = atoi(e);
+#endif
+  a.tile_stride = (int64_t)32 * a.max_boxes * 128;
+  r.tile_stride = a.tile_stride;
+  r.grid = grid;
+  r.ipc = a.items_per_chunk;
+  for (int k = 0; k < 4; ++k) {
+    r.item_g[k] = a.item_g[k];
+    r.item_mt[k] = a.item_mt[k];
+  }
+  for (int g = 0; g < 2; ++g) {
+    r.grp_pcol0[g] = a.grp[g].pcol0;
+    r.grp_ncols[g] = a.grp[g].nboxes * 32;
+  }
   if (grid >= 1) {
     k_umma_dw<<<grid, DW_THREADS, smem, st>>>(a);
     GTE_CHECK_LAUNCH("k_umma_dw");
@@ -395,7 +490,33 @@ static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
   return GTE_OK;
 }
 
+int umma_dw_debug_times(int64_t* out_host, int32_t count) {
+#ifdef GTE_EXPERIMENTS
+  if (count > 148 * 16) count = 148 * 16;
+  GTE_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_dw_dbg, (size_t)count * 8), "gte_umma_debug_times");
+  return GTE_OK;
+#else
+  (void)out_host;
+  (void)count;
+  return fail(GTE_ERR_UNSUPPORTED, "built without -DGTE_EXPERIMENTS");
+#endif
+}
+
 static int boxes_of(int k) { return (k + 31) / 32; }
+
+// Operand map: the 3-D blocked view (one TMA request per run of 32-column blocks) when every block lies inside the row's
+// leading dimension, 2-D boxes (one request per block, columns past `cols` zero filled) otherwise.
+static int dw_make_map(CUtensorMap* m, int32_t* blocked, const float* p, int64_t rows, int64_t cols, int64_t ld, int box_blocks) {
+  *blocked = (box_blocks > 1 && ld >= 32 * ((cols + 31) / 32)) ? 1 : 0;
+#ifdef GTE_EXPERIMENTS
+  if (const char* e = getenv("GTE_DW_DBG")) if (atoi(e) & 2) *blocked = 0;
+#endif
+  if (*blocked) {
+    if (make_tmap_3d_blocks(m, p, rows, cols, ld, DW_KB, box_blocks, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) == GTE_OK) return GTE_OK;
+    *blocked = 0;  // a driver that refuses the overlapping strides: plain boxes
+  }
+  return make_tmap_2d(m, p, rows, cols, ld, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
 
 static bool tma_ok(const float* p, int64_t ld) { return p == nullptr || (aligned16(p) && ld % 4 == 0); }
 
@@ -412,10 +533,9 @@ int gte_umma_bwd_weight_supported(int32_t fo, int32_t k1, int32_t k2) {
 
 size_t gte_umma_bwd_weight_workspace_bytes(int32_t n, int32_t fo, int32_t k1, int32_t k2) {
   if (!gte_umma_bwd_weight_supported(fo, k1, k2) || n < 0) return 0;
-  const int64_t nchunks = ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS < DW_MIN_CHUNK_ROWS ? DW_CHUNK_ROWS : DW_MIN_CHUNK_ROWS);
-  const int64_t rows = ceil_div64(fo, 128) * 128;
-  const int64_t ldp = 32 * (boxes_of(k1) + boxes_of(k2));
-  return (size_t)(nchunks * rows * ldp * 4 + 256);
+  const int nb1 = boxes_of(k1), nb2 = boxes_of(k2);
+  const int mb = nb1 + nb2 <= DW_MAX_BOXES ? nb1 + nb2 : (nb1 > nb2 ? nb1 : nb2);
+  return dw_workspace_bytes(mb);  // one partial tile per persistent CTA, whatever n is
 }
 
 int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const float* x1, int64_t ldx1, int32_t k1,
@@ -435,19 +555,16 @@ int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const 
   DwArgs a{};
   DwReduceArgs r{};
   a.n = n;
-  a.chunk_rows = DW_CHUNK_ROWS;
-  a.nchunks = (int)ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS);
   const int mtiles = (fo + 127) / 128;
-  a.ldp = 32 * (nb1 + nb2);
-  a.chunk_stride = (int64_t)mtiles * 128 * a.ldp;
   a.partial = static_cast<float*>(ws);
+  int b_blocked[2] = {0, 0};
   if (n > 0) {
-    int rc = make_tmap_2d(&a.tmA[0], dz, n, fo, lddz, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    int rc = dw_make_map(&a.tmA[0], &a.a_blocked[0], dz, n, fo, lddz, 4);
     if (rc) return rc;
-    rc = make_tmap_2d(&a.tmB[0], x1, n, k1, ldx1, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = dw_make_map(&a.tmB[0], &b_blocked[0], x1, n, k1, ldx1, nb1);
     if (rc) return rc;
     if (k2 > 0) {
-      rc = make_tmap_2d(&a.tmB[1], x2, n, k2, ldx2, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      rc = dw_make_map(&a.tmB[1], &b_blocked[1], x2, n, k2, ldx2, nb2);
       if (rc) return rc;
     }
   }
@@ -455,10 +572,11 @@ int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const 
   const bool one_group = nb1 + nb2 <= DW_MAX_BOXES;
   int ngroups = 0;
   auto add_boxes = [&](DwGroup& G, int map, int nb) {
-    for (int b = 0; b < nb; ++b) G.box[G.nboxes++] = DwBox{map, b * 32};
+    G.run[G.nruns++] = DwRun{map, 0, nb, b_blocked[map]};
+    G.nboxes += nb;
   };
   DwGroup& G0 = a.grp[0];
-  G0.a = 0; G0.nboxes = 0; G0.pcol0 = 0; G0.ones_b_col = -1; G0.ones_a_col = -1;
+  G0.a = 0; G0.nboxes = 0; G0.nruns = 0; G0.pcol0 = 0; G0.ones_b_col = -1; G0.ones_a_col = -1;
   add_boxes(G0, 0, nb1);
   ngroups = 1;
   if (k2 > 0) {
@@ -466,7 +584,7 @@ int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const 
       add_boxes(G0, 1, nb2);
     } else {
       DwGroup& G1 = a.grp[1];
-      G1.a = 0; G1.nboxes = 0; G1.pcol0 = 32 * nb1; G1.ones_b_col = -1; G1.ones_a_col = -1;
+      G1.a = 0; G1.nboxes = 0; G1.nruns = 0; G1.pcol0 = 32 * nb1; G1.ones_b_col = -1; G1.ones_a_col = -1;
       add_boxes(G1, 1, nb2);
       ngroups = 2;
     }
@@ -488,15 +606,11 @@ int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const 
     }
   }
   r.partial = a.partial;
-  r.ldp = a.ldp;
-  r.chunk_stride = a.chunk_stride;
-  r.nchunks = n > 0 ? a.nchunks : 0;
   r.accumulate = accumulate;
   r.nseg = 0;
   r.seg[r.nseg++] = DwSeg{0, fo, 0, k1, dW, lddw, 1};
   if (k2 > 0) r.seg[r.nseg++] = DwSeg{0, fo, 32 * nb1, k2, dW + k1, lddw, 1};
   if (db_fused) r.seg[r.nseg++] = DwSeg{0, fo, k1, 1, db, 1, 0};
-  if (n == 0) a.nchunks = 0;
   int rc = dw_launch(a, r, as_stream(stream));
   if (rc) return rc;
   if (db && !db_fused) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight: db needs k1 %% 32 != 0 (no free padding column)");
@@ -507,9 +621,7 @@ int gte_umma_linear_bwd_weight(const float* dz, int64_t lddz, int32_t fo, const 
 //   dW[:, col1:col1+k] (+)= dz1^T x ; dW[:, col2:col2+k] (+)= dz2^T x ; db (+)= colsum(dz1)
 size_t gte_umma_bwd_weight2_workspace_bytes(int32_t n, int32_t fo, int32_t k) {
   if (n < 0 || fo < 1 || fo > 32 || k < 1 || k > 256) return 0;
-  const int64_t nchunks = ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS < DW_MIN_CHUNK_ROWS ? DW_CHUNK_ROWS : DW_MIN_CHUNK_ROWS);
-  const int64_t rows = ceil_div64(k + 1, 128) * 128;
-  return (size_t)(nchunks * rows * 64 * 4 + 256);
+  return dw_workspace_bytes(2);
 }
 
 int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz2, int64_t lddz2, int32_t fo,
@@ -531,24 +643,21 @@ int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz
   DwArgs a{};
   DwReduceArgs r{};
   a.n = n;
-  a.chunk_rows = DW_CHUNK_ROWS;
-  a.nchunks = (int)ceil_div64(n > 0 ? n : 1, DW_CHUNK_ROWS);
   const int mtiles = (k + (db_fused ? 1 : 0) + 127) / 128;
-  a.ldp = 64;
-  a.chunk_stride = (int64_t)mtiles * 128 * a.ldp;
   a.partial = static_cast<float*>(ws);
+  int b_blocked[2] = {0, 0};
   if (n > 0) {
-    int rc = make_tmap_2d(&a.tmA[0], x, n, k, ldx, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    int rc = dw_make_map(&a.tmA[0], &a.a_blocked[0], x, n, k, ldx, 4);
     if (rc) return rc;
-    rc = make_tmap_2d(&a.tmB[0], dz1, n, fo, lddz1, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = dw_make_map(&a.tmB[0], &b_blocked[0], dz1, n, fo, lddz1, 1);
     if (rc) return rc;
-    rc = make_tmap_2d(&a.tmB[1], dz2, n, fo, lddz2, 32, DW_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = dw_make_map(&a.tmB[1], &b_blocked[1], dz2, n, fo, lddz2, 1);
     if (rc) return rc;
   }
   DwGroup& G = a.grp[0];
-  G.a = 0; G.nboxes = 2; G.pcol0 = 0; G.ones_b_col = -1; G.ones_a_col = db_fused ? k : -1;
-  G.box[0] = DwBox{0, 0};
-  G.box[1] = DwBox{1, 0};
+  G.a = 0; G.nboxes = 2; G.nruns = 2; G.pcol0 = 0; G.ones_b_col = -1; G.ones_a_col = db_fused ? k : -1;
+  G.run[0] = DwRun{0, 0, 1, b_blocked[0]};
+  G.run[1] = DwRun{1, 0, 1, b_blocked[1]};
   a.max_boxes = 2;
   a.items_per_chunk = 0;
   for (int mt = 0; mt < mtiles; ++mt) {
@@ -557,15 +666,11 @@ int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz
     ++a.items_per_chunk;
   }
   r.partial = a.partial;
-  r.ldp = a.ldp;
-  r.chunk_stride = a.chunk_stride;
-  r.nchunks = n > 0 ? a.nchunks : 0;
   r.accumulate = accumulate;
   r.nseg = 0;
   r.seg[r.nseg++] = DwSeg{0, k, 0, fo, dW + col1, 1, lddw};   // out[j][o] -> dW[o][col1 + j]
   r.seg[r.nseg++] = DwSeg{0, k, 32, fo, dW + col2, 1, lddw};
   if (db_fused) r.seg[r.nseg++] = DwSeg{k, 1, 0, fo, db, 0, 1};  // ones row: column sums of dz1
-  if (n == 0) a.nchunks = 0;
   return dw_launch(a, r, as_stream(stream));
 }
 

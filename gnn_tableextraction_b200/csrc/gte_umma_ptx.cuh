@@ -65,6 +65,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // DRAM -> L2 prefetch of one tensor box (no shared memory, no barrier): issued a few k-blocks ahead so that
 // the real TMA load finds its data in L2
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
@@ -377,6 +388,27 @@ static inline int make_tmap_2d(CUtensorMap* m, const float* ptr, int64_t rows, i
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GTE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return GTE_OK;
+}
+
+// The same row-major matrix seen as [column block][row][32 columns]: ONE request then brings `box_blocks` 32-column
+// blocks of `box_rows` rows, laid out block after block in shared memory -- exactly the MN-major operand tile the
+// weight-gradient kernel builds from 2-D boxes, at a fraction of the TMA requests (the unit handles one request per
+// ~160-220 clocks, which bounded that kernel at 11 boxes per stage).  Needs ld >= 32 * ceil(cols / 32): the last block
+// is read to its full width (padding columns of the row; they only reach outputs nobody reads).  Blocks past the last
+// one are zero filled.
+static inline int make_tmap_3d_blocks(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                                      int box_blocks, CUtensorMapSwizzle swizzle) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(GTE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[3] = {32, (cuuint64_t)rows, (cuuint64_t)((cols + 31) / 32)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_blocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GTE_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
   return GTE_OK;
 }
 

@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(128, 1) k_rate(int N, int mode, int iters, lon
   if (warp == 1 && lane == 0 && rank == 0) {
     const int M = PAIR ? 256 : 128;
     const uint32_t fmt = (mode == 2) ? 1u : 2u;  // bf16 : tf32
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    if (mode == 6 || mode == 7) idesc |= (1u << 15) | (1u << 16);  // both operands MN-major
     const int brows = PAIR ? N / 2 : N;
     // stage s: A_hi @ s*64K, A_lo @ +16K, B_hi @ +32K, B_lo @ +32K + brows*128
     auto desc = [&](int s, int which) {
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(128, 1) k_rate(int N, int mode, int iters, lon
       if (which == 1) off += 16 * 1024;
       if (which == 2) off += 32 * 1024;
       if (which == 3) off += 32 * 1024 + brows * 128;
+      if (mode == 6 || mode == 7) return make_desc_mn_sw128_32b(smem_u32(base + off), 2048);  // 16-row boxes
       return make_desc_k_sw128(smem_u32(base + off));
     };
     const long long t0 = clock64();
@@ -79,6 +81,12 @@ __global__ void __launch_bounds__(128, 1) k_rate(int N, int mode, int iters, lon
               else { umma_tf32(tm + 256, dal + a2, dbh + a2, idesc, 1u); umma_tf32(tm + 256, dah + a2, dbl + a2, idesc, 1u); }
             }
           }
+        } else if (mode == 6) {  // MN-major operands (weight-gradient kernel), 3x pattern; K step = 1024 B
+          const uint64_t a6 = (uint64_t)(((k & 1) * 1024) >> 4);
+          if (PAIR) { umma_tf32_pair(tm + 256, dal + a6, dbh + a6, idesc, 1u); umma_tf32_pair(tm + 256, dah + a6, dbl + a6, idesc, 1u); umma_tf32_pair(tm, dah + a6, dbh + a6, idesc, 1u); }
+          else { umma_tf32(tm + 256, dal + a6, dbh + a6, idesc, 1u); umma_tf32(tm + 256, dah + a6, dbl + a6, idesc, 1u); umma_tf32(tm, dah + a6, dbh + a6, idesc, 1u); }
+        } else if (mode == 7) {  // MN-major, one accumulator, same operands
+          for (int j = 0; j < 3; ++j) { if (PAIR) umma_tf32_pair(tm, dah, dbh, idesc, 1u); else umma_tf32(tm, dah, dbh, idesc, 1u); }
         } else if (mode == 5) {  // same accumulator for everything, operands alternate as in the 3x pattern
           if (PAIR) {
             umma_tf32_pair(tm, dal + adv, dbh + adv, idesc, 1u); umma_tf32_pair(tm, dah + adv, dbl + adv, idesc, 1u); umma_tf32_pair(tm, dah + adv, dbh + adv, idesc, 1u);
@@ -119,10 +127,10 @@ int main() {
   cudaFuncSetAttribute(k_rate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k_rate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int iters = 200;
-  const char* names[] = {"tf32 1acc same-operands", "tf32 3x pattern", "bf16 1acc", "tf32 3x pattern, 3 stages", "tf32 3x grouped by acc", "tf32 3x operands, 1 acc"};
+  const char* names[] = {"tf32 1acc same-operands", "tf32 3x pattern", "bf16 1acc", "tf32 3x pattern, 3 stages", "tf32 3x grouped by acc", "tf32 3x operands, 1 acc", "tf32 MN-major 3x pattern", "tf32 MN-major 1acc"};
   for (int pair = 0; pair < 2; ++pair)
     for (int N : {224, 256, 64})
-      for (int mode = 0; mode < 6; ++mode) {
+      for (int mode = 0; mode < 8; ++mode) {
         if (pair && (N / 2) % 8) continue;
         cudaMemset(d, 0, 148 * 8);
         if (pair) {
