@@ -50,12 +50,12 @@ constexpr size_t U2_SMEM_MAX = 227 * 1024;
 struct U2Layout {
   uint32_t bh_bytes, stage_bytes, epi_off, par_off, stat_off, bar_off, tmem_off, total;
 };
-__host__ __device__ inline U2Layout u2_layout(int BN, int stages) {
+__host__ __device__ inline U2Layout u2_layout(int BN, int stages, int epi_bufs) {
   U2Layout L;
   L.bh_bytes = (uint32_t)(BN / 2) * 128u;                  // this CTA's half of one weight tile (hi or lo)
   L.stage_bytes = 2u * UM_A_BYTES + 2u * L.bh_bytes;       // A raw + A lo + W_hi half + W_lo half (multiples of 1024)
   L.epi_off = (uint32_t)stages * L.stage_bytes;
-  L.par_off = L.epi_off + U2_EPI_WARPS * U2_EPI_BUF;       // bias / gamma / beta
+  L.par_off = L.epi_off + U2_EPI_WARPS * U2_EPI_BUF * (uint32_t)epi_bufs;  // bias / gamma / beta
   L.stat_off = L.par_off + 3u * UM_MAX_BN * 4u;            // [parity][half][128 rows] float2 (mean, M2)
   L.bar_off = L.stat_off + 2u * 2u * 128u * 8u;
   L.tmem_off = L.bar_off + (3u * U2_MAX_STAGES + 4u) * 8u;
@@ -70,7 +70,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
   // identical carve-up in both CTAs of the pair (same kernel, same dynamic shared-memory offset): the MMA descriptors
   // and the multicast barrier offsets are valid in either CTA
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const U2Layout L = u2_layout(P.BN, P.stages);
+  const U2Layout L = u2_layout(P.BN, P.stages, P.epi_bufs);
   const int S = P.stages;
   uint8_t* const tiles = base;
   auto sA_hi_p = [&](int s) { return tiles + s * L.stage_bytes; };
@@ -251,7 +251,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
     const int ew = warp - U2_EPI_WARP0;
     const int q = warp & 3;      // TMEM lane quarter this warp may touch
     const int half = ew >> 2;    // which half of the column chunks
-    uint8_t* const stb = s_stage + ew * U2_EPI_BUF;
+    uint8_t* const stb = s_stage + ew * U2_EPI_BUF * P.epi_bufs;
+    const int nbuf = P.epi_bufs;
     const uint32_t tempty_leader = mapa_shared(smem_u32(&bar_tempty[0]), 0);
     int store_seq = 0;
     int acc = 0;
@@ -305,7 +306,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
               s2 = fmaf(d, d, s2);
             }
           }
-          if (store_z) epi_store_chunk_tma(stb, 1, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
+          if (store_z) epi_store_chunk_tma(stb, nbuf, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
         }
         float mh = 0.f, m2h = 0.f;
         if (my_n > 0.f) {
@@ -337,16 +338,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
         for (int c = c_beg; c < c_end; ++c) {
           load_chunk(c);
           epi_norm_act(x, s_gamma + c * 32, s_beta + c * 32, true, P.relu != 0, mean, rstd);
-          if (store_y) epi_store_chunk_tma(stb, 1, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
+          if (store_y) epi_store_chunk_tma(stb, nbuf, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
         }
       } else {
         if (ew == 0 && lane == 0) stamp(t, 2);
         for (int c = c_beg; c < c_end; ++c) {
           load_chunk(c);
-          if (store_z) epi_store_chunk_tma(stb, 1, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
+          if (store_z) epi_store_chunk_tma(stb, nbuf, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
           if (P.y != nullptr) {
             epi_norm_act(x, s_gamma + c * 32, s_beta + c * 32, false, P.relu != 0, 0.f, 1.f);
-            if (store_y) epi_store_chunk_tma(stb, 1, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
+            if (store_y) epi_store_chunk_tma(stb, nbuf, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
           }
         }
       }
@@ -369,23 +370,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
   }
 }
 
-static int u2_pick_stages(int BN) {
+// Ring depth and store tiles per epilogue warp.  A tile's k loop of one or two k-blocks (input layer, class-layer input
+// gradient) never has more than two stages in flight and is bound by its epilogue's TMA stores: two stages, and the
+// shared memory goes to up to four store tiles per warp.  Long k loops take the deepest ring that fits with one tile.
+static void u2_pick(int BN, int kb_total, int* stages, int* epi_bufs) {
+  *stages = 0;
+  *epi_bufs = 1;
+  if (kb_total <= 2) {
+    for (int b = 4; b >= 1; --b)
+      if (1024 + (size_t)u2_layout(BN, 2, b).total <= U2_SMEM_MAX) {
+        *stages = 2;
+        *epi_bufs = b;
+        return;
+      }
+    return;
+  }
   for (int s = U2_MAX_STAGES; s >= 2; --s)
-    if (1024 + (size_t)u2_layout(BN, s).total <= U2_SMEM_MAX) return s;
-  return 0;
+    if (1024 + (size_t)u2_layout(BN, s, 1).total <= U2_SMEM_MAX) {
+      *stages = s;
+      // leftover shared memory: a second store tile per warp
+      if (1024 + (size_t)u2_layout(BN, s, 2).total <= U2_SMEM_MAX) *epi_bufs = 2;
+      return;
+    }
 }
 
 bool umma_pair_supported(const UmmaArgs& a) {
   const int m_tiles = (a.M + UM_BM - 1) / UM_BM;
-  return a.tma_store != 0 && m_tiles >= 2 && a.BN % 16 == 0 && a.BN >= 16 && a.BN <= UM_MAX_BN && sm_count() >= 2 &&
-         u2_pick_stages(a.BN) >= 2;
+  int st = 0, eb = 0;
+  u2_pick(a.BN, 3, &st, &eb);
+  return a.tma_store != 0 && m_tiles >= 2 && a.BN % 16 == 0 && a.BN >= 16 && a.BN <= UM_MAX_BN && sm_count() >= 2 && st >= 2;
 }
 
 int launch_umma_pair(UmmaArgs& a, cudaStream_t st) {
   if (int rc = setup_weight_maps(a, a.BN / 2)) return rc;
-  a.stages = u2_pick_stages(a.BN);
   const int kb_total = a.kblocks[0] + (a.nseg > 1 ? a.kblocks[1] : 0);
-  const size_t smem = 1024 + (size_t)u2_layout(a.BN, a.stages).total;
+  int stages = 0, epi_bufs = 1;
+  u2_pick(a.BN, kb_total, &stages, &epi_bufs);
+  if (stages < 2) return fail(GTE_ERR_UNSUPPORTED, "k_umma_gemm_pair: BN=%d does not fit shared memory", a.BN);
+  a.stages = stages;
+  a.epi_bufs = epi_bufs;
+  const size_t smem = 1024 + (size_t)u2_layout(a.BN, a.stages, a.epi_bufs).total;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_gemm_pair<true>), smem, "k_umma_gemm_pair")) return rc;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_gemm_pair<false>), smem, "k_umma_gemm_pair")) return rc;
   const int m_tiles = (a.M + UM_BM - 1) / UM_BM;

@@ -181,43 +181,17 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on a barrier that may live in the peer CTA (address from mapa_shared), release at cluster scope
+// Arrive on a barrier that may live in the peer CTA (address from mapa_shared).  Default semantics (.release.cta), as
+// CUTLASS's ClusterBarrier::arrive does for the same purpose: what the peer must see was either written through the
+// async proxy (TMA, tcgen05) or fenced to it (fence.proxy.async) before this arrive.  The explicit .release.cluster /
+// .acquire.cluster forms were measured to cost 60 % of all stall samples of the pair kernel (ncu source page: every
+// arrive became MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, every wait iteration a CCTL.IVALL that invalidates L1).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait on a local barrier whose arrivals may come from the peer CTA: acquire at cluster scope
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// same, with nanosleep backoff, for roles that routinely wait a long time
-__device__ __forceinline__ void mbar_wait_cluster_backoff(uint32_t bar, uint32_t parity) {
-  uint32_t done, ns = 32;
-  while (true) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(ns);
-    if (ns < 512) ns <<= 1;
-  }
-}
+// waits on barriers whose arrivals come from the peer CTA / from multicast tcgen05.commit: the plain try_wait loops
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_cluster_backoff(uint32_t bar, uint32_t parity) { mbar_wait_backoff(bar, parity); }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -300,15 +274,17 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 
 // One 32-row x 32-column accumulator chunk (thread = row) -> dense, 128B-swizzled shared tile [32][32] floats
 // -> one asynchronous TMA store (bounds clipped by the tensor map).  `bufs` is 1024-byte aligned and warp private;
-// `seq` counts this warp's stores: with nbuf == 2 two buffers alternate (one older store may still be reading).
+// `seq` counts this warp's stores; nbuf (1..4) tiles of 4096 bytes rotate.
 __device__ __forceinline__ void epi_store_chunk_tma(uint8_t* bufs, int nbuf, int& seq, const float (&v)[32],
                                                     const CUtensorMap* map, int32_t col0, int32_t row0) {
   const int lane = threadIdx.x & 31;
-  uint8_t* buf = bufs + (nbuf == 2 ? (seq & 1) * 4096 : 0);
+  uint8_t* buf = bufs + (seq % nbuf) * 4096;  // nbuf store tiles rotate: nbuf - 1 older stores may still be reading theirs
   if (seq >= nbuf) {
     if (lane == 0) {
-      if (nbuf == 2) tma_store_wait_read<1>();
-      else tma_store_wait_read<0>();
+      if (nbuf == 1) tma_store_wait_read<0>();
+      else if (nbuf == 2) tma_store_wait_read<1>();
+      else if (nbuf == 3) tma_store_wait_read<2>();
+      else tma_store_wait_read<3>();
     }
     __syncwarp();
   }
