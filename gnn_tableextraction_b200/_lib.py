@@ -68,6 +68,8 @@ SIGNATURES = {
     "gte_relu_l2norm_fwd": (ci, [vp, i64, f32, vp, i64, i32, i32, vp]),
     "gte_relu_l2norm_bwd": (ci, [vp, i64, vp, i64, f32, vp, i64, i32, i32, vp]),
     "gte_relu_fwd": (ci, [vp, i64, vp, i64, i32, i32, vp]),
+    "gte_dropout_concat": (ci, [vp, i64, i32, vp, i64, i32, i32, f32, C.c_uint64, C.c_uint64, vp, vp, i64, vp, i64, vp]),
+    "gte_rng_advance": (ci, [vp, i64, vp]),
     "gte_relu_bwd": (ci, [vp, i64, vp, i64, vp, i64, i32, i32, vp]),
     "gte_cross_entropy_workspace_bytes": (sz, [i32]),
     "gte_cross_entropy_fwd": (ci, [vp, i64, vp, ci, vp, i32, i32, vp, vp, sz, vp]),

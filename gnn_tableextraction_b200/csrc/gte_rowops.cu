@@ -435,6 +435,61 @@ static int ce_grid(int32_t n) {
 }
 
 // ----------------------------------------------------------------- Adam ---
+// ---------------------------------------------------------------- dropout ----
+// nn.Dropout on the (never materialised) concatenation [x1 | x2] (models.py:30-33,60-61,113): element (row, c) of the
+// concatenation -- c < f1 in x1, else in x2 -- is kept with probability 1 - p and scaled by 1 / (1 - p).  The keep
+// decision is a pure function of (seed, offset, row * (f1 + f2) + c) through Philox4x32-10 (the generator family torch's
+// CUDA dropout uses; the stream layout is this library's own, so masks are statistically, not bitwise, equal to ATen's):
+// counter = (element >> 2) + offset, the element's word = element & 3.  The backward pass calls the same kernel on the
+// gradients with the same (seed, offset): the mask is recomputed, never stored.
+__device__ __forceinline__ uint2 mulhilo32(uint32_t a, uint32_t b) {
+  const uint64_t p = (uint64_t)a * b;
+  return make_uint2((uint32_t)p, (uint32_t)(p >> 32));
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t counter, uint64_t seed) {
+  uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint2 m0 = mulhilo32(0xD2511F53u, c0), m1 = mulhilo32(0xCD9E8D57u, c2);
+    const uint32_t n0 = m1.y ^ c1 ^ k0, n2 = m0.y ^ c3 ^ k1;
+    c0 = n0; c1 = m1.x; c2 = n2; c3 = m0.x;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__global__ void k_dropout2(const float* __restrict__ x1, int64_t ldx1, int32_t f1, const float* __restrict__ x2, int64_t ldx2,
+                           int32_t f2, int64_t n, float p, uint64_t seed_host, uint64_t offset_host,
+                           const int64_t* __restrict__ rng_dev, float* __restrict__ y1, int64_t ldy1, float* __restrict__ y2,
+                           int64_t ldy2) {
+  const uint64_t seed = rng_dev ? (uint64_t)rng_dev[0] : seed_host;
+  const uint64_t offset = rng_dev ? (uint64_t)rng_dev[1] + offset_host : offset_host;
+  const int64_t ft = (int64_t)f1 + f2;
+  const int64_t groups = (n * ft + 3) >> 2;  // one Philox call per 4 consecutive elements of the concatenation
+  const float scale = 1.0f / (1.0f - p);
+  // keep iff u >= p with u = word * 2^-32 (uniform in [0, 1)): integer threshold, no float rounding of the uniform
+  const uint32_t thresh = (uint32_t)fminf(fmaxf(p * 4294967296.0f, 0.f), 4294967040.0f);
+  int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; gidx < groups; gidx += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10((uint64_t)gidx + offset, seed);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t el = gidx * 4 + e;
+      if (el >= n * ft) break;
+      const int64_t row = el / ft;
+      const int32_t c = (int32_t)(el - row * ft);
+      const bool keep = w[e] >= thresh;
+      if (c < f1) y1[row * ldy1 + c] = keep ? x1[row * ldx1 + c] * scale : 0.f;
+      else y2[row * ldy2 + (c - f1)] = keep ? x2[row * ldx2 + (c - f1)] * scale : 0.f;
+    }
+  }
+}
+
+__global__ void k_rng_advance(int64_t* rng, int64_t by) { rng[1] += by; }
+
 __global__ void k_step_inc(int64_t* step) { *step += 1; }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -664,6 +719,28 @@ int gte_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   k_adam<<<ew_grid(count), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, weight_decay,
                                         step_host, step_dev, grad_scale, grad_den);
   GTE_CHECK_LAUNCH("k_adam");
+  return GTE_OK;
+}
+
+int gte_dropout_concat(const float* x1, int64_t ldx1, int32_t f1, const float* x2, int64_t ldx2, int32_t f2, int32_t n,
+                       float p, uint64_t seed, uint64_t offset, const int64_t* rng_dev, float* y1, int64_t ldy1, float* y2,
+                       int64_t ldy2, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && f1 >= 0 && f2 >= 0, "gte_dropout_concat: bad size");
+  GTE_CHECK_ARG(p >= 0.f && p < 1.f, "gte_dropout_concat: p must be in [0, 1) (p = 1 zeroes everything: use a memset)");
+  if (n == 0 || f1 + f2 == 0) return GTE_OK;
+  GTE_CHECK_ARG((f1 == 0 || (x1 && y1 && ldx1 >= f1 && ldy1 >= f1)) && (f2 == 0 || (x2 && y2 && ldx2 >= f2 && ldy2 >= f2)),
+                "gte_dropout_concat: bad argument");
+  const int64_t groups = ((int64_t)n * (f1 + f2) + 3) / 4;
+  k_dropout2<<<ew_grid(groups), 256, 0, as_stream(stream)>>>(x1, ldx1, f1, x2, ldx2, f2, n, p, seed, offset, rng_dev, y1, ldy1,
+                                                            y2, ldy2);
+  GTE_CHECK_LAUNCH("k_dropout2");
+  return GTE_OK;
+}
+
+int gte_rng_advance(int64_t* rng_dev, int64_t by, gte_stream_t stream) {
+  GTE_CHECK_ARG(rng_dev && by >= 0, "gte_rng_advance: bad argument");
+  k_rng_advance<<<1, 1, 0, as_stream(stream)>>>(rng_dev, by);
+  GTE_CHECK_LAUNCH("k_rng_advance");
   return GTE_OK;
 }
 

@@ -384,9 +384,10 @@ struct DwReduceArgs {
   int32_t accumulate;
 };
 
-__global__ void __launch_bounds__(RED_THREADS) k_umma_dw_reduce(const DwReduceArgs R) {
-  __shared__ float red[RED_THREADS];
-  int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+// One thread per output element, rows fastest: consecutive threads read consecutive floats of the column-major partial
+// tiles (coalesced), each thread adds its <= 148 partials in ascending CTA order (fixed order => reproducible).
+__global__ void __launch_bounds__(256) k_umma_dw_reduce(const DwReduceArgs R) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int s = 0;
   bool valid = false;
   for (; s < R.nseg; ++s) {
@@ -397,29 +398,30 @@ __global__ void __launch_bounds__(RED_THREADS) k_umma_dw_reduce(const DwReduceAr
     }
     i -= cnt;
   }
-  int row = 0, col = 0, nb = 0;
-  int64_t pidx = 0, stride = 0;
-  if (valid) {
-    // rows fastest: consecutive threads read consecutive floats of the column-major partial tiles
-    col = (int)(i / R.seg[s].nrows);
-    row = (int)(i % R.seg[s].nrows);
-    const int prow = R.seg[s].prow0 + row, pcol = R.seg[s].pcol0 + col;
-    const int mt = prow >> 7, r = prow & 127;
-    int g = 0;
-    if (pcol >= R.grp_pcol0[1] && R.grp_ncols[1] > 0) g = 1;
-    const int c = pcol - R.grp_pcol0[g];
-    int sub = 0;
-    for (int k = 0; k < R.ipc; ++k)
-      if (R.item_g[k] == g && R.item_mt[k] == mt) sub = k;
-    nb = (R.grid - sub + R.ipc - 1) / R.ipc;  // CTAs sub, sub + ipc, ... hold the partials of this output tile
-    pidx = (int64_t)sub * R.tile_stride + (int64_t)c * 128 + r;
-    stride = (int64_t)R.ipc * R.tile_stride;
+  if (!valid) return;
+  const int col = (int)(i / R.seg[s].nrows), row = (int)(i % R.seg[s].nrows);
+  const int prow = R.seg[s].prow0 + row, pcol = R.seg[s].pcol0 + col;
+  const int mt = prow >> 7, r = prow & 127;
+  int g = 0;
+  if (pcol >= R.grp_pcol0[1] && R.grp_ncols[1] > 0) g = 1;
+  const int c = pcol - R.grp_pcol0[g];
+  int sub = 0;
+  for (int k = 0; k < R.ipc; ++k)
+    if (R.item_g[k] == g && R.item_mt[k] == mt) sub = k;
+  const int nb = (R.grid - sub + R.ipc - 1) / R.ipc;  // CTAs sub, sub + ipc, ... hold the partials of this output tile
+  const float* p = R.partial + (int64_t)sub * R.tile_stride + (int64_t)c * 128 + r;
+  const int64_t stride = (int64_t)R.ipc * R.tile_stride;
+  float v = 0.f;
+  int b = 0;
+  for (; b + 4 <= nb; b += 4) {  // four loads in flight, added in order
+    const float p0 = p[(int64_t)b * stride], p1 = p[(int64_t)(b + 1) * stride], p2 = p[(int64_t)(b + 2) * stride],
+                p3 = p[(int64_t)(b + 3) * stride];
+    v += p0; v += p1; v += p2; v += p3;
   }
-  float v = reduce_partials_block(R.partial, nb, stride, pidx, valid, red);
-  if ((threadIdx.x >> 5) != 0 || !valid) return;
-  float* p = R.seg[s].dst + row * R.seg[s].stride_row + col * R.seg[s].stride_col;
-  if (R.accumulate) v += *p;
-  *p = v;
+  for (; b < nb; ++b) v += p[(int64_t)b * stride];
+  float* d = R.seg[s].dst + row * R.seg[s].stride_row + col * R.seg[s].stride_col;
+  if (R.accumulate) v += *d;
+  *d = v;
 }
 
 constexpr int DW_CHUNK_ROWS_DEFAULT = 512;
@@ -484,7 +486,7 @@ static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
   int64_t total = 0;
   for (int s = 0; s < r.nseg; ++s) total += (int64_t)r.seg[s].nrows * r.seg[s].ncols;
   if (total > 0) {
-    k_umma_dw_reduce<<<(unsigned)ceil_div64(total, 32), RED_THREADS, 0, st>>>(r);
+    k_umma_dw_reduce<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(r);
     GTE_CHECK_LAUNCH("k_umma_dw_reduce");
   }
   return GTE_OK;

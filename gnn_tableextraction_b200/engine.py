@@ -50,9 +50,6 @@ class SageTrainer:
         for layer in model.layers:
             if layer.activation is not None and not _is_relu(layer.activation):
                 raise GteError("SageTrainer: only activation=F.relu/None is fused; use the nn.Module path otherwise")
-        if _dropout_p(model.dropout) > 0 or any(_dropout_p(layer.dropout) > 0 for layer in model.layers):
-            raise GteError("SageTrainer: dropout > 0 is not implemented in the explicit train step (it would silently "
-                           "train without dropout); use the nn.Module path (model(g) + autograd) for dropout > 0")
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.class_w = None if class_weights is None else class_weights.to(self.device, torch.float32).contiguous()
         self.pg = process_group
@@ -60,6 +57,15 @@ class SageTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
 
+        # Dropout (models.py:30-33,60-61,113): masks come from Philox keyed by (seed, offset) held on the DEVICE, so a
+        # captured step draws fresh masks on every replay: every call site of a step uses base offset + its own share,
+        # and the base advances once per step (gte_rng_advance, captured with the step).
+        self._drop_p = [_dropout_p(model.dropout)] + [_dropout_p(layer.dropout) for layer in model.layers]
+        self.has_dropout = any(p > 0 for p in self._drop_p)
+        gen = torch.cuda.default_generators[self.device.index if self.device.index is not None else torch.cuda.current_device()]
+        rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
+        # ranks share the seed (torch.manual_seed) but must not share masks: disjoint regions of the counter space
+        self.rng_dev = torch.tensor([int(gen.initial_seed()) & (2 ** 63 - 1), rank << 44], dtype=torch.int64, device=self.device)
         # one flat fp32 buffer for parameters, gradients and both Adam moments;
         # the nn.Parameters become views, so state_dict()/load_state_dict() keep working
         total = sum(p.numel() for p in params)
@@ -107,19 +113,30 @@ class SageTrainer:
                 layer.lynorm.weight.data if has_ln else None, layer.lynorm.bias.data if has_ln else None, has_ln,
                 layer.lynorm.eps if has_ln else 1e-5, _is_relu(layer.activation))
 
-    def forward(self, g: PageGraphBatch, keep_ctx: bool = True, layer_outputs: Optional[list] = None):
+    def forward(self, g: PageGraphBatch, keep_ctx: bool = True, layer_outputs: Optional[list] = None,
+                training: bool = False):
         """Layer loop of ``GcnSAGE.forward`` (models.py:105-116).  ``layer_outputs`` (tests): a list that receives every
-        layer's output tensor (the parity tests read the ReLU on/off patterns from it)."""
+        layer's output tensor (the parity tests read the ReLU on/off patterns from it).  ``training``: dropout active."""
         h = g.ndata["feat"]
         w_edge = g.edata["feat"]
         ctxs: List[L.LayerCtx] = []
-        for layer in self.model.layers:
+        used = 0  # Philox counters consumed so far in this step
+        drop_on = training and self.has_dropout
+        if drop_on and self._drop_p[0] > 0:  # models.py:113: dropout on the input features (they need no gradient)
+            h, _ = ops.dropout_concat(h, None, self._drop_p[0], rng_dev=self.rng_dev, offset=used)
+            used += ops.dropout_counters(h.shape[0], h.shape[1])
+        for li, layer in enumerate(self.model.layers):
             W, b, gamma, beta, has_ln, eps, relu = self._layer_args(layer)
+            drop = None
+            if drop_on and self._drop_p[1 + li] > 0:
+                drop = L.DropoutSpec(self._drop_p[1 + li], 0, used, self.rng_dev)
+                used += ops.dropout_counters(h.shape[0], W.shape[1])
             h, ctx = L.sage_layer_forward(g, h, w_edge, W, b, gamma, beta, ln=has_ln, relu=relu, eps=eps, agg=L.GCN,
-                                          use_pp=layer.use_pp, save_for_backward=keep_ctx)
+                                          use_pp=layer.use_pp, save_for_backward=keep_ctx, dropout=drop)
             ctxs.append(ctx if keep_ctx else None)
             if layer_outputs is not None:
                 layer_outputs.append(h)
+        self._rng_used = used
         return h, ctxs
 
     def backward(self, g: PageGraphBatch, ctxs: List[L.LayerCtx], dlogits: torch.Tensor):
@@ -142,7 +159,7 @@ class SageTrainer:
     # The step in three kernel-only stages with the two collectives in between, so that under data
     # parallelism each stage can be replayed from its own CUDA graph while NCCL runs eagerly.
     def _stage_forward(self, g: PageGraphBatch, labels: torch.Tensor):
-        logits, ctxs = self.forward(g)
+        logits, ctxs = self.forward(g, training=self.model.training)
         ops.cross_entropy_fwd(logits, labels, self.class_w, stats=self.stats)
         return logits, ctxs
 
@@ -150,6 +167,8 @@ class SageTrainer:
         den = self._one if self.dp_fused else self.stats[1:2]
         dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, den)
         self.backward(g, ctxs, dlogits)
+        if getattr(self, "_rng_used", 0) > 0:
+            ops.rng_advance(self.rng_dev, self._rng_used)  # the next step (or graph replay) draws new masks
 
     def _stage_update(self):
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],

@@ -39,6 +39,19 @@ MEAN = "mean"  # sum / max(in_deg, 1)                          -- WeightedMeanSA
 
 
 @dataclass
+class DropoutSpec:
+    """Training-mode dropout of one call site: probability + where its mask lives in the Philox stream (ops.dropout_concat)."""
+
+    p: float
+    seed: int = 0
+    offset: int = 0
+    rng_dev: Optional[torch.Tensor] = None  # device int64[2] (seed, base offset): captured steps draw fresh masks per replay
+
+    def active(self) -> bool:
+        return self.p > 0.0
+
+
+@dataclass
 class LayerCtx:
     strategy: str = "agg"
     agg: str = GCN
@@ -53,6 +66,7 @@ class LayerCtx:
     relu: bool = False
     fin: int = 0
     fout: int = 0
+    drop: Optional[DropoutSpec] = None  # the mask of [h | ah] is recomputed from this in the backward pass
 
 
 def pick_strategy(fin: int, fout: int, use_pp: bool) -> str:
@@ -132,24 +146,36 @@ def aggregate_backward(g: PageGraphBatch, d_out: torch.Tensor, w_edge: torch.Ten
 def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Optional[torch.Tensor],
                        W: torch.Tensor, b: Optional[torch.Tensor], gamma: Optional[torch.Tensor],
                        beta: Optional[torch.Tensor], *, ln: bool, relu: bool, eps: float = 1e-5, agg: str = GCN,
-                       use_pp: bool = False, strategy: Optional[str] = None, save_for_backward: bool = True):
+                       use_pp: bool = False, strategy: Optional[str] = None, save_for_backward: bool = True,
+                       dropout: Optional[DropoutSpec] = None):
     """Returns (out [N, Fout], LayerCtx).  ``save_for_backward=False`` (inference): the fused tensor-core epilogue does not
-    write the pre-activation z (it only exists for the backward pass)."""
+    write the pre-activation z (it only exists for the backward pass).  ``dropout`` (training): nn.Dropout on the
+    concatenation [h | ah * norm] before the linear (models.py:60-61), in-kernel Philox, never materialising the concat."""
     fout = W.shape[0]
     fin = W.shape[1] if use_pp else W.shape[1] // 2
     if h.shape[1] != (W.shape[1] if use_pp else fin):
         raise _lib.GteError(f"layer expects {W.shape[1] if use_pp else fin} input features, got {h.shape[1]}")
     st = strategy or pick_strategy(fin, fout, use_pp)
+    drop = dropout if (dropout is not None and dropout.active()) else None
+    if drop is not None and st == "proj":
+        st = "agg"  # the mask acts on [h | ah]: aggregate first
     if GEMM_MODE != "ffma" and h.shape[0] >= UMMA_MIN_ROWS and not ops._aligned_mat(h):
         # e.g. the raw [N, 13] BBOX features: one padded copy gives 16-byte aligned rows for TMA / 128-bit loads
         hp = ops.empty_padded(h.shape[0], h.shape[1], h.device)
         hp.copy_(h)
         h = hp
-    ctx = LayerCtx(strategy=st, agg=agg, h=h, ln=ln, relu=relu, fin=fin, fout=fout, w_edge=w_edge)
+    ctx = LayerCtx(strategy=st, agg=agg, h=h, ln=ln, relu=relu, fin=fin, fout=fout, w_edge=w_edge, drop=drop)
     if st == "pp":  # pre-propagated input: plain linear (models.py:49)
+        if drop is not None:
+            h, _ = ops.dropout_concat(h, None, drop.p, drop.seed, drop.offset, drop.rng_dev)
+            ctx.h = h
         z = ops.linear_fwd(h, None, W, b)
     elif st == "agg":
         ah = aggregate_forward(g, h, w_edge, agg)
+        if drop is not None:
+            # the dropped operands are what the linear (and, in backward, dW) sees; d[h | ah] gets the same mask back
+            h, ah = ops.dropout_concat(h, ah, drop.p, drop.seed, drop.offset, drop.rng_dev)
+            ctx.h = h
         ctx.ah = ah
         if use_umma(h.shape[0], fin, fout, h, ah):
             # tensor cores: projection + bias + LayerNorm + ReLU in one kernel
@@ -202,9 +228,15 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
         dz = ops.relu_bwd(dy, ctx.z)
     else:
         dz = dy
+    drop = ctx.drop
     if ctx.strategy == "pp":
         ops.linear_bwd_weight(dz, ctx.h, None, dW, db, accumulate)
-        return ops.linear_bwd_data(dz, W, 0, W.shape[1]) if need_dh else None
+        if not need_dh:
+            return None
+        dh = ops.linear_bwd_data(dz, W, 0, W.shape[1])
+        if drop is not None:
+            ops.dropout_concat(dh, None, drop.p, drop.seed, drop.offset, drop.rng_dev, inplace=True)
+        return dh
     if ctx.strategy == "agg":
         if use_umma_dw(dz.shape[0], fout, fin, fin, db is not None, dz, ctx.h, ctx.ah):
             ops.umma_linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
@@ -221,6 +253,8 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
         else:
             d_self = ops.linear_bwd_data(dz, W, 0, fin)
             d_ah = ops.linear_bwd_data(dz, W, fin, fin)
+        if drop is not None:  # same mask as in the forward pass, recomputed
+            ops.dropout_concat(d_self, d_ah, drop.p, drop.seed, drop.offset, drop.rng_dev, inplace=True)
         return aggregate_backward(g, d_ah, ctx.w_edge, addend=d_self)
     # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
     #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn
@@ -269,7 +303,7 @@ class SageLayerFunction(torch.autograd.Function):
     """One fused autograd node per layer (replaces ~10 ATen/DGL nodes of the reference)."""
 
     @staticmethod
-    def forward(ctx, h, W, b, gamma, beta, w_edge, g, ln, relu, eps, agg, use_pp):
+    def forward(ctx, h, W, b, gamma, beta, w_edge, g, ln, relu, eps, agg, use_pp, drop=None):
         _no_edge_grad(w_edge)
         ctx.in_dtype = h.dtype
         h = _as_mat(h.detach())
@@ -278,7 +312,7 @@ class SageLayerFunction(torch.autograd.Function):
                                            None if b is None else b.detach(),
                                            None if gamma is None else gamma.detach(),
                                            None if beta is None else beta.detach(),
-                                           ln=ln, relu=relu, eps=eps, agg=agg, use_pp=use_pp)
+                                           ln=ln, relu=relu, eps=eps, agg=agg, use_pp=use_pp, dropout=drop)
         ctx.lctx = lctx  # kept until the node is freed, so backward(retain_graph=True) can run again
         ctx.g = g
         ctx.save_for_backward(W, gamma, beta)
@@ -301,7 +335,37 @@ class SageLayerFunction(torch.autograd.Function):
                                      need_dh=ctx.needs_input_grad[0])
         if dh is not None and dh.dtype != ctx.in_dtype:
             dh = dh.to(ctx.in_dtype)
-        return dh, dW, db, dgamma, dbeta, None, None, None, None, None, None, None
+        return dh, dW, db, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+class DropoutFunction(torch.autograd.Function):
+    """``nn.Dropout(p)`` in training mode on one feature matrix (models.py:113), native kernel, mask recomputed in backward."""
+
+    @staticmethod
+    def forward(ctx, x, drop):
+        ctx.drop, ctx.in_dtype = drop, x.dtype
+        x = _as_mat(x.detach())
+        with torch.cuda.device(x.device):
+            return ops.dropout_concat(x, None, drop.p, drop.seed, drop.offset, drop.rng_dev)[0]
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _as_mat(dy)
+        d = ctx.drop
+        with torch.cuda.device(dy.device):
+            dx = ops.dropout_concat(dy, None, d.p, d.seed, d.offset, d.rng_dev)[0]
+        return (dx if dx.dtype == ctx.in_dtype else dx.to(ctx.in_dtype)), None
+
+
+def torch_generator_dropout_spec(p: float, device: torch.device, n: int, f: int) -> DropoutSpec:
+    """A DropoutSpec keyed from torch's CUDA generator of `device` (the seed torch.manual_seed set), advancing that
+    generator's Philox offset past the counters this call site will consume -- reproducible under the same seed."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[idx]
+    seed, off = int(gen.initial_seed()), int(gen.get_offset())
+    need = ops.dropout_counters(n, f)
+    gen.set_offset(off + 4 * need)  # torch keeps the offset a multiple of 4; the next call site starts past this one
+    return DropoutSpec(float(p), seed, off)
 
 
 class AggregateFunction(torch.autograd.Function):

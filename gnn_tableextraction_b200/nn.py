@@ -77,16 +77,13 @@ class GcnSAGELayer(nn.Module):
                 raise KeyError("feat")  # same failure as the reference when edge weights are absent (models.py:53)
             w_edge = pg.edata["feat"]
 
-        if self._dropout_active() and not self.use_pp:
-            # dropout acts on the concatenated [h | ah*norm] (models.py:60-61): materialise it, then plain linear
-            ah = L.AggregateFunction.apply(h, w_edge, pg, L.GCN)
-            x = self.dropout(torch.cat((h, ah), dim=1))
-            out = L.SageLayerFunction.apply(x, self.linear.weight, self.linear.bias, gamma, beta, None, None,
-                                            has_ln, fused_relu, eps, L.GCN, True)
-        else:
-            x = self.dropout(h) if self._dropout_active() else h
-            out = L.SageLayerFunction.apply(x, self.linear.weight, self.linear.bias, gamma, beta, w_edge, pg,
-                                            has_ln, fused_relu, eps, L.GCN, self.use_pp)
+        drop = None
+        if self._dropout_active():
+            # nn.Dropout on [h | ah * norm] (models.py:60-61) inside the layer's kernels: Philox keyed from torch's CUDA
+            # generator, the concat is never materialised, the mask is recomputed in backward
+            drop = L.torch_generator_dropout_spec(self.dropout.p, h.device, h.shape[0], h.shape[1] if self.use_pp else 2 * h.shape[1])
+        out = L.SageLayerFunction.apply(h, self.linear.weight, self.linear.bias, gamma, beta, w_edge, pg,
+                                        has_ln, fused_relu, eps, L.GCN, self.use_pp, drop)
         if act and not fused_relu:
             out = act(out)
         return out
@@ -113,7 +110,8 @@ class GcnSAGE(nn.Module):
     def forward(self, g):
         pg = as_page_graph_batch(g)
         h = pg.ndata["feat"]
-        h = self.dropout(h)
+        if self.training and self.dropout.p > 0:  # models.py:113, native kernel (mask recomputed in backward)
+            h = L.DropoutFunction.apply(h, L.torch_generator_dropout_spec(self.dropout.p, h.device, h.shape[0], h.shape[1]))
         for layer in self.layers:
             h = layer(pg, h)
         return h

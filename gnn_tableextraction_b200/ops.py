@@ -623,6 +623,37 @@ def relu_l2norm_bwd(dy, z, eps: float = 1e-12, out=None):
     return out
 
 
+def dropout_concat(x1, x2, p: float, seed: int = 0, offset: int = 0, rng_dev: Optional[torch.Tensor] = None,
+                   inplace: bool = False):
+    """Training-mode ``nn.Dropout(p)`` on the concatenation ``[x1 | x2]`` without materialising it (models.py:60-61);
+    ``x2`` may be None (input features, models.py:113).  Returns (y1, y2).  The mask depends only on
+    (seed, offset, element index): call it again on the gradients with the same arguments for the backward pass."""
+    x1p, ld1, f1 = _mat(x1, "dropout.x1")
+    n = x1.shape[0]
+    x2p, ld2, f2 = (None, 0, 0)
+    if x2 is not None:
+        x2p, ld2, f2 = _mat(x2, "dropout.x2")
+        if x2.shape[0] != n:
+            raise GteError("dropout_concat: row mismatch")
+    y1 = x1 if inplace else empty_padded(n, f1, x1.device)
+    y2 = None if x2 is None else (x2 if inplace else empty_padded(n, f2, x1.device))
+    y1p, ldy1, _ = _mat(y1, "dropout.y1")
+    y2p, ldy2 = (None, 0) if y2 is None else _mat(y2, "dropout.y2")[:2]
+    check(lib().gte_dropout_concat(x1p, ld1, f1, x2p, ld2, f2, n, float(p), int(seed) & (2 ** 64 - 1), int(offset),
+                                   _vec(rng_dev, "rng_dev", torch.int64, 2), y1p, ldy1, y2p, ldy2, _stream()),
+          "gte_dropout_concat")
+    return y1, y2
+
+
+def dropout_counters(n: int, f: int) -> int:
+    """Philox counters one dropout_concat launch over n x f elements consumes."""
+    return (int(n) * int(f) + 3) // 4
+
+
+def rng_advance(rng_dev: torch.Tensor, by: int) -> None:
+    check(lib().gte_rng_advance(_vec(rng_dev, "rng_dev", torch.int64, 2), int(by), _stream()), "gte_rng_advance")
+
+
 def relu_fwd(z, out=None):
     zp, ldz, f = _mat(z, "relu.z")
     n = z.shape[0]

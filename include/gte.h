@@ -371,6 +371,23 @@ int gte_relu_l2norm_bwd(const float* dy, int64_t lddy, const float* z, int64_t l
                         float* dz, int64_t lddz, int32_t n, int32_t f, gte_stream_t stream);
 /* elementwise relu helpers for activation=F.relu without LayerNorm */
 int gte_relu_fwd(const float* z, int64_t ldz, float* y, int64_t ldy, int32_t n, int32_t f, gte_stream_t stream);
+
+/*
+ * nn.Dropout(p) in training mode on the concatenation [x1 | x2] that the layers never materialise (models.py:30-33,
+ * 60-61: `h = self.dropout(concat(h, ah * norm))`; models.py:113: the input features, then x2 = NULL, f2 = 0):
+ *   y[r, c] = keep(r, c) ? x[r, c] / (1 - p) : 0,   keep ~ Bernoulli(1 - p)
+ * keep(r, c) is a pure function of (seed, offset, r * (f1 + f2) + c) through Philox4x32-10, so the backward pass calls
+ * the same entry on the gradients with the same (seed, offset) -- the mask is recomputed, never stored.  Statistically
+ * (not bitwise) equal to ATen's mask.  One launch consumes ceil(n (f1 + f2) / 4) counters starting at `offset`.
+ * `rng_dev` (device int64[2] = {seed, base offset}, may be NULL): when given, seed = rng_dev[0] and the offset is
+ * rng_dev[1] + `offset` -- a captured CUDA graph then draws fresh masks on every replay after gte_rng_advance.
+ * In-place use (y = x) is allowed.
+ */
+int gte_dropout_concat(const float* x1, int64_t ldx1, int32_t f1, const float* x2, int64_t ldx2, int32_t f2, int32_t n,
+                       float p, uint64_t seed, uint64_t offset, const int64_t* rng_dev, float* y1, int64_t ldy1, float* y2,
+                       int64_t ldy2, gte_stream_t stream);
+/* rng_dev[1] += by  (one launch; graph-replay safe like the optimiser's step counter) */
+int gte_rng_advance(int64_t* rng_dev, int64_t by, gte_stream_t stream);
 int gte_relu_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, float* dz, int64_t lddz,
                  int32_t n, int32_t f, gte_stream_t stream);
 

@@ -801,3 +801,40 @@ def test_spmm_paged_packed_edges_through_l1_at_512_pages(f):
     for p_id, ref in zip(sample, _oracle_rows_for_pages(pages, sample, noff, x, f)):
         lo = int(noff[p_id])
         assert rel_err(y[lo:lo + 300], ref) < 2e-6, p_id
+
+
+# ------------------------------------------------------------- native dropout (models.py:30-33,60-61,113) -----
+@pytest.mark.parametrize("p", [0.1, 0.5, 0.8])
+def test_dropout_concat_statistics_determinism_and_indexing(p):
+    n, f1, f2 = 20000, 218, 218
+    x1, x2 = _padded(torch.ones(n, f1)), _padded(torch.ones(n, f2))
+    y1, y2 = ops.dropout_concat(x1, x2, p, seed=1234, offset=40)
+    y = torch.cat([y1, y2], 1)
+    kept = y != 0
+    # kept values are x / (1 - p); the keep rate is 1 - p within 5 sigma
+    assert torch.allclose(y[kept], torch.full_like(y[kept], 1.0 / (1.0 - p)), rtol=1e-6)
+    rate, m = kept.float().mean().item(), n * (f1 + f2)
+    assert abs(rate - (1 - p)) < 5 * (p * (1 - p) / m) ** 0.5
+    # per-column and per-row keep rates are unbiased as well (no stripe patterns from the counter layout)
+    assert (kept.float().mean(0) - (1 - p)).abs().max().item() < 6 * (p * (1 - p) / n) ** 0.5
+    assert (kept.float().mean(1) - (1 - p)).abs().max().item() < 6 * (p * (1 - p) / (f1 + f2)) ** 0.5
+    # same (seed, offset) => same mask (this is what the backward pass relies on); other offsets / seeds differ
+    z1, z2 = ops.dropout_concat(x1, x2, p, seed=1234, offset=40)
+    assert torch.equal(z1, y1) and torch.equal(z2, y2)
+    assert not torch.equal(ops.dropout_concat(x1, x2, p, seed=1234, offset=41)[0], y1)
+    assert not torch.equal(ops.dropout_concat(x1, x2, p, seed=1235, offset=40)[0], y1)
+    # the mask is a function of the element index of the concatenation: one [n, f1 + f2] matrix gets the same mask
+    xc = _padded(torch.ones(n, f1 + f2))
+    assert torch.equal(ops.dropout_concat(xc, None, p, seed=1234, offset=40)[0], y)
+    # device-side state (captured steps): same numbers => same mask; advancing the base offset moves the mask
+    rng = torch.tensor([1234, 30], dtype=torch.int64, device=DEV)
+    assert torch.equal(ops.dropout_concat(x1, x2, p, offset=10, rng_dev=rng)[0], y1)
+    ops.rng_advance(rng, 7)
+    assert int(rng[1].item()) == 37
+    assert not torch.equal(ops.dropout_concat(x1, x2, p, offset=10, rng_dev=rng)[0], y1)
+    # in place, and on real data: y = x * mask / (1 - p) with the mask of a single [n, f1] matrix
+    xr = _padded(torch.randn(n, f1))
+    m1 = ops.dropout_concat(_padded(torch.ones(n, f1)), None, p, seed=1234, offset=40)[0]
+    ref = xr * m1
+    ops.dropout_concat(xr, None, p, seed=1234, offset=40, inplace=True)
+    assert rel_err(xr, ref) < 1e-6

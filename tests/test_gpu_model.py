@@ -527,3 +527,125 @@ def test_captured_predict_pass_equals_eager_predict_pages():
         assert torch.equal(preds, p2), i
         sizes = torch.tensor(hbatch["batch_num_nodes"], dtype=torch.float64, device=DEV)
         assert torch.equal(corr[:6].to(torch.float64) / sizes, acc), i
+
+
+# ------------------------------------------------------------------ dropout p > 0 on the native kernels -----
+class _MaskMul(torch.nn.Module):
+    """stands in for nn.Dropout in the oracle: multiplies by a GIVEN scaled keep mask"""
+
+    def __init__(self, m):
+        super().__init__()
+        self.m = m
+
+    def forward(self, x):
+        return x * self.m
+
+
+def _mask(n, f, p, seed, offset, rng_dev=None):
+    """the scaled keep mask [n, f] a dropout call site with these Philox coordinates applies (ones through the kernel)"""
+    from gnn_tableextraction_b200 import ops
+
+    ones = ops.empty_padded(n, f, DEV)
+    ones.fill_(1.0)
+    return ops.dropout_concat(ones, None, p, seed=seed, offset=offset, rng_dev=rng_dev)[0].cpu()
+
+
+def test_layer_dropout_matches_oracle_under_the_same_mask():
+    """GcnSAGELayer(dropout=0.5).train(): the mask acts on [h | ah * norm] (models.py:60-61) inside the kernels and is
+    recomputed in backward -- output, dh and every parameter gradient equal the oracle run with that same mask"""
+    pages = synth.make_pages(5, n=260, k=6)  # 1300 rows: tensor-core route
+    og = oracle_graph_from_pages(pages)
+    g = gte.PageGraphBatch.from_pages(pages, DEV)
+    p, fin, fo = 0.5, 48, 40
+    torch.manual_seed(5)
+    ol = so.OracleGcnSAGELayer(fin, fo, F.relu, p)
+    cl = gte.GcnSAGELayer(fin, fo, F.relu, p)
+    cl.load_state_dict(ol.state_dict())
+    cl = cl.to(DEV).train()
+    h0 = torch.randn(1300, fin)
+    up = torch.randn(1300, fo)
+    torch.manual_seed(77)
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    h = h0.to(DEV).requires_grad_(True)
+    y = cl(g, h)
+    assert gen.get_offset() > off  # the call site consumed its share of torch's Philox stream
+    (y * up.to(DEV)).sum().backward()
+    M = _mask(1300, 2 * fin, p, seed, off)
+    assert 0.45 < (M != 0).float().mean().item() < 0.55
+    ol.train()
+    ol.dropout = _MaskMul(M)
+    ho = h0.clone().requires_grad_(True)
+    yo = ol(og, ho)
+    (yo * up).sum().backward()
+    assert rel_err(y, yo) < TOL
+    assert rel_err(h.grad, ho.grad) < TOL
+    for (k, a), (_, b) in zip(cl.named_parameters(), ol.named_parameters()):
+        assert rel_err(a.grad, b.grad) < TOL, k
+    # a second forward draws a different mask; eval() is the identity
+    assert not torch.equal(cl(g, h.detach()), y.detach())
+    cl.eval(), ol.eval()
+    ol.dropout = _MaskMul(torch.ones(1))
+    assert rel_err(cl(g, h.detach()), ol(og, h0)) < TOL
+
+
+def test_trainer_with_dropout_matches_oracle_under_its_masks_and_redraws_per_replay():
+    """SageTrainer trains WITH dropout (it used to train silently without): one step equals the oracle step under
+    the masks the device-side Philox state yields; captured replays draw a new mask every time; predict is unaffected"""
+    from gnn_tableextraction_b200 import ops
+
+    pages = synth.make_pages(6, n=200, k=6)
+    og = oracle_graph_from_pages(pages)
+    hb = batch_pages_host(pages)
+    p = 0.3
+    torch.manual_seed(9)
+    om = so.OracleGcnSAGE(13, 40, 9, 3, F.relu, p)
+    cm = gte.GcnSAGE(13, 40, 9, 3, F.relu, p)
+    cm.load_state_dict(om.state_dict())
+    cm = cm.to(DEV).train()
+    tr = gte.SageTrainer(cm)
+    assert tr.has_dropout
+    n = 1200
+    rng0 = tr.rng_dev.clone()
+    # masks of the three call sites of one step, in the trainer's order: input features, layer 0, layer 1
+    used = 0
+    M_in = _mask(n, 13, p, 0, used, rng0)
+    used += ops.dropout_counters(n, 13)
+    M0 = _mask(n, 26, p, 0, used, rng0)
+    used += ops.dropout_counters(n, 26)
+    M1 = _mask(n, 80, p, 0, used, rng0)
+    used += ops.dropout_counters(n, 80)
+    g = gte.PageGraphBatch.from_host(hb, DEV)
+    outs = []
+    tr.forward(g, keep_ctx=False, layer_outputs=outs, training=True)  # same Philox state as the step below: same masks
+    relu_masks = [(o > 0).cpu() if layer.activation is not None else None for o, layer in zip(outs, cm.layers)]
+    stats = tr.train_step(g).cpu()
+    assert int(tr.rng_dev[1].item()) - int(rng0[1].item()) == used
+    om.train()
+    om.dropout = _MaskMul(M_in)
+    om.layers[0].dropout = _MaskMul(M0)
+    om.layers[1].dropout = _MaskMul(M1)
+    om(og)
+    check_relu_patterns(om, relu_masks)
+    ref = om(og, relu_masks=relu_masks)
+    oloss = torch.nn.CrossEntropyLoss()(ref, og.ndata["label"].long())
+    oloss.backward()
+    assert abs(stats[0].item() / stats[1].item() - oloss.item()) < TOL * max(1.0, abs(oloss.item()))
+    for (k, a), (_, b) in zip(cm.named_parameters(), om.named_parameters()):
+        assert rel_err(a.grad, b.grad) < TOL, k
+    # captured: every replay advances the device-side offset => different masks => different losses on the same batch
+    cm2 = gte.GcnSAGE(13, 40, 9, 3, F.relu, p)
+    cm2.load_state_dict(om.state_dict())
+    tr2 = gte.SageTrainer(cm2.to(DEV).train(), lr=0.0, weight_decay=0.0)
+    tr2.capture(hb)
+    losses = []
+    for _ in range(3):
+        tr2.load_batch(hb)
+        s = tr2.replay().cpu()
+        losses.append(s[0].item() / s[1].item())
+    assert len({round(l, 6) for l in losses}) == 3
+    # inference never drops
+    cm2.eval()
+    a = tr2.predict(gte.PageGraphBatch.from_host(hb, DEV))
+    b = tr2.predict(gte.PageGraphBatch.from_host(hb, DEV))
+    assert torch.equal(a, b)
