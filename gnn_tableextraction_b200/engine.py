@@ -81,7 +81,12 @@ class SageTrainer:
         self.dp_fused = self.world > 1 or os.environ.get("GTE_DP_FUSED", "0") == "1"
         self._flat_len = o
         self.flat_param = torch.zeros(o, dtype=torch.float32, device=self.device)
-        self.flat_grad = torch.zeros(o + 4, dtype=torch.float32, device=self.device)
+        self.flat_grad = None
+        self._dp_peer = None
+        if self.world > 1 and os.environ.get("GTE_DP_PEER", "1") != "0":
+            self._setup_peer_exchange(o + 4)
+        if self.flat_grad is None:
+            self.flat_grad = torch.zeros(o + 4, dtype=torch.float32, device=self.device)
         self.exp_avg = torch.zeros(o, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(o, dtype=torch.float32, device=self.device)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -96,6 +101,8 @@ class SageTrainer:
                 p.grad = gv
                 self._grad_views[id(p)] = gv
         self.stats = self.flat_grad[o:o + 3] if self.dp_fused else torch.zeros(3, dtype=torch.float32, device=self.device)
+        # peer exchange: the tail of flat_grad keeps the LOCAL statistics, the fused kernel writes the global ones here
+        self.stats_global = torch.zeros(4, dtype=torch.float32, device=self.device) if self._dp_peer else None
         self._one = torch.ones(1, dtype=torch.float32, device=self.device)
         if self.world > 1:
             # every rank must start from the same parameters / optimiser state (DDP broadcasts from rank 0 too):
@@ -175,11 +182,55 @@ class SageTrainer:
                       beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step_dev=self.step_dev,
                       grad_den=self.stats[1:2] if self.dp_fused else None, count=self._flat_len)
 
+    def _setup_peer_exchange(self, numel: int):
+        """Flat gradient buffer in symmetric memory (every rank can load every other rank's buffer over NVLink) for the
+        fused all-reduce + Adam kernel.  Falls back to NCCL + gte_adam_step when the ranks cannot map each other."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            group = self.pg if self.pg is not None else torch.distributed.group.WORLD
+            buf = symm_mem.empty(numel, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group)
+            if int(getattr(hdl, "offset", 0)) != 0 or hdl.world_size != self.world or hdl.signal_pad_size < 2048:
+                raise RuntimeError("unexpected symmetric-memory layout")
+            # this library's words of every rank's signal pad: 1 KB into the pad (torch's own barriers use its first words)
+            pads = torch.tensor([int(p) + 1024 for p in hdl.signal_pad_ptrs], dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
+            torch.distributed.barrier(group)
+            self.flat_grad = buf
+            self._dp_peer = {"hdl": hdl, "grad_ptrs": int(hdl.buffer_ptrs_dev), "pads": pads, "rank": int(hdl.rank),
+                             "local": torch.zeros(4, dtype=torch.int32, device=self.device)}
+        except Exception as exc:  # no P2P mapping (or an older torch): the NCCL path still works
+            import warnings
+
+            warnings.warn(f"SageTrainer: peer-memory gradient exchange unavailable ({type(exc).__name__}: {exc}); using NCCL")
+            self.flat_grad, self._dp_peer = None, None
+
+    def _stage_exchange_update(self):
+        """gradient all-reduce + Adam: ONE kernel over NVLink peer memory when the ranks share symmetric memory, else one
+        NCCL all-reduce (gradients + loss statistics in one buffer) + gte_adam_step"""
+        if self._dp_peer is not None:
+            d = self._dp_peer
+            ops.dp_allreduce_adam(d["grad_ptrs"], d["pads"].data_ptr(), d["rank"], self.world, self._flat_len, self._flat_len,
+                                  self.flat_param, self.exp_avg, self.exp_avg_sq, self.stats_global, lr=self.lr,
+                                  beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.wd,
+                                  step_dev=self.step_dev, local_words=d["local"])
+        else:
+            self._all_reduce(self.flat_grad)  # dp_fused: gradients + [sum w*nll, sum w, #correct] in one collective
+            self._stage_update()
+
+    def _result(self) -> torch.Tensor:
+        return self.stats_global[:3] if self._dp_peer is not None else self.stats
+
+    def step_stats(self) -> torch.Tensor:
+        """device tensor [sum w*nll, sum w, #correct] of the last step (global over ranks)"""
+        return self._result()
+
     def _step_impl(self, g: PageGraphBatch, labels: torch.Tensor):
         logits, ctxs = self._stage_forward(g, labels)
         self._stage_backward(g, labels, logits, ctxs)
-        self._all_reduce(self.flat_grad)  # dp_fused: gradients + [sum w*nll, sum w, #correct] in one collective
-        self._stage_update()
+        self._stage_exchange_update()
         return logits
 
     # ------------------------------------------------------------- API -----
@@ -191,7 +242,7 @@ class SageTrainer:
             labels = g.ndata["label"]
         with torch.cuda.device(self.device):
             self._step_impl(g, labels)
-        return self.stats
+        return self._result()
 
     @torch.no_grad()
     def predict(self, g: PageGraphBatch) -> torch.Tensor:
@@ -245,7 +296,7 @@ class SageTrainer:
         batches are fed with ``load_batch`` + ``replay``.  ``split`` (default: data-parallel
         runs) captures the kernels in one graph and leaves the all-reduce and Adam outside it."""
         if split is None:
-            split = self.world > 1
+            split = self.world > 1 and self._dp_peer is None  # the peer-memory exchange is an ordinary kernel: one graph
         if mode not in ("train", "predict"):
             raise GteError(f"capture: unknown mode {mode}")
         self._mode = mode
@@ -378,8 +429,7 @@ class SageTrainer:
         graph = self._graphs[which] if getattr(self, "_graphs", None) else self._graph
         if isinstance(graph, tuple):
             graph[0].replay()
-            self._all_reduce(self.flat_grad)
-            self._stage_update()
+            self._stage_exchange_update()
         else:
             graph.replay()
 
@@ -387,7 +437,7 @@ class SageTrainer:
         if getattr(self, "_mode", "train") == "predict":
             st = self._statics[which]
             return st["preds"], st["correct"]
-        return self.stats
+        return self._result()
 
     def replay(self):
         self._replay_graphs()

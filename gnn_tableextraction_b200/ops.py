@@ -737,6 +737,19 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, e
     )
 
 
+def dp_allreduce_adam(peer_grad_ptrs_dev: int, peer_signal_ptrs_dev: int, rank: int, world: int, count: int, stats_off: int,
+                      param, exp_avg, exp_avg_sq, stats_out, *, lr, beta1, beta2, eps, weight_decay, step_dev, local_words):
+    """One-shot all-reduce of the ranks' flat gradient buffers over NVLink peer memory fused with Adam (gte.h)."""
+    for t, nm in ((param, "param"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _vec(t, nm, n=count)
+    check(lib().gte_dp_allreduce_adam(int(peer_grad_ptrs_dev), int(peer_signal_ptrs_dev), int(rank), int(world), int(count),
+                                      int(stats_off), param.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                      _vec(stats_out, "stats_out", n=3), float(lr), float(beta1), float(beta2), float(eps),
+                                      float(weight_decay), _vec(step_dev, "step_dev", torch.int64, 1),
+                                      _vec(local_words, "local_words", torch.int32, 4), _stream()),
+          "gte_dp_allreduce_adam")
+
+
 # ------------------------------------------- either side of the layers ----
 def page_predictions(logits, page_off, num_pages: int, labels=None):
     """``logits.argmax(1)`` for a batch of pages + per-page number of correct predictions

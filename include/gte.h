@@ -421,6 +421,24 @@ int gte_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float weight_decay, int64_t step_host, int64_t* step_dev, float grad_scale,
                   const float* grad_den, gte_stream_t stream);
 
+/*
+ * Data-parallel step tail in ONE kernel: one-shot all-reduce of the flat gradient buffers over NVLink peer memory
+ * (P2P loads, summed in rank order => bit-identical replicas) fused with the Adam update of gte_adam_step (device step
+ * counter, division by the global label-weight sum found at stats_off + 1).  Replaces `ncclAllReduce` + optimizer.step()
+ * of a data-parallel model_train.py:330-332; capturable in a CUDA graph with the rest of the step.
+ *   peer_grad_ptrs_dev / peer_signal_ptrs_dev: DEVICE arrays [world] of device pointers -- every rank's flat gradient
+ *     buffer ([count parameters ... stats_off: sum w*nll, sum w, #correct]) and the 2*world uint32 words this library
+ *     owns inside every rank's signal pad (zero before the first call).  Both come from a symmetric-memory rendezvous
+ *     (torch.distributed._symmetric_memory); the entry itself never allocates or maps memory.
+ *   local_words: [4] uint32 device words of this rank, zero before the first call.
+ *   stats_out [3]: the global statistics.
+ * Every rank must call it once per step on the stream that produced its gradients.
+ */
+int gte_dp_allreduce_adam(const void* peer_grad_ptrs_dev, const void* peer_signal_ptrs_dev, int32_t rank, int32_t world,
+                          int64_t count, int64_t stats_off, float* param, float* exp_avg, float* exp_avg_sq,
+                          float* stats_out, float lr, float beta1, float beta2, float eps, float weight_decay,
+                          int64_t* step_dev, uint32_t* local_words, gte_stream_t stream);
+
 /* ---------------------------------------- either side of the layers ---- */
 /*
  * Batched predict tail (model_predict.py:144-154): preds[i] = argmax_j logits[i, j] (first maximal index; NaN

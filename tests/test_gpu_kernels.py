@@ -838,3 +838,37 @@ def test_dropout_concat_statistics_determinism_and_indexing(p):
     ref = xr * m1
     ops.dropout_concat(xr, None, p, seed=1234, offset=40, inplace=True)
     assert rel_err(xr, ref) < 1e-6
+
+
+def test_dp_allreduce_adam_single_rank_equals_adam_step():
+    """the fused exchange + optimiser kernel with world = 1 (its own buffer as the only peer) == gte_adam_step with the
+    device-side denominator: same parameters and moments, step counter advanced, statistics copied out; three calls in a
+    row exercise the sequence numbers of the flag protocol"""
+    n = 4096 * 3 + 8
+    gen = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=gen)
+    pa, pb = p0.clone().to(DEV), p0.clone().to(DEV)
+    ma, mb = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    va, vb = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step_a, step_b = torch.zeros(1, dtype=torch.int64, device=DEV), torch.zeros(1, dtype=torch.int64, device=DEV)
+    grad = torch.zeros(n + 4, device=DEV)
+    ptrs = torch.tensor([grad.data_ptr()], dtype=torch.int64, device=DEV)
+    pad = torch.zeros(64, dtype=torch.int32, device=DEV)
+    pads = torch.tensor([pad.data_ptr()], dtype=torch.int64, device=DEV)
+    local = torch.zeros(4, dtype=torch.int32, device=DEV)
+    stats = torch.zeros(4, device=DEV)
+    for it in range(3):
+        grad[:n] = torch.randn(n, generator=gen).to(DEV) * 100.0
+        grad[n:n + 3] = torch.tensor([321.0, 153600.0 + it, 777.0], device=DEV)
+        ops.adam_step(pa, grad, ma, va, lr=0.01, weight_decay=5e-4, step_dev=step_a, grad_den=grad[n + 1:n + 2], count=n)
+        ops.dp_allreduce_adam(ptrs.data_ptr(), pads.data_ptr(), 0, 1, n, n, pb, mb, vb, stats, lr=0.01, beta1=0.9, beta2=0.999,
+                              eps=1e-8, weight_decay=5e-4, step_dev=step_b, local_words=local)
+        assert torch.equal(stats[:3], grad[n:n + 3])
+    assert step_a.item() == step_b.item() == 3 and local[0].item() == 3 and local[2].item() == 0
+    assert rel_err(pb, pa) < 1e-6 and rel_err(mb, ma) < 1e-6 and rel_err(vb, va) < 1e-6
+    # a step without weighted labels leaves the replica untouched (and still completes the handshake)
+    grad[n + 1] = 0.0
+    before = pb.clone()
+    ops.dp_allreduce_adam(ptrs.data_ptr(), pads.data_ptr(), 0, 1, n, n, pb, mb, vb, stats, lr=0.01, beta1=0.9, beta2=0.999,
+                          eps=1e-8, weight_decay=5e-4, step_dev=step_b, local_words=local)
+    assert torch.equal(pb, before) and local[0].item() == 4
