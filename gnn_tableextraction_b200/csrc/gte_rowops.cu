@@ -256,6 +256,21 @@ __global__ void __launch_bounds__(RED_THREADS)
   out[i] = s;
 }
 
+// three reductions over one partial matrix [nb][3 * f] in one launch: out_k[i] (+)= sum_b partial[b * 3f + k * f + i]
+__global__ void __launch_bounds__(RED_THREADS)
+    k_reduce_partials3(const float* __restrict__ partial, int nb, int32_t f, float* __restrict__ out0, float* __restrict__ out1,
+                       float* __restrict__ out2, int accumulate) {
+  __shared__ float red[RED_THREADS];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int nout = (out2 ? 3 : 2) * f;
+  const bool valid = i < nout;
+  float s = reduce_partials_block(partial, nb, 3 * (int64_t)f, i, valid, red);
+  if ((threadIdx.x >> 5) != 0 || !valid) return;
+  float* out = i < f ? out0 + i : (i < 2 * f ? out1 + (i - f) : out2 + (i - 2 * f));
+  if (accumulate) s += *out;
+  *out = s;
+}
+
 static int ln_bwd_grid(int32_t n) {
   int64_t b = ceil_div64(n, ROW_WARPS);
   // 128 registers x 256 threads: two CTAs are resident per SM; one wave (measured 90 us vs 99 us with four CTAs per SM
@@ -599,16 +614,10 @@ int gte_layernorm_act_bwd(const float* dy, int64_t lddy, const float* z, int64_t
     GTE_CHECK_LAUNCH("k_layernorm_act_bwd");
   }
   const int nb = n > 0 ? grid : 0;
-  k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial, nb, 3 * (int64_t)f, f, dgamma, accumulate);
-  GTE_CHECK_LAUNCH("k_reduce_partials");
-  k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial + f, nb, 3 * (int64_t)f, f, dbeta,
-                                                                 accumulate);
-  GTE_CHECK_LAUNCH("k_reduce_partials");
-  if (dz_colsum) {
-    k_reduce_partials<<<(unsigned)ceil_div64(f, 32), RED_THREADS, 0, st>>>(partial + 2 * f, nb, 3 * (int64_t)f, f, dz_colsum,
-                                                                   accumulate);
-    GTE_CHECK_LAUNCH("k_reduce_partials");
-  }
+  // dgamma, dbeta and (optionally) the column sums of dz live side by side in every partial row: one launch
+  k_reduce_partials3<<<(unsigned)ceil_div64((dz_colsum ? 3 : 2) * (int64_t)f, 32), RED_THREADS, 0, st>>>(partial, nb, f, dgamma, dbeta,
+                                                                                                   dz_colsum, accumulate);
+  GTE_CHECK_LAUNCH("k_reduce_partials3");
   return GTE_OK;
 }
 

@@ -384,10 +384,14 @@ struct DwReduceArgs {
   int32_t accumulate;
 };
 
-// One thread per output element, rows fastest: consecutive threads read consecutive floats of the column-major partial
-// tiles (coalesced), each thread adds its <= 148 partials in ascending CTA order (fixed order => reproducible).
-__global__ void __launch_bounds__(256) k_umma_dw_reduce(const DwReduceArgs R) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// 32 consecutive output elements (rows fastest: consecutive threads read consecutive floats of the column-major partial
+// tiles) x 8 slices of the <= 148 partials per block; slice s adds partials s, s + 8, ... in ascending order, then slice 0
+// adds the slice sums in ascending order -- a fixed order, so the result is reproducible.
+constexpr int DWR_SLICES = 8;
+__global__ void __launch_bounds__(32 * DWR_SLICES) k_umma_dw_reduce(const DwReduceArgs R) {
+  __shared__ float red[DWR_SLICES][32];
+  const int ox = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  int64_t i = (int64_t)blockIdx.x * 32 + ox;
   int s = 0;
   bool valid = false;
   for (; s < R.nseg; ++s) {
@@ -398,30 +402,33 @@ __global__ void __launch_bounds__(256) k_umma_dw_reduce(const DwReduceArgs R) {
     }
     i -= cnt;
   }
-  if (!valid) return;
-  const int col = (int)(i / R.seg[s].nrows), row = (int)(i % R.seg[s].nrows);
-  const int prow = R.seg[s].prow0 + row, pcol = R.seg[s].pcol0 + col;
-  const int mt = prow >> 7, r = prow & 127;
-  int g = 0;
-  if (pcol >= R.grp_pcol0[1] && R.grp_ncols[1] > 0) g = 1;
-  const int c = pcol - R.grp_pcol0[g];
-  int sub = 0;
-  for (int k = 0; k < R.ipc; ++k)
-    if (R.item_g[k] == g && R.item_mt[k] == mt) sub = k;
-  const int nb = (R.grid - sub + R.ipc - 1) / R.ipc;  // CTAs sub, sub + ipc, ... hold the partials of this output tile
-  const float* p = R.partial + (int64_t)sub * R.tile_stride + (int64_t)c * 128 + r;
-  const int64_t stride = (int64_t)R.ipc * R.tile_stride;
+  int row = 0, col = 0;
   float v = 0.f;
-  int b = 0;
-  for (; b + 4 <= nb; b += 4) {  // four loads in flight, added in order
-    const float p0 = p[(int64_t)b * stride], p1 = p[(int64_t)(b + 1) * stride], p2 = p[(int64_t)(b + 2) * stride],
-                p3 = p[(int64_t)(b + 3) * stride];
-    v += p0; v += p1; v += p2; v += p3;
+  if (valid) {
+    col = (int)(i / R.seg[s].nrows);
+    row = (int)(i % R.seg[s].nrows);
+    const int prow = R.seg[s].prow0 + row, pcol = R.seg[s].pcol0 + col;
+    const int mt = prow >> 7, r = prow & 127;
+    int g = 0;
+    if (pcol >= R.grp_pcol0[1] && R.grp_ncols[1] > 0) g = 1;
+    const int c = pcol - R.grp_pcol0[g];
+    int sub = 0;
+    for (int k = 0; k < R.ipc; ++k)
+      if (R.item_g[k] == g && R.item_mt[k] == mt) sub = k;
+    const int nb = (R.grid - sub + R.ipc - 1) / R.ipc;  // CTAs sub, sub + ipc, ... hold the partials of this output tile
+    const float* p = R.partial + (int64_t)sub * R.tile_stride + (int64_t)c * 128 + r;
+    const int64_t stride = (int64_t)R.ipc * R.tile_stride;
+    for (int b = sy; b < nb; b += DWR_SLICES) v += p[(int64_t)b * stride];
   }
-  for (; b < nb; ++b) v += p[(int64_t)b * stride];
+  red[sy][ox] = v;
+  __syncthreads();
+  if (sy != 0 || !valid) return;
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < DWR_SLICES; ++k) t += red[k][ox];
   float* d = R.seg[s].dst + row * R.seg[s].stride_row + col * R.seg[s].stride_col;
-  if (R.accumulate) v += *d;
-  *d = v;
+  if (R.accumulate) t += *d;
+  *d = t;
 }
 
 constexpr int DW_CHUNK_ROWS_DEFAULT = 512;
@@ -486,7 +493,7 @@ static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
   int64_t total = 0;
   for (int s = 0; s < r.nseg; ++s) total += (int64_t)r.seg[s].nrows * r.seg[s].ncols;
   if (total > 0) {
-    k_umma_dw_reduce<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(r);
+    k_umma_dw_reduce<<<(unsigned)ceil_div64(total, 32), 32 * DWR_SLICES, 0, st>>>(r);
     GTE_CHECK_LAUNCH("k_umma_dw_reduce");
   }
   return GTE_OK;

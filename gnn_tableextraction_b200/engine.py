@@ -163,8 +163,8 @@ class SageTrainer:
         if self.world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
-    # The step in three kernel-only stages with the two collectives in between, so that under data
-    # parallelism each stage can be replayed from its own CUDA graph while NCCL runs eagerly.
+    # The step in kernel-only stages (forward + loss, backward, exchange + update): with the peer-memory exchange they
+    # are ONE CUDA graph; with the NCCL fallback the first two are captured and the collective + Adam run eagerly.
     def _stage_forward(self, g: PageGraphBatch, labels: torch.Tensor):
         logits, ctxs = self.forward(g, training=self.model.training)
         ops.cross_entropy_fwd(logits, labels, self.class_w, stats=self.stats)
