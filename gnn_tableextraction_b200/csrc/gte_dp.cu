@@ -38,12 +38,12 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 // peer memory must not be served from this SM's L1 (it holds last step's values of the same addresses)
 __device__ __forceinline__ float4 ld_peer_v4(const float* p) {
   float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ float ld_peer(const float* p) {
   float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 
@@ -88,15 +88,35 @@ __global__ void __launch_bounds__(DP_THREADS) k_dp_allreduce_adam(const DpArgs A
   }
 
   // ---- (2) one-shot all-reduce in rank order + Adam on the local replica ---------------------------------------------
-  if (tid == 0) {
+  // all peer loads of a batch are issued before the first one is used: one NVLink round trip, not `world` of them
+  if (tid < 32) {
+    float v = 0.f, w3 = 0.f;
+    if (tid < A.world) {
+      v = ld_peer(A.peer_grad[tid] + A.stats_off + 1);
+      if (blockIdx.x == 0) w3 = v;
+    }
+    // rank-order sum of the `world` values held by lanes 0..world-1 (fixed order: lane 0 adds them one by one)
     float den = 0.f;
-    for (int r = 0; r < A.world; ++r) den += ld_peer(A.peer_grad[r] + A.stats_off + 1);
-    s_den = den;
-  }
-  if (blockIdx.x == 0 && tid < 3) {  // global loss statistics for the caller
-    float s = 0.f;
-    for (int r = 0; r < A.world; ++r) s += ld_peer(A.peer_grad[r] + A.stats_off + tid);
-    A.stats_out[tid] = s;
+    for (int r = 0; r < A.world; ++r) den += __shfl_sync(0xffffffffu, v, r);
+    if (tid == 0) s_den = den;
+    if (blockIdx.x == 0) {  // global loss statistics for the caller
+      float a0 = 0.f, a2 = 0.f;
+      if (tid < A.world) {
+        a0 = ld_peer(A.peer_grad[tid] + A.stats_off);
+        a2 = ld_peer(A.peer_grad[tid] + A.stats_off + 2);
+      }
+      float s0 = 0.f, s2 = 0.f;
+      for (int r = 0; r < A.world; ++r) {
+        s0 += __shfl_sync(0xffffffffu, a0, r);
+        s2 += __shfl_sync(0xffffffffu, a2, r);
+      }
+      if (tid == 0) {
+        A.stats_out[0] = s0;
+        A.stats_out[1] = den;
+        A.stats_out[2] = s2;
+      }
+      (void)w3;
+    }
   }
   __syncthreads();
   const float den = s_den;
@@ -109,11 +129,14 @@ __global__ void __launch_bounds__(DP_THREADS) k_dp_allreduce_adam(const DpArgs A
     const float bc2_sqrt = (float)sqrt(bc2);
     const int64_t n4 = A.count >> 2;
     for (int64_t i = (int64_t)blockIdx.x * DP_THREADS + tid; i < n4; i += (int64_t)gridDim.x * DP_THREADS) {
-      float4 g = ld_peer_v4(A.peer_grad[0] + 4 * i);
-      for (int r = 1; r < A.world; ++r) {
-        const float4 q = ld_peer_v4(A.peer_grad[r] + 4 * i);
-        g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
-      }
+      float4 q[DP_MAX_WORLD];
+#pragma unroll
+      for (int r = 0; r < DP_MAX_WORLD; ++r)  // every peer's load in flight before the first add
+        if (r < A.world) q[r] = ld_peer_v4(A.peer_grad[r] + 4 * i);
+      float4 g = q[0];
+#pragma unroll
+      for (int r = 1; r < DP_MAX_WORLD; ++r)
+        if (r < A.world) { g.x += q[r].x; g.y += q[r].y; g.z += q[r].z; g.w += q[r].w; }
       float4 p = reinterpret_cast<float4*>(A.param)[i];
       float4 m = reinterpret_cast<float4*>(A.exp_avg)[i];
       float4 v = reinterpret_cast<float4*>(A.exp_avg_sq)[i];
