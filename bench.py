@@ -129,7 +129,8 @@ class OpTimer:
 
     NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "spmm_packed", "paged_pack_edges", "build_page_formats", "gram_stream", "wide_out", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
-             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2", "umma_linear_fwd_stacked", "umma_linear_bwd_data2"]
+             "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2", "umma_linear_fwd_stacked", "umma_linear_bwd_data2",
+             "umma_linear_fwd_comb", "umma_linear_bwd_data_comb", "umma_linear_bwd_weight_comb", "umma_linear_bwd_weight2_comb"]
 
     def __init__(self, ops, torch):
         self.ops, self.torch, self.rec, self.orig = ops, torch, [], {}
@@ -166,6 +167,14 @@ class OpTimer:
             return (name, int(a[0].shape[0]), 2 * int(a[0].shape[1]), int(a[2].shape[1]))
         if name == "umma_linear_fwd":
             return (name, int(a[0].shape[0]), int(a[2]) * (2 if a[1] is not None else 1), int(a[5]))
+        if name == "umma_linear_fwd_comb":  # (xc, fin, pack, bias, fo)
+            return (name, int(a[0].shape[0]), 32, int(a[4]))
+        if name == "umma_linear_bwd_data_comb":  # (dc, fo, pack, fin)
+            return (name, int(a[0].shape[0]), 32, int(a[3]))
+        if name == "umma_linear_bwd_weight_comb":  # (dz, xc, w, ...)
+            return (name, int(a[0].shape[0]), int(a[0].shape[1]), 32)
+        if name == "umma_linear_bwd_weight2_comb":  # (dc, fo, x, ...)
+            return (name, int(a[0].shape[0]), 32, int(a[2].shape[1]))
         if name == "umma_linear_bwd_data":
             return (name, int(a[0].shape[0]), int(a[0].shape[1]), int(a[2]) * int(a[3]))
         return (name,)
@@ -214,6 +223,12 @@ def op_cost(key):
     if n == "umma_linear_fwd_stacked":
         _, N, K, Fo = key
         return 4 * N * K + 4 * N * 32, 2 * N * K * Fo
+    if n == "umma_linear_fwd_comb":  # reads the [n, 32] operand, writes z and y
+        _, N, K, Fo = key
+        return 4 * N * K + 8 * N * Fo + 4 * K * Fo, 2 * N * K * Fo
+    if n in ("umma_linear_bwd_data_comb", "umma_linear_bwd_weight_comb", "umma_linear_bwd_weight2_comb"):
+        _, N, a, b = key
+        return 4 * N * (a + b) + 4 * a * b, 2 * N * a * b
     if n == "umma_linear_fwd":  # reads [h | ah], writes z and y
         _, N, K, Fo = key
         return 4 * N * K + 8 * N * Fo + 4 * K * Fo, 2 * N * K * Fo
@@ -235,27 +250,33 @@ def op_cost(key):
 
 def ncu_traffic(op_key):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind an op, from the committed
-    `ncu --set full` summary (profiles/r01_kernel_metrics.json, written by scripts/summarize_profiles.py from a
-    capture of this same workload).  None when no capture of that kernel at this size is on file."""
-    path = os.path.join(ROOT, "profiles", "r01_kernel_metrics.json")
+    `ncu --set full` summary (profiles/r02_kernel_metrics.json, written by scripts/summarize_profiles.py from a
+    capture of one step of this same workload).  None when no capture of that kernel at this size is on file."""
+    path = os.path.join(ROOT, "profiles", "r02_kernel_metrics.json")
     if not os.path.exists(path):
         return None
     try:
         m = json.load(open(path))
     except Exception:
         return None
-    name = op_key[0]
-    if name == "umma_linear_bwd_weight":
-        recs = [r for k, v in m.items() if k.startswith("k_umma_dw grid") for r in v]
-        want = max(recs, key=lambda r: r.get("time_us", 0)) if (recs and op_key[3] > 64) else None
-    elif name == "spmm":
-        recs = [r for k, v in m.items() if k.startswith("k_spmm_paged_pk<8, 2") for r in v
-                if r.get("capture", "").startswith("r01_spmm_cfg2")]
-        recs = sorted(recs, key=lambda r: r.get("dram_bytes", 0))
-        want = (recs[-1] if op_key[4] else recs[0]) if recs else None  # with addend = the larger traffic
-    else:
-        want = None
-    return None if want is None else {"bytes": want["dram_bytes"], "capture": "profiles/r01_kernel_metrics.json: " + want["capture"]}
+
+    def recs(prefix):
+        return sorted((r for k, v in m.items() if k.startswith(prefix) for r in v), key=lambda r: -r.get("time_us", 0))
+
+    name, want = op_key[0], None
+    if name == "umma_linear_bwd_weight" and op_key[3] > 64:
+        r = recs("k_umma_dw grid")
+        want = r[0] if r else None
+    elif name == "umma_linear_fwd" and op_key[2] > 64:  # hidden layer: the longest launch of the pair kernel
+        r = recs("k_umma_gemm_pair<1>")
+        want = r[0] if r else None
+    elif name == "umma_linear_bwd_data" and op_key[2] > 64:  # second longest (the stacked class forward is far shorter)
+        r = recs("k_umma_gemm_pair<1>")
+        want = r[1] if len(r) > 1 else None
+    elif name == "spmm" and op_key[2] > 64:
+        r = sorted(recs("k_spmm_paged_pk<8, 2"), key=lambda q: q.get("dram_bytes", 0))
+        want = (r[-1] if op_key[4] else r[0]) if r else None  # with addend = the larger traffic
+    return None if want is None else {"bytes": want["dram_bytes"], "capture": "profiles/r02_kernel_metrics.json: " + want["capture"]}
 
 
 # ------------------------------------------------------------- CPU arm -----

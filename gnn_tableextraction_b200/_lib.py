@@ -62,6 +62,10 @@ SIGNATURES = {
     "gte_umma_linear_bwd_weight": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, ci, i32, vp, sz, vp]),
     "gte_umma_bwd_weight2_workspace_bytes": (sz, [i32, i32, i32]),
     "gte_umma_linear_bwd_weight2": (ci, [vp, i64, vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, vp, ci, i32, vp, sz, vp]),
+    "gte_umma_linear_fwd_comb": (ci, [vp, i64, i32, vp, vp, vp, vp, f32, ci, ci, vp, i64, vp, i64, vp, vp, i32, i32, vp]),
+    "gte_umma_linear_bwd_data_comb": (ci, [vp, i64, i32, vp, vp, i64, i32, i32, vp]),
+    "gte_umma_linear_bwd_weight_comb": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, vp, ci, i32, vp, sz, vp]),
+    "gte_umma_linear_bwd_weight2_comb": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, vp, ci, i32, vp, sz, vp]),
     "gte_layernorm_act_fwd": (ci, [vp, i64, vp, vp, f32, ci, vp, i64, vp, vp, i32, i32, vp]),
     "gte_layernorm_act_bwd_workspace_bytes": (sz, [i32, i32]),
     "gte_layernorm_act_bwd": (ci, [vp, i64, vp, i64, vp, vp, vp, vp, ci, vp, i64, vp, vp, vp, ci, i32, i32, vp, sz, vp]),
@@ -82,7 +86,7 @@ SIGNATURES = {
     "gte_dp_allreduce_adam": (ci, [vp, vp, i32, i32, i64, i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp, vp]),
 }
 
-GTE_TUNE_UMMA_PAIR, GTE_TUNE_DW_PAIR = 0, 1
+GTE_TUNE_UMMA_PAIR, GTE_TUNE_DW_PAIR, GTE_TUNE_EPI_STORE = 0, 1, 2
 GTE_AGG_SUM, GTE_AGG_SUM_NORM, GTE_AGG_MEAN = 0, 1, 2
 GTE_NORM_INV_DEG_ZERO, GTE_NORM_INV_DEG_CLAMP = 0, 1
 GTE_LABEL_I64, GTE_LABEL_I32, GTE_LABEL_F32 = 0, 1, 2

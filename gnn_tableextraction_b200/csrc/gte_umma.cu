@@ -331,20 +331,41 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
 // half 0 = tf32 hi, half 1 = tf32(lo); zero padded.
 // stacked pack (narrow layers, fo <= 16, nseg == 2): Ps[half][32][Kp], row o = W[o, 0:fin] (self block),
 //            row 16+o = W[o, fin:2fin] (neighbour block): ONE pass over x gives [x Ws^T | x Wn^T] side by side.
+// combined packs (nseg == 2) for operands stored side by side in ONE 32-column matrix (columns [0, w) = self block,
+//            [16, 16+w) = neighbour block, the rest zero), so that the whole contraction is a single k-block:
+//   Pc[half][BN][32]   (fin <= 16)  Pc[o][k] = W[o, k] (k < fin), W[o, fin + k-16] (16 <= k < 16+fin)     z = [h|ah] W^T
+//   Pd[half][BNb][32]  (fo <= 16)   Pd[j][k] = W[k, j] (k < fo),  W[k-16, fin + j] (16 <= k < 16+fo)      dx = [dz|gq] W
 __global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
                             float* __restrict__ Pf, int32_t BN, int32_t Kp, float* __restrict__ Pb, int32_t BNb,
-                            int32_t Kpb, float* __restrict__ Ps) {
+                            int32_t Kpb, float* __restrict__ Ps, float* __restrict__ Pc, float* __restrict__ Pd) {
   const int64_t per_f = (int64_t)BN * Kp, per_b = (int64_t)BNb * Kpb;
   const int64_t total_f = (int64_t)nseg * per_f, total_b = (int64_t)nseg * per_b;
   const int64_t total_s = Ps ? (int64_t)32 * Kp : 0;
+  const int64_t total_c = Pc ? (int64_t)BN * 32 : 0;
+  const int64_t total_d = Pd ? (int64_t)BNb * 32 : 0;
+  const int64_t end_b = total_f + total_b, end_s = end_b + total_s, end_c = end_s + total_c;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < total_f + total_b + total_s; i += stride) {
+  for (; i < end_c + total_d; i += stride) {
     float w = 0.f;
     float* dst;
     int64_t half_stride;
-    if (i >= total_f + total_b) {
-      const int64_t r = i - total_f - total_b;
+    if (i >= end_c) {
+      const int64_t r = i - end_c;
+      const int j = (int)(r >> 5), k = (int)(r & 31);
+      const int o = k & 15, blk = k >> 4;
+      if (o < fo && j < fin) w = W[(int64_t)o * ldw + (int64_t)blk * fin + j];
+      dst = Pd + r;
+      half_stride = total_d;
+    } else if (i >= end_s) {
+      const int64_t r = i - end_s;
+      const int o = (int)(r >> 5), k = (int)(r & 31);
+      const int kk = k & 15, blk = k >> 4;
+      if (o < fo && kk < fin) w = W[(int64_t)o * ldw + (int64_t)blk * fin + kk];
+      dst = Pc + r;
+      half_stride = total_c;
+    } else if (i >= end_b) {
+      const int64_t r = i - end_b;
       const int row = (int)(r / Kp), k = (int)(r % Kp);
       const int o = row & 15, blk = row >> 4;
       if (o < fo && k < fin) w = W[(int64_t)o * ldw + (int64_t)blk * fin + k];
@@ -382,7 +403,11 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct PackDims {
   int BN, Kp, BNb, Kpb;
-  size_t fwd_floats, bwd_floats, stacked_floats;
+  size_t fwd_floats, bwd_floats, stacked_floats, combf_floats, combb_floats;
+  size_t off_stacked() const { return fwd_floats + bwd_floats; }
+  size_t off_combf() const { return off_stacked() + stacked_floats; }
+  size_t off_combb() const { return off_combf() + combf_floats; }
+  size_t total() const { return off_combb() + combb_floats; }
 };
 static PackDims pack_dims(int fo, int fin, int nseg) {
   PackDims d;
@@ -393,6 +418,8 @@ static PackDims pack_dims(int fo, int fin, int nseg) {
   d.fwd_floats = (size_t)nseg * PK_PLANES * d.BN * d.Kp;
   d.bwd_floats = (size_t)nseg * PK_PLANES * d.BNb * d.Kpb;
   d.stacked_floats = (fo <= 16 && nseg == 2) ? (size_t)PK_PLANES * 32 * d.Kp : 0;
+  d.combf_floats = (fin <= 16 && nseg == 2) ? (size_t)PK_PLANES * d.BN * 32 : 0;
+  d.combb_floats = (fo <= 16 && nseg == 2) ? (size_t)PK_PLANES * d.BNb * 32 : 0;
   return d;
 }
 
@@ -481,7 +508,7 @@ int gte_umma_supported(int32_t fo, int32_t fin) {
 size_t gte_umma_pack_bytes(int32_t fo, int32_t fin, int32_t nseg) {
   if (!gte_umma_supported(fo, fin) || nseg < 1 || nseg > 2) return 0;
   PackDims d = pack_dims(fo, fin, nseg);
-  return (d.fwd_floats + d.bwd_floats + d.stacked_floats) * 4;
+  return d.total() * 4;
 }
 
 int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg, float* pack,
@@ -491,10 +518,11 @@ int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, 
   if (!gte_umma_supported(fo, fin)) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_pack_weights: fo=%d fin=%d unsupported", fo, fin);
   GTE_CHECK_ARG(aligned16(pack), "gte_umma_pack_weights: pack buffer must be 16-byte aligned");
   PackDims d = pack_dims(fo, fin, nseg);
-  const int64_t total = (int64_t)nseg * ((int64_t)d.BN * d.Kp + (int64_t)d.BNb * d.Kpb) + (int64_t)d.stacked_floats / PK_PLANES;
+  const int64_t total = (int64_t)(d.total() / PK_PLANES);
   k_umma_pack<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
       W, ldw, fo, fin, nseg, pack, d.BN, d.Kp, pack + d.fwd_floats, d.BNb, d.Kpb,
-      d.stacked_floats ? pack + d.fwd_floats + d.bwd_floats : nullptr);
+      d.stacked_floats ? pack + d.off_stacked() : nullptr, d.combf_floats ? pack + d.off_combf() : nullptr,
+      d.combb_floats ? pack + d.off_combb() : nullptr);
   GTE_CHECK_LAUNCH("k_umma_pack");
   return GTE_OK;
 }
@@ -639,6 +667,82 @@ int gte_umma_linear_bwd_data2(const float* dz1, int64_t lddz1, const float* dz2,
     a.blo[0][s] = a.bhi[0][s] + per;
   }
   a.b_cols = d.Kpb;
+  a.out[0] = dx;
+  a.ldo[0] = lddx;
+  return launch_umma(a, as_stream(stream));
+}
+
+// Narrow-INPUT layer (fin <= 16, the input layer) on a combined operand: xc[n, 32] holds h in columns [0, fin) and
+// A_hat h in columns [16, 16+fin), every other column finite (they meet zero weights): z = [h | ah] W^T + b is a
+// single k-block instead of two segments of one k-block each; same epilogue as gte_umma_linear_fwd.
+int gte_umma_linear_fwd_comb(const float* xc, int64_t ldx, int32_t fin, const float* pack, const float* bias,
+                             const float* gamma, const float* beta, float eps, int relu, int fuse_ln, float* z,
+                             int64_t ldz, float* y, int64_t ldy, float* mean, float* rstd, int32_t n, int32_t fo,
+                             gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0, "gte_umma_linear_fwd_comb: negative n");
+  if (fin < 1 || fin > 16 || !gte_umma_supported(fo, fin))
+    return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_fwd_comb: fo=%d fin=%d unsupported (fin <= 16)", fo, fin);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(xc && pack && (z || y), "gte_umma_linear_fwd_comb: null argument (z may be NULL only when y is given)");
+  GTE_CHECK_ARG(!fuse_ln || (gamma && beta && mean && rstd && y), "gte_umma_linear_fwd_comb: fused LayerNorm needs gamma/beta/mean/rstd/y");
+  GTE_CHECK_ARG(aligned16(xc) && ldx % 4 == 0 && ldx >= 32, "gte_umma_linear_fwd_comb: xc must be 16-byte aligned with ld %% 4 == 0, ld >= 32");
+  GTE_CHECK_ARG((!z || ldz >= fo) && (!y || ldy >= fo), "gte_umma_linear_fwd_comb: output leading dimension < fo");
+  PackDims d = pack_dims(fo, fin, 2);
+  const float* pc = pack + d.off_combf();
+  UmmaArgs a{};
+  a.nseg = 1;
+  a.ngroups = 1;
+  a.M = n;
+  a.N = fo;
+  a.BN = d.BN;
+  a.kblocks[0] = 1;
+  int rc = make_map(&a.tmA[0], xc, n, 32, ldx, UM_BM);
+  if (rc) return rc;
+  a.bhi[0][0] = pc;
+  a.blo[0][0] = pc + (size_t)d.BN * 32;
+  a.b_cols = 32;
+  a.out[0] = z;
+  a.ldo[0] = ldz;
+  a.y = y;
+  a.ldy = ldy;
+  a.bias = bias;
+  a.bias_n = fo;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.mean = mean;
+  a.rstd = rstd;
+  a.eps = eps;
+  a.fuse_ln = fuse_ln ? 1 : 0;
+  a.relu = relu ? 1 : 0;
+  return launch_umma(a, as_stream(stream));
+}
+
+// Narrow-OUTPUT (class) layer backward on a combined operand: dc[n, 32] holds dz in columns [0, fo) and A_hat^T dz in
+// columns [16, 16+fo), every other column finite: dx = dz Ws + gq Wn as a single k-block (gte_umma_linear_bwd_data2
+// runs the same contraction as two segments).
+int gte_umma_linear_bwd_data_comb(const float* dc, int64_t lddc, int32_t fo, const float* pack, float* dx, int64_t lddx,
+                                  int32_t n, int32_t fin, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0, "gte_umma_linear_bwd_data_comb: negative n");
+  if (fo < 1 || fo > 16 || !gte_umma_supported(fo, fin))
+    return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_data_comb: fo=%d fin=%d unsupported (fo <= 16)", fo, fin);
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(dc && pack && dx, "gte_umma_linear_bwd_data_comb: null argument");
+  GTE_CHECK_ARG(aligned16(dc) && lddc % 4 == 0 && lddc >= 32, "gte_umma_linear_bwd_data_comb: dc must be 16-byte aligned with ld %% 4 == 0, ld >= 32");
+  GTE_CHECK_ARG(lddx >= fin, "gte_umma_linear_bwd_data_comb: output leading dimension < fin");
+  PackDims d = pack_dims(fo, fin, 2);
+  const float* pd = pack + d.off_combb();
+  UmmaArgs a{};
+  a.nseg = 1;
+  a.ngroups = 1;
+  a.M = n;
+  a.N = fin;
+  a.BN = d.BNb;
+  a.kblocks[0] = 1;
+  int rc = make_map(&a.tmA[0], dc, n, 32, lddc, UM_BM);
+  if (rc) return rc;
+  a.bhi[0][0] = pd;
+  a.blo[0][0] = pd + (size_t)d.BNb * 32;
+  a.b_cols = 32;
   a.out[0] = dx;
   a.ldo[0] = lddx;
   return launch_umma(a, as_stream(stream));

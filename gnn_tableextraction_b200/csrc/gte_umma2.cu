@@ -277,6 +277,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
       const bool store_z = P.out[grp] != nullptr && rows_live;
       const bool store_y = P.y != nullptr && rows_live;
       float x[32];
+      const int rows_valid = rows_live ? (int)min((int64_t)32, (int64_t)P.M - row0) : 0;
+      // one 32 x 32 chunk of this warp's rows to `dst` (z / dx or y): a TMA store of the swizzled tile, or the warp's
+      // own row-contiguous global stores (P.tma_store == 2)
+      auto put_chunk = [&](const CUtensorMap* map, float* dst, int64_t ld, int c) {
+#ifdef GTE_EXPERIMENTS
+        if (P.dbg & 2) return;  // timing experiment: no output stores
+#endif
+        if (P.tma_store == 2)
+          epi_store_chunk_lsu(stb, x, dst + row0 * ld + c * 32, ld, rows_valid, P.N - c * 32);
+        else
+          epi_store_chunk_tma(stb, nbuf, store_seq, x, map, c * 32, (int32_t)row0);
+      };
 #define load_chunk(c) epi_load_chunk<SPLIT>(t_base + (c) * 32, s_bias + (c) * 32, x)
       if (P.fuse_ln) {
         // pass 1: z leaves, and this warp's columns are summed around a shift (the mean of its first chunk), which
@@ -291,6 +303,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
             for (int j = 0; j < 32; ++j) s0 += (j < nv) ? x[j] : 0.f;
             shift = s0 / (float)nv;
           }
+#ifdef GTE_EXPERIMENTS
+          if (P.dbg & 8) { s1 += x[0]; s2 += x[1]; } else  // timing experiment: no statistics math
+#endif
           if (nv == 32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -306,7 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
               s2 = fmaf(d, d, s2);
             }
           }
-          if (store_z) epi_store_chunk_tma(stb, nbuf, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
+          if (store_z) put_chunk(&P.tmOut[grp], P.out[grp], P.ldo[grp], c);
         }
         float mh = 0.f, m2h = 0.f;
         if (my_n > 0.f) {
@@ -337,17 +352,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
         // pass 2: normalise + activation
         for (int c = c_beg; c < c_end; ++c) {
           load_chunk(c);
+#ifdef GTE_EXPERIMENTS
+          if (!(P.dbg & 4))  // timing experiment: no normalisation math
+#endif
           epi_norm_act(x, s_gamma + c * 32, s_beta + c * 32, true, P.relu != 0, mean, rstd);
-          if (store_y) epi_store_chunk_tma(stb, nbuf, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
+          if (store_y) put_chunk(&P.tmY, P.y, P.ldy, c);
         }
       } else {
         if (ew == 0 && lane == 0) stamp(t, 2);
         for (int c = c_beg; c < c_end; ++c) {
           load_chunk(c);
-          if (store_z) epi_store_chunk_tma(stb, nbuf, store_seq, x, &P.tmOut[grp], c * 32, (int32_t)row0);
+          if (store_z) put_chunk(&P.tmOut[grp], P.out[grp], P.ldo[grp], c);
           if (P.y != nullptr) {
             epi_norm_act(x, s_gamma + c * 32, s_beta + c * 32, false, P.relu != 0, 0.f, 1.f);
-            if (store_y) epi_store_chunk_tma(stb, nbuf, store_seq, x, &P.tmY, c * 32, (int32_t)row0);
+            if (store_y) put_chunk(&P.tmY, P.y, P.ldy, c);
           }
         }
       }
@@ -409,6 +427,7 @@ int launch_umma_pair(UmmaArgs& a, cudaStream_t st) {
   if (stages < 2) return fail(GTE_ERR_UNSUPPORTED, "k_umma_gemm_pair: BN=%d does not fit shared memory", a.BN);
   a.stages = stages;
   a.epi_bufs = epi_bufs;
+  if (tuning(GTE_TUNE_EPI_STORE) == 1) a.tma_store = 2;
   const size_t smem = 1024 + (size_t)u2_layout(a.BN, a.stages, a.epi_bufs).total;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_gemm_pair<true>), smem, "k_umma_gemm_pair")) return rc;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_gemm_pair<false>), smem, "k_umma_gemm_pair")) return rc;

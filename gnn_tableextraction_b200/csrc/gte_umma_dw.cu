@@ -683,4 +683,99 @@ int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz
   return dw_launch(a, r, as_stream(stream));
 }
 
+// Combined-operand forms: the two narrow blocks live side by side in ONE 32-column matrix (columns [0, w) and
+// [16, 16+w)), so the narrow side of the contraction is a single full-width TMA box instead of two short-row boxes.
+//
+// Narrow-x form (input layer): xc[n, 32] = [h | ah]:  dW[:, 0:w] (+)= dz^T xc[:, 0:w] ; dW[:, w:2w] (+)= dz^T xc[:, 16:16+w] ;
+// db (+)= colsum(dz) through the free column w (w < 16).
+int gte_umma_linear_bwd_weight_comb(const float* dz, int64_t lddz, int32_t fo, const float* xc, int64_t ldx, int32_t w,
+                                    float* dW, int64_t lddw, float* db, int accumulate, int32_t n, void* ws,
+                                    size_t ws_bytes, gte_stream_t stream) {
+  if (fo < 1 || fo > 256 || w < 1 || w > 16)
+    return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight_comb: fo=%d w=%d unsupported", fo, w);
+  GTE_CHECK_ARG(n >= 0 && dW && (n == 0 || (dz && xc)), "gte_umma_linear_bwd_weight_comb: bad argument");
+  GTE_CHECK_ARG(tma_ok(dz, lddz) && tma_ok(xc, ldx), "gte_umma_linear_bwd_weight_comb: operands must be 16-byte aligned with ld %% 4 == 0");
+  GTE_CHECK_ARG(lddz >= fo && ldx >= 32 && lddw >= 2 * (int64_t)w, "gte_umma_linear_bwd_weight_comb: leading dimension too small");
+  if (db && w >= 16) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight_comb: db needs w < 16 (no free padding column)");
+  const size_t need = dw_workspace_bytes(1);
+  if (ws == nullptr || ws_bytes < need)
+    return fail(GTE_ERR_WORKSPACE, "gte_umma_linear_bwd_weight_comb: workspace %zu < required %zu", ws_bytes, need);
+  DwArgs a{};
+  DwReduceArgs r{};
+  a.n = n;
+  const int mtiles = (fo + 127) / 128;
+  a.partial = static_cast<float*>(ws);
+  int b_blocked = 0;
+  if (n > 0) {
+    int rc = dw_make_map(&a.tmA[0], &a.a_blocked[0], dz, n, fo, lddz, 4);
+    if (rc) return rc;
+    rc = dw_make_map(&a.tmB[0], &b_blocked, xc, n, 32, ldx, 1);
+    if (rc) return rc;
+  }
+  DwGroup& G = a.grp[0];
+  G.a = 0; G.nboxes = 1; G.nruns = 1; G.pcol0 = 0; G.ones_b_col = db ? w : -1; G.ones_a_col = -1;
+  G.run[0] = DwRun{0, 0, 1, b_blocked};
+  a.max_boxes = 1;
+  a.items_per_chunk = 0;
+  for (int mt = 0; mt < mtiles; ++mt) {
+    a.item_g[a.items_per_chunk] = 0;
+    a.item_mt[a.items_per_chunk] = mt;
+    ++a.items_per_chunk;
+  }
+  r.partial = a.partial;
+  r.accumulate = accumulate;
+  r.nseg = 0;
+  r.seg[r.nseg++] = DwSeg{0, fo, 0, w, dW, lddw, 1};
+  r.seg[r.nseg++] = DwSeg{0, fo, 16, w, dW + w, lddw, 1};
+  if (db) r.seg[r.nseg++] = DwSeg{0, fo, w, 1, db, 1, 0};
+  return dw_launch(a, r, as_stream(stream));
+}
+
+// Narrow-dz form (class layer) on dc[n, 32] = [dz | gq]: A = x [n, k <= 256];
+//   dW[:, col1:col1+k] (+)= dc[:, 0:fo]^T x ; dW[:, col2:col2+k] (+)= dc[:, 16:16+fo]^T x ; db (+)= colsum(dc[:, 0:fo])
+int gte_umma_linear_bwd_weight2_comb(const float* dc, int64_t lddc, int32_t fo, const float* x, int64_t ldx, int32_t k,
+                                     float* dW, int64_t lddw, int32_t col1, int32_t col2, float* db, int accumulate,
+                                     int32_t n, void* ws, size_t ws_bytes, gte_stream_t stream) {
+  if (fo < 1 || fo > 16 || k < 1 || k > 256)
+    return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight2_comb: fo=%d k=%d unsupported", fo, k);
+  GTE_CHECK_ARG(n >= 0 && dW && (n == 0 || (dc && x)), "gte_umma_linear_bwd_weight2_comb: bad argument");
+  GTE_CHECK_ARG(tma_ok(dc, lddc) && tma_ok(x, ldx), "gte_umma_linear_bwd_weight2_comb: operands must be 16-byte aligned with ld %% 4 == 0");
+  GTE_CHECK_ARG(lddc >= 32 && ldx >= k && lddw >= (int64_t)col1 + k && lddw >= (int64_t)col2 + k,
+                "gte_umma_linear_bwd_weight2_comb: leading dimension too small");
+  const size_t need = dw_workspace_bytes(1);
+  if (ws == nullptr || ws_bytes < need)
+    return fail(GTE_ERR_WORKSPACE, "gte_umma_linear_bwd_weight2_comb: workspace %zu < required %zu", ws_bytes, need);
+  const bool db_fused = db != nullptr && (k % 128 != 0);
+  if (db && !db_fused) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight2_comb: db needs k %% 128 != 0");
+  DwArgs a{};
+  DwReduceArgs r{};
+  a.n = n;
+  const int mtiles = (k + (db_fused ? 1 : 0) + 127) / 128;
+  a.partial = static_cast<float*>(ws);
+  int b_blocked = 0;
+  if (n > 0) {
+    int rc = dw_make_map(&a.tmA[0], &a.a_blocked[0], x, n, k, ldx, 4);
+    if (rc) return rc;
+    rc = dw_make_map(&a.tmB[0], &b_blocked, dc, n, 32, lddc, 1);
+    if (rc) return rc;
+  }
+  DwGroup& G = a.grp[0];
+  G.a = 0; G.nboxes = 1; G.nruns = 1; G.pcol0 = 0; G.ones_b_col = -1; G.ones_a_col = db_fused ? k : -1;
+  G.run[0] = DwRun{0, 0, 1, b_blocked};
+  a.max_boxes = 1;
+  a.items_per_chunk = 0;
+  for (int mt = 0; mt < mtiles; ++mt) {
+    a.item_g[a.items_per_chunk] = 0;
+    a.item_mt[a.items_per_chunk] = mt;
+    ++a.items_per_chunk;
+  }
+  r.partial = a.partial;
+  r.accumulate = accumulate;
+  r.nseg = 0;
+  r.seg[r.nseg++] = DwSeg{0, k, 0, fo, dW + col1, 1, lddw};   // out[j][o] -> dW[o][col1 + j]
+  r.seg[r.nseg++] = DwSeg{0, k, 16, fo, dW + col2, 1, lddw};
+  if (db_fused) r.seg[r.nseg++] = DwSeg{k, 1, 0, fo, db, 0, 1};  // ones row: column sums of dz
+  return dw_launch(a, r, as_stream(stream));
+}
+
 }  // extern "C"

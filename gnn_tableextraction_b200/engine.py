@@ -146,7 +146,8 @@ class SageTrainer:
         self._rng_used = used
         return h, ctxs
 
-    def backward(self, g: PageGraphBatch, ctxs: List[L.LayerCtx], dlogits: torch.Tensor):
+    def backward(self, g: PageGraphBatch, ctxs: List[L.LayerCtx], dlogits: torch.Tensor,
+                 dy_comb: Optional[torch.Tensor] = None):
         dy = dlogits
         layers = list(self.model.layers)
         for i in range(len(layers) - 1, -1, -1):
@@ -157,7 +158,7 @@ class SageTrainer:
                 g, ctxs[i], dy, W, gamma, beta, gv[id(layer.linear.weight)],
                 None if layer.linear.bias is None else gv[id(layer.linear.bias)],
                 gv[id(layer.lynorm.weight)] if has_ln else None, gv[id(layer.lynorm.bias)] if has_ln else None,
-                need_dh=(i > 0), accumulate=False)
+                need_dh=(i > 0), accumulate=False, dy_comb=dy_comb if i == len(layers) - 1 else None)
 
     def _all_reduce(self, t: torch.Tensor):
         if self.world > 1:
@@ -172,8 +173,12 @@ class SageTrainer:
 
     def _stage_backward(self, g: PageGraphBatch, labels: torch.Tensor, logits, ctxs):
         den = self._one if self.dp_fused else self.stats[1:2]
-        dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, den)
-        self.backward(g, ctxs, dlogits)
+        dc = L.class_grad_buffer(ctxs[-1], logits.shape[0], logits.device)
+        if dc is not None:  # the class layer consumes [d logits | A_hat^T d logits] as one operand: write it in place
+            dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, den, out=ops.comb_views(dc, logits.shape[1])[0])
+        else:
+            dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, den)
+        self.backward(g, ctxs, dlogits, dy_comb=dc)
         if getattr(self, "_rng_used", 0) > 0:
             ops.rng_advance(self.rng_dev, self._rng_used)  # the next step (or graph replay) draws new masks
 

@@ -67,6 +67,7 @@ class LayerCtx:
     fin: int = 0
     fout: int = 0
     drop: Optional[DropoutSpec] = None  # the mask of [h | ah] is recomputed from this in the backward pass
+    comb: Optional[torch.Tensor] = None  # narrow input (fin <= 16): [h | ah] side by side in one [n, 32] operand
 
 
 def pick_strategy(fin: int, fout: int, use_pp: bool) -> str:
@@ -118,29 +119,46 @@ def _agg_mode(agg: str) -> int:
 
 
 def aggregate_forward(g: PageGraphBatch, h: torch.Tensor, w_edge: torch.Tensor, agg: str = GCN,
-                      addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      addend: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``update_all(u_mul_e, sum|mean)`` (+ ``* norm``): models.py:53-54,69-71,149."""
     if PAGE_FORMATS:
         g.prepare(w_edge)  # first call per batch: CSC + CSR + norm + packed edges in one kernel
     indptr, indices, _ = g.csc()
     if _use_packed(g, h, addend):
         return ops.spmm_packed(indptr, g.packed_edges("csc", w_edge), h, g.pages(), mode=_agg_mode(agg),
-                               row_norm=g.norm() if agg == GCN else None, addend=addend)
+                               row_norm=g.norm() if agg == GCN else None, addend=addend, out=out)
     return ops.spmm(indptr, indices, g.weights_csc(w_edge), h, mode=_agg_mode(agg),
-                    row_norm=g.norm() if agg == GCN else None, addend=addend, pages=g.pages())
+                    row_norm=g.norm() if agg == GCN else None, addend=addend, pages=g.pages(), out=out)
 
 
 def aggregate_backward(g: PageGraphBatch, d_out: torch.Tensor, w_edge: torch.Tensor,
-                       addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       addend: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """d h[u] = sum_{u->v} w_e * norm[v] * d_out[v] (+ addend[u]) on the CSR (reverse graph)."""
     if PAGE_FORMATS:
         g.prepare(w_edge)
     indptr, indices, _ = g.csr()
     if _use_packed(g, d_out, addend):
         return ops.spmm_packed(indptr, g.packed_edges("csr", w_edge), d_out, g.pages(), mode=_lib.GTE_AGG_SUM,
-                               addend=addend)
+                               addend=addend, out=out)
     return ops.spmm(indptr, indices, g.weights_csr(w_edge), d_out, mode=_lib.GTE_AGG_SUM, pre_scale=g.norm(),
-                    addend=addend, pages=g.pages())
+                    addend=addend, pages=g.pages(), out=out)
+
+
+COMB = os.environ.get("GTE_COMB", "1") != "0"  # combined [n, 32] operands for the narrow layers (0: two operands, A/B runs)
+
+
+def _comb_rows(n: int) -> bool:
+    return COMB and GEMM_MODE != "ffma" and (GEMM_MODE == "umma" or n >= UMMA_MIN_ROWS)
+
+
+def class_grad_buffer(ctx: "LayerCtx", n: int, device) -> Optional[torch.Tensor]:
+    """The class layer's backward wants its incoming gradient as the self block of a combined [n, 32] operand
+    (d logits | A_hat^T d logits): a caller that PRODUCES that gradient (the trainer's loss backward) writes it into
+    ``comb_views(buf, fout)[0]`` of the buffer returned here and passes the buffer as ``dy_comb``.  None: not wanted."""
+    if (ctx.strategy == "proj" and not ctx.ln and not ctx.relu and ctx.fout <= ops.COMB_W and ctx.pack is not None
+            and _comb_rows(n) and ctx.fin <= 256 and ops._aligned_mat(ctx.h)):
+        return ops.comb_buffer(n, device)
+    return None
 
 
 def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Optional[torch.Tensor],
@@ -159,8 +177,16 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
     drop = dropout if (dropout is not None and dropout.active()) else None
     if drop is not None and st == "proj":
         st = "agg"  # the mask acts on [h | ah]: aggregate first
-    if GEMM_MODE != "ffma" and h.shape[0] >= UMMA_MIN_ROWS and not ops._aligned_mat(h):
-        # e.g. the raw [N, 13] BBOX features: one padded copy gives 16-byte aligned rows for TMA / 128-bit loads
+    xc = ahs = None
+    if st == "agg" and fin <= ops.COMB_W and _comb_rows(h.shape[0]) and ops.umma_supported(fout, fin):
+        # narrow input (the [N, 13] BBOX features): h and A_hat h side by side in one zero-padded [n, 32] operand --
+        # aligned rows for the gather, ONE k-block for the projection, one full-row TMA box for the weight gradient
+        xc = ops.comb_buffer(h.shape[0], h.device)
+        hs, ahs = ops.comb_views(xc, fin)
+        hs.copy_(h)
+        h = hs
+    elif GEMM_MODE != "ffma" and h.shape[0] >= UMMA_MIN_ROWS and not ops._aligned_mat(h):
+        # unaligned rows: one padded copy gives 16-byte aligned rows for TMA / 128-bit loads
         hp = ops.empty_padded(h.shape[0], h.shape[1], h.device)
         hp.copy_(h)
         h = hp
@@ -171,12 +197,23 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
             ctx.h = h
         z = ops.linear_fwd(h, None, W, b)
     elif st == "agg":
-        ah = aggregate_forward(g, h, w_edge, agg)
+        ah = aggregate_forward(g, h, w_edge, agg, out=ahs)
         if drop is not None:
             # the dropped operands are what the linear (and, in backward, dW) sees; d[h | ah] gets the same mask back
-            h, ah = ops.dropout_concat(h, ah, drop.p, drop.seed, drop.offset, drop.rng_dev)
+            outs = None
+            if xc is not None:
+                xc = ops.comb_buffer(h.shape[0], h.device)
+                outs = ops.comb_views(xc, fin)
+            h, ah = ops.dropout_concat(h, ah, drop.p, drop.seed, drop.offset, drop.rng_dev, out=outs)
             ctx.h = h
         ctx.ah = ah
+        if xc is not None:
+            ctx.comb = xc
+            ctx.pack = ops.umma_pack_weights(W, fin, 2)
+            z, y, ctx.mean, ctx.rstd = ops.umma_linear_fwd_comb(xc, fin, ctx.pack, b, fout, gamma=gamma, beta=beta,
+                                                                eps=eps, relu=relu, fuse_ln=ln, want_z=save_for_backward)
+            ctx.z = z
+            return (y if y is not None else z), ctx
         if use_umma(h.shape[0], fin, fout, h, ah):
             # tensor cores: projection + bias + LayerNorm + ReLU in one kernel
             ctx.pack = ops.umma_pack_weights(W, fin, 2)
@@ -216,8 +253,10 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
 def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Tensor, W: torch.Tensor,
                         gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], dW: torch.Tensor,
                         db: Optional[torch.Tensor], dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor],
-                        *, need_dh: bool, accumulate: bool = False) -> Optional[torch.Tensor]:
-    """Writes dW/db/dgamma/dbeta (overwrite or accumulate) and returns dh (or None)."""
+                        *, need_dh: bool, accumulate: bool = False,
+                        dy_comb: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Writes dW/db/dgamma/dbeta (overwrite or accumulate) and returns dh (or None).  ``dy_comb``: the buffer from
+    class_grad_buffer() whose self block IS ``dy`` (saves one copy of the class-layer gradient)."""
     fin, fout = ctx.fin, ctx.fout
     if ctx.ln:
         # the linear-bias gradient (column sums of dz) falls out of the same pass
@@ -238,7 +277,9 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
             ops.dropout_concat(dh, None, drop.p, drop.seed, drop.offset, drop.rng_dev, inplace=True)
         return dh
     if ctx.strategy == "agg":
-        if use_umma_dw(dz.shape[0], fout, fin, fin, db is not None, dz, ctx.h, ctx.ah):
+        if ctx.comb is not None and ops._aligned_mat(dz) and fout <= 256 and (db is None or fin < ops.COMB_W):
+            ops.umma_linear_bwd_weight_comb(dz, ctx.comb, fin, dW, db, accumulate)
+        elif use_umma_dw(dz.shape[0], fout, fin, fin, db is not None, dz, ctx.h, ctx.ah):
             ops.umma_linear_bwd_weight(dz, ctx.h, ctx.ah, dW, db, accumulate)
         elif (db is None and 2 * fin <= 32 and dz.shape[0] >= SKINNY_MIN_ROWS and dW.stride(1) == 1
               and ops.gram_stream_supported(fout, 2 * fin, dz, ctx.h, ctx.ah)):
@@ -258,6 +299,15 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
         return aggregate_backward(g, d_ah, ctx.w_edge, addend=d_self)
     # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
     #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn
+    dc = dy_comb if dy_comb is not None else class_grad_buffer(ctx, dz.shape[0], dz.device)
+    if dc is not None and (db is None or fin % 128 != 0):
+        # [dz | A_hat^T dz] side by side: one full-row TMA box for the weight gradient, one k-block for dh
+        dzv, gqv = ops.comb_views(dc, fout)
+        if dy_comb is None:
+            dzv.copy_(dz)
+        aggregate_backward(g, dzv, ctx.w_edge, out=gqv)
+        ops.umma_linear_bwd_weight2_comb(dc, fout, ctx.h, dW, 0, fin, db, accumulate)
+        return ops.umma_linear_bwd_data_comb(dc, fout, ctx.pack, fin) if need_dh else None
     gq = aggregate_backward(g, dz, ctx.w_edge)
     if (2 * fout <= 32 and dz.shape[0] >= SKINNY_MIN_ROWS and dW.stride(1) == 1 and GEMM_MODE != "umma"
             and ops.gram_stream_supported(fin, 2 * fout, ctx.h, dz, gq)):

@@ -563,6 +563,96 @@ def umma_linear_bwd_weight2(dz1, dz2, x, dW, col1: int, col2: int, db, accumulat
     )
 
 
+# -- combined [n, 32] operands (columns [0, w) = self block, [16, 16+w) = neighbour block, the rest zero) --------
+COMB_W = 16   # widest block a combined operand can hold
+COMB_LD = 32
+
+
+def comb_buffer(n: int, device) -> torch.Tensor:
+    """Zeroed [n, 32] combined operand (the padding columns meet zero weights, so they must be finite)."""
+    return torch.zeros((n, COMB_LD), dtype=torch.float32, device=device)
+
+
+def comb_views(buf: torch.Tensor, w: int):
+    """(self block, neighbour block) column views of a combined operand."""
+    return buf[:, :w], buf[:, COMB_W:COMB_W + w]
+
+
+def _comb(buf, what):
+    if not (buf.is_cuda and buf.dtype == torch.float32 and buf.dim() == 2 and buf.shape[1] == COMB_LD
+            and buf.stride(1) == 1 and buf.stride(0) % 4 == 0 and buf.data_ptr() % 16 == 0):
+        raise GteError(f"{what}: a combined operand is a float32 [n, {COMB_LD}] CUDA matrix, 16-byte aligned")
+    return buf.data_ptr(), buf.stride(0)
+
+
+def umma_linear_fwd_comb(xc, fin: int, pack, bias, fo: int, *, gamma=None, beta=None, eps: float = 1e-5,
+                         relu: bool = False, fuse_ln: bool = False, want_y: bool = False, want_z: bool = True):
+    """umma_linear_fwd for a narrow input (fin <= 16) held as one combined operand xc = [h | A_hat h]."""
+    xp, ldx = _comb(xc, "umma_linear_fwd_comb.xc")
+    n = xc.shape[0]
+    dev = xc.device
+    need_y = fuse_ln or want_y or relu
+    z = empty_padded(n, fo, dev) if (want_z or not need_y) else None
+    zp, ldz = (None, 0) if z is None else _mat(z, "umma.z")[:2]
+    y = empty_padded(n, fo, dev) if need_y else None
+    yp, ldy = (None, 0) if y is None else _mat(y, "umma.y")[:2]
+    mean = torch.empty(n, dtype=torch.float32, device=dev) if fuse_ln else None
+    rstd = torch.empty(n, dtype=torch.float32, device=dev) if fuse_ln else None
+    check(
+        lib().gte_umma_linear_fwd_comb(xp, ldx, fin, _vec(pack, "pack"), _vec(bias, "bias", n=fo),
+                                       _vec(gamma, "gamma", n=fo), _vec(beta, "beta", n=fo), float(eps),
+                                       1 if relu else 0, 1 if fuse_ln else 0, zp, ldz, yp, ldy, _ptr(mean), _ptr(rstd),
+                                       n, fo, _stream()),
+        "gte_umma_linear_fwd_comb",
+    )
+    return z, y, mean, rstd
+
+
+def umma_linear_bwd_data_comb(dc, fo: int, pack, fin: int):
+    """dx = dc[:, :fo] W[:, :fin] + dc[:, 16:16+fo] W[:, fin:2 fin] (class layer; dc = [dz | A_hat^T dz])."""
+    dp, ldd = _comb(dc, "umma_linear_bwd_data_comb.dc")
+    n = dc.shape[0]
+    dx = empty_padded(n, fin, dc.device)
+    dxp, lddx, _ = _mat(dx, "umma_bwd_comb.dx")
+    check(lib().gte_umma_linear_bwd_data_comb(dp, ldd, fo, _vec(pack, "pack"), dxp, lddx, n, fin, _stream()),
+          "gte_umma_linear_bwd_data_comb")
+    return dx
+
+
+def umma_linear_bwd_weight_comb(dz, xc, w: int, dW, db, accumulate=False):
+    """dW[:, :w] (+)= dz^T xc[:, :w] ; dW[:, w:2w] (+)= dz^T xc[:, 16:16+w] ; db (+)= colsum(dz) (w < 16)."""
+    dzp, lddz, fo = _mat(dz, "umma_dw_comb.dz")
+    xp, ldx = _comb(xc, "umma_linear_bwd_weight_comb.xc")
+    dWp, lddw, kw = _mat(dW, "umma_dw_comb.dW")
+    n = dz.shape[0]
+    if dW.shape[0] != fo or 2 * w > kw or xc.shape[0] != n:
+        raise GteError("umma_linear_bwd_weight_comb: shape mismatch")
+    l = lib()
+    ws = workspace(l.gte_umma_bwd_weight_workspace_bytes(n, fo, COMB_LD, 0), dz.device)
+    check(
+        l.gte_umma_linear_bwd_weight_comb(dzp, lddz, fo, xp, ldx, w, dWp, lddw, _vec(db, "db", n=fo),
+                                          1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),
+        "gte_umma_linear_bwd_weight_comb",
+    )
+
+
+def umma_linear_bwd_weight2_comb(dc, fo: int, x, dW, col1: int, col2: int, db, accumulate=False):
+    """dW[:, col1:+k] (+)= dc[:, :fo]^T x ; dW[:, col2:+k] (+)= dc[:, 16:16+fo]^T x ; db (+)= colsum(dc[:, :fo])."""
+    dp, ldd = _comb(dc, "umma_linear_bwd_weight2_comb.dc")
+    xp, ldx, k = _mat(x, "umma_dw2_comb.x")
+    dWp, lddw, kw = _mat(dW, "umma_dw2_comb.dW")
+    n = dc.shape[0]
+    if dW.shape[0] != fo or max(col1, col2) + k > kw or x.shape[0] != n:
+        raise GteError("umma_linear_bwd_weight2_comb: shape mismatch")
+    l = lib()
+    ws = workspace(l.gte_umma_bwd_weight2_workspace_bytes(n, fo, k), dc.device)
+    check(
+        l.gte_umma_linear_bwd_weight2_comb(dp, ldd, fo, xp, ldx, k, dWp, lddw, col1, col2, _vec(db, "db", n=fo),
+                                           1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),
+        "gte_umma_linear_bwd_weight2_comb",
+    )
+
+
 # ---------------------------------------------------------------- row ops ---
 def layernorm_act_fwd(z, gamma, beta, eps: float, relu: bool, out=None):
     zp, ldz, f = _mat(z, "ln.z")
@@ -624,7 +714,7 @@ def relu_l2norm_bwd(dy, z, eps: float = 1e-12, out=None):
 
 
 def dropout_concat(x1, x2, p: float, seed: int = 0, offset: int = 0, rng_dev: Optional[torch.Tensor] = None,
-                   inplace: bool = False):
+                   inplace: bool = False, out=None):
     """Training-mode ``nn.Dropout(p)`` on the concatenation ``[x1 | x2]`` without materialising it (models.py:60-61);
     ``x2`` may be None (input features, models.py:113).  Returns (y1, y2).  The mask depends only on
     (seed, offset, element index): call it again on the gradients with the same arguments for the backward pass."""
@@ -635,8 +725,11 @@ def dropout_concat(x1, x2, p: float, seed: int = 0, offset: int = 0, rng_dev: Op
         x2p, ld2, f2 = _mat(x2, "dropout.x2")
         if x2.shape[0] != n:
             raise GteError("dropout_concat: row mismatch")
-    y1 = x1 if inplace else empty_padded(n, f1, x1.device)
-    y2 = None if x2 is None else (x2 if inplace else empty_padded(n, f2, x1.device))
+    if out is not None:
+        y1, y2 = out
+    else:
+        y1 = x1 if inplace else empty_padded(n, f1, x1.device)
+        y2 = None if x2 is None else (x2 if inplace else empty_padded(n, f2, x1.device))
     y1p, ldy1, _ = _mat(y1, "dropout.y1")
     y2p, ldy2 = (None, 0) if y2 is None else _mat(y2, "dropout.y2")[:2]
     check(lib().gte_dropout_concat(x1p, ld1, f1, x2p, ld2, f2, n, float(p), int(seed) & (2 ** 64 - 1), int(offset),

@@ -74,10 +74,13 @@ int64_t gte_launch_count(void);
  *   GTE_TUNE_UMMA_PAIR   1 (default): tensor-core projections run on CTA pairs (tcgen05 cta_group::2) when the shape
  *                        allows it; 0: always the single-CTA kernel
  *   GTE_TUNE_DW_PAIR     same for the tensor-core weight gradients
+ *   GTE_TUNE_EPI_STORE   0 (default): the pair kernel's epilogue leaves through TMA stores; 1: through the epilogue
+ *                        warps' own row-contiguous 128-bit global stores
  */
 #define GTE_TUNE_UMMA_PAIR 0
 #define GTE_TUNE_DW_PAIR 1
-#define GTE_TUNE_COUNT 2
+#define GTE_TUNE_EPI_STORE 2
+#define GTE_TUNE_COUNT 3
 int gte_set_tuning(int key, int value);
 int gte_get_tuning(int key);
 /* SM count and compute capability of the current device. */
@@ -345,6 +348,37 @@ int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz
                                 int32_t fo, const float* x, int64_t ldx, int32_t k, float* dW,
                                 int64_t lddw, int32_t col1, int32_t col2, float* db, int accumulate,
                                 int32_t n, void* ws, size_t ws_bytes, gte_stream_t stream);
+
+/*
+ * Combined-operand forms for the narrow sides of the model (the 13-wide input layer, the 9-wide class
+ * layer): the self block and the neighbour block live side by side in ONE [n, 32] matrix, columns
+ * [0, w) and [16, 16+w), every other column FINITE (zero): the narrow side of each contraction is then
+ * a single k-block / a single full-row TMA box.  Same results contract as the two-operand forms they
+ * replace (models.py:47-62 with `pool` aggregation; concat order self | neighbour):
+ *   fwd_comb          (fin <= 16)  z = [xc[:, :fin] | xc[:, 16:16+fin]] W^T + b, epilogue as gte_umma_linear_fwd
+ *   bwd_data_comb     (fo  <= 16)  dx = dc[:, :fo] W[:, :fin] + dc[:, 16:16+fo] W[:, fin:2 fin]
+ *   bwd_weight_comb   (w   <= 16)  dW[:, :w] (+)= dz^T xc[:, :w] ; dW[:, w:2w] (+)= dz^T xc[:, 16:16+w] ;
+ *                                  db (+)= colsum(dz) (needs w < 16)
+ *   bwd_weight2_comb  (fo  <= 16)  dW[:, col1:col1+k] (+)= dc[:, :fo]^T x ; dW[:, col2:col2+k] (+)=
+ *                                  dc[:, 16:16+fo]^T x ; db (+)= colsum(dc[:, :fo]) (needs k % 128 != 0)
+ * pack = gte_umma_pack_weights(..., nseg = 2) of the same W.  Workspace: the *_workspace_bytes of the
+ * two-operand forms is sufficient.
+ */
+int gte_umma_linear_fwd_comb(const float* xc, int64_t ldx, int32_t fin, const float* pack,
+                             const float* bias, const float* gamma, const float* beta, float eps,
+                             int relu, int fuse_ln, float* z, int64_t ldz, float* y, int64_t ldy,
+                             float* mean, float* rstd, int32_t n, int32_t fo, gte_stream_t stream);
+int gte_umma_linear_bwd_data_comb(const float* dc, int64_t lddc, int32_t fo, const float* pack,
+                                  float* dx, int64_t lddx, int32_t n, int32_t fin,
+                                  gte_stream_t stream);
+int gte_umma_linear_bwd_weight_comb(const float* dz, int64_t lddz, int32_t fo, const float* xc,
+                                    int64_t ldx, int32_t w, float* dW, int64_t lddw, float* db,
+                                    int accumulate, int32_t n, void* ws, size_t ws_bytes,
+                                    gte_stream_t stream);
+int gte_umma_linear_bwd_weight2_comb(const float* dc, int64_t lddc, int32_t fo, const float* x,
+                                     int64_t ldx, int32_t k, float* dW, int64_t lddw, int32_t col1,
+                                     int32_t col2, float* db, int accumulate, int32_t n, void* ws,
+                                     size_t ws_bytes, gte_stream_t stream);
 
 /* ------------------------------------------- row normalisation + act ---- */
 /*

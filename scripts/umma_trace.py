@@ -40,3 +40,6 @@ a0 = ops.empty_padded(n, 13, DEV); a0.normal_()
 W0 = torch.randn(218, 26, device=DEV) * 0.2
 p0 = ops.umma_pack_weights(W0, 13, 2)
 run("fwd 26->218 LN", lambda: ops.umma_linear_fwd(f, a0, 13, p0, b, 218, gamma=g, beta=be, relu=True, fuse_ln=True))
+xc = ops.comb_buffer(n, DEV)
+xc[:, :13].normal_(); xc[:, 16:29].normal_()
+run("fwd comb 32->218 LN", lambda: ops.umma_linear_fwd_comb(xc, 13, p0, b, 218, gamma=g, beta=be, relu=True, fuse_ln=True))

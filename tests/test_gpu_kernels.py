@@ -582,6 +582,77 @@ def test_umma_input_layer_narrow_k(umma_kernel):
     assert rel_err(z, z64) < 3e-6 and rel_err(y, y64) < 5e-6
 
 
+def _comb(a, b):
+    """[n, 32] combined operand: a in columns [0, w), b in [16, 16+w), zeros elsewhere"""
+    buf = ops.comb_buffer(a.shape[0], DEV)
+    va, vb = ops.comb_views(buf, a.shape[1])
+    va.copy_(a)
+    vb.copy_(b)
+    return buf
+
+
+@pytest.mark.parametrize("n,fin,fo", [(1500, 13, 218), (129, 16, 64), (40000, 13, 218), (7, 1, 256)])
+def test_umma_comb_input_layer_forms(n, fin, fo, umma_kernel):
+    """combined [h | ah] operand (narrow input): forward = the two-operand forward bit for bit (same products, one
+    k-block instead of two); weight gradient + bias gradient vs fp64"""
+    gen = torch.Generator().manual_seed(n + fin)
+    h = torch.randn(n, fin, generator=gen) * 50
+    ah = torch.randn(n, fin, generator=gen) * 30 + 3
+    W = (torch.rand(fo, 2 * fin, generator=gen) - 0.5) * (2 / (2 * fin) ** 0.5)
+    b = torch.randn(fo, generator=gen) * 0.1
+    gamma, beta = torch.rand(fo, generator=gen) + 0.5, torch.randn(fo, generator=gen) * 0.1
+    pack = ops.umma_pack_weights(W.to(DEV), fin, 2)
+    xc = _comb(h, ah)
+    kw = dict(gamma=gamma.to(DEV), beta=beta.to(DEV), relu=True, fuse_ln=True)
+    z, y, mean, rstd = ops.umma_linear_fwd_comb(xc, fin, pack, b.to(DEV), fo, **kw)
+    z64 = torch.cat([h, ah], 1).double() @ W.double().t() + b.double()
+    y64 = F.relu(F.layer_norm(z64, (fo,), gamma.double(), beta.double(), 1e-5))
+    assert rel_err(z, z64) < 3e-6 and rel_err(y, y64) < 5e-6
+    z2, y2, _, _ = ops.umma_linear_fwd(_padded(h), _padded(ah), fin, pack, b.to(DEV), fo, **kw)
+    _log_err(f"fwd_comb n={n} fin={fin} fo={fo}: z={rel_err(z, z64):.2e} two-operand z", rel_err(z2, z64))
+    # y only (inference)
+    zi, yi, _, _ = ops.umma_linear_fwd_comb(xc, fin, pack, b.to(DEV), fo, want_z=False, **kw)
+    assert zi is None and torch.equal(yi, y)
+    # weight gradient
+    dz = torch.randn(n, fo, generator=gen)
+    dW = torch.full((fo, 2 * fin), 5.0, device=DEV)
+    db = torch.full((fo,), 5.0, device=DEV) if fin < 16 else None
+    ops.umma_linear_bwd_weight_comb(_padded(dz), xc, fin, dW, db)
+    ref = dz.double().t() @ torch.cat([h, ah], 1).double()
+    assert rel_err(dW, ref) < 3e-6
+    if db is not None:
+        assert rel_err(db, dz.double().sum(0)) < 3e-6
+    dW2 = torch.empty_like(dW)
+    ops.umma_linear_bwd_weight_comb(_padded(dz), xc, fin, dW2, None)
+    assert torch.equal(dW2, dW)  # deterministic
+    ops.umma_linear_bwd_weight_comb(_padded(dz), xc, fin, dW2, None, accumulate=True)
+    assert rel_err(dW2, 2 * ref) < 3e-6
+
+
+@pytest.mark.parametrize("n,fin,fo", [(3000, 218, 9), (40000, 218, 9), (200, 100, 16), (5, 255, 1)])
+def test_umma_comb_class_layer_forms(n, fin, fo, umma_kernel):
+    """combined [dz | A^T dz] operand (narrow output): input gradient and weight / bias gradients vs fp64"""
+    gen = torch.Generator().manual_seed(n + fo)
+    x = torch.randn(n, fin, generator=gen)
+    W = (torch.rand(fo, 2 * fin, generator=gen) - 0.5) * 0.1
+    dz, gq = torch.randn(n, fo, generator=gen), torch.randn(n, fo, generator=gen) * 2
+    pack = ops.umma_pack_weights(W.to(DEV), fin, 2)
+    dc = _comb(dz, gq)
+    dx = ops.umma_linear_bwd_data_comb(dc, fo, pack, fin)
+    ref = dz.double() @ W.double()[:, :fin] + gq.double() @ W.double()[:, fin:]
+    assert dx.shape == (n, fin) and rel_err(dx, ref) < 3e-6
+    dW = torch.full((fo, 2 * fin), 3.0, device=DEV)
+    db = torch.full((fo,), 3.0, device=DEV)
+    ops.umma_linear_bwd_weight2_comb(dc, fo, _padded(x), dW, 0, fin, db)
+    e1, e2 = rel_err(dW[:, :fin], dz.double().t() @ x.double()), rel_err(dW[:, fin:], gq.double().t() @ x.double())
+    _log_err(f"bwd_weight2_comb n={n} fo={fo} k={fin}: e1={e1:.2e} e2", e2)
+    assert e1 < 3e-6 and e2 < 3e-6
+    assert rel_err(db, dz.double().sum(0)) < 3e-6
+    dW2 = torch.full_like(dW, 1.0)
+    ops.umma_linear_bwd_weight2_comb(dc, fo, _padded(x), dW2, 0, fin, None, accumulate=True)
+    assert rel_err(dW2 - 1.0, torch.cat([dz.double().t() @ x.double(), gq.double().t() @ x.double()], 1)) < 1e-5
+
+
 # ------------------------------------------------- narrow dense streams ----
 @pytest.mark.parametrize("n,wide,nq1,nq2", [(5000, 218, 13, 13), (3001, 218, 9, 9), (2, 7, 3, 0), (777, 256, 16, 16),
                                             (40000, 218, 13, 13), (64, 100, 1, 0), (2049, 33, 5, 2)])

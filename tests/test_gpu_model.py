@@ -368,14 +368,21 @@ def test_tensor_core_route_matches_reference_golden(name, paged, monkeypatch, um
         g.ndata["label"] = t(d["label"], torch.float32)
     else:
         g = _cuda_graph(d)
-    calls = _spy(monkeypatch, ["umma_linear_fwd", "umma_linear_bwd_data", "umma_linear_bwd_weight", "spmm_packed"])
+    calls = _spy(monkeypatch, ["umma_linear_fwd", "umma_linear_bwd_data", "umma_linear_bwd_weight", "spmm_packed",
+                               "umma_linear_fwd_comb", "umma_linear_bwd_weight_comb", "umma_linear_bwd_weight2_comb",
+                               "umma_linear_bwd_data_comb", "umma_linear_fwd_stacked"])
     logits, masks = cuda_forward_with_masks(model, g)
     assert rel_err(logits, d["logits"]) < TOL
     cw = torch.from_numpy(d["class_w"]).to(DEV) if "class_w" in d else None
     loss = gte.CrossEntropyLoss(weight=cw)(logits, g.ndata["label"])
     assert abs(loss.item() - float(d["loss"])) < TOL * max(1.0, abs(float(d["loss"])))
     loss.backward()
-    assert calls["umma_linear_fwd"] >= nl - 1 and calls["umma_linear_bwd_weight"] >= nl - 1 and calls["umma_linear_bwd_data"] >= 1
+    # input layer: combined [h | ah] operand; hidden layers: two-operand forms; class layer: stacked forward and the
+    # combined [dz | A^T dz] operand in backward -- every projection and weight gradient on the tensor cores
+    assert calls["umma_linear_fwd_comb"] == 1 and calls["umma_linear_bwd_weight_comb"] == 1
+    nh = len(model.layers) - 2  # hidden layers
+    assert nh >= 1 and calls["umma_linear_fwd"] == nh and calls["umma_linear_bwd_weight"] == nh and calls["umma_linear_bwd_data"] == nh
+    assert calls["umma_linear_fwd_stacked"] == 1 and calls["umma_linear_bwd_weight2_comb"] == 1 and calls["umma_linear_bwd_data_comb"] == 1
     assert (calls["spmm_packed"] > 0) == paged
     if paged:
         g.check_page_structure()
