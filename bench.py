@@ -507,12 +507,18 @@ def run_ours(args):
         # dominant kernel
         dkey, (dms, dcnt) = max(tab.items(), key=lambda kv: kv[1][0] * kv[1][1])
         b, fl = op_cost(dkey)
-        hbm_t, tensor_peak = b / (pk["hbm_gbs"] * 1e9), pk["bf16_tflops_sustained"] / 2.0  # TF32 dense = bf16/2
-        if "linear" in dkey[0] and fl / (tensor_peak * 1e12) > hbm_t:
-            roofline = {"kernel": "/".join(str(x) for x in dkey), "bound": "tensor", "achieved": fl / dms / 1e9,
-                        "peak": tensor_peak, "unit": "TFLOP/s", "frac": fl / dms / 1e9 / tensor_peak, "traffic": None,
-                        "peak_source": pk["source"] + " bf16 sustained / 2 (TF32 rate); fp32-exact FFMA or 3xTF32 "
-                                                      "needs >= 3x the flops counted here"}
+        hbm_t, tensor_peak = b / (pk["hbm_gbs"] * 1e9), pk["bf16_tflops_sustained"] / 2.0  # TF32 dense = bf16 / 2
+        # The tensor-core kernels are 3xTF32: every fp32 product of the contraction is THREE tf32 MMAs (hi*hi, hi*lo,
+        # lo*hi) -- that is what holds the 1e-5 fp32 parity bar.  So the tensor pipe has 3x the algorithmic flops to
+        # execute, and that executed work is what its roofline bounds.
+        mma_fl = 3 * fl if dkey[0].startswith("umma_") else fl
+        if "linear" in dkey[0] and mma_fl / (tensor_peak * 1e12) > hbm_t:
+            roofline = {"kernel": "/".join(str(x) for x in dkey), "bound": "tensor", "achieved": mma_fl / dms / 1e9,
+                        "peak": tensor_peak, "unit": "TFLOP/s", "frac": mma_fl / dms / 1e9 / tensor_peak, "traffic": None,
+                        "alg_flops": fl, "executed_mma_flops": mma_fl,
+                        "hbm_frac_on_alg_bytes": b / dms / 1e6 / pk["hbm_gbs"],
+                        "peak_source": pk["source"] + " bf16 sustained / 2 (TF32 dense rate); executed flops = 3 x "
+                                                      "algorithmic (3xTF32 split: three tf32 MMAs per fp32 product)"}
         else:
             roofline = {"kernel": "/".join(str(x) for x in dkey), "bound": "hbm", "achieved": b / dms / 1e6,
                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": b / dms / 1e6 / pk["hbm_gbs"], "traffic": None,

@@ -36,6 +36,17 @@ namespace gte {
 
 #ifdef GTE_EXPERIMENTS
 __device__ long long g_umma2_dbg[148 * 16 * 8];
+// per-CTA role accounting (clock64 cycles): 0 span (producer), 1 producer waits on empty, 2 split waits on full,
+// 3 split work, 4 MMA waits on tempty, 5 MMA waits on ready, 6 MMA loop span, 7 epilogue waits on tfull,
+// 8 epilogue work, 9 k-blocks
+__device__ long long g_umma2_acc[148 * 16];
+#define U2_T0() const long long t0__ = clock64()
+#define U2_ACC(var) var += clock64() - t0__
+#define U2_PUT(slot, v) do { if (blockIdx.x < 148) g_umma2_acc[blockIdx.x * 16 + (slot)] = (v); } while (0)
+#else
+#define U2_T0()
+#define U2_ACC(var)
+#define U2_PUT(slot, v)
 #endif
 
 constexpr int U2_THREADS = 448;
@@ -162,13 +173,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
       if (P.dbg & 32) pf_t = total;  // timing experiment: no L2 prefetch
 #endif
       for (int i = 0; i < U2_PREFETCH; ++i) pf_step();
+      long long w_pe = 0, n_kb = 0;
+      const long long t_begin = clock64();
+      (void)w_pe; (void)n_kb; (void)t_begin;
       for (int t = cluster_id; t < total; t += nclusters) {
         const int mt = 2 * (t / P.ngroups) + (int)rank, grp = t % P.ngroups;
         stamp(t, 7);
         for (int seg = 0; seg < P.nseg; ++seg) {
           for (int kb = 0; kb < P.kblocks[seg]; ++kb) {
             pf_step();
-            mbar_wait_cluster_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
+            ++n_kb;
+            {
+              U2_T0();
+              mbar_wait_cluster_backoff(smem_u32(&bar_empty[stage]), phase ^ 1);
+              U2_ACC(w_pe);
+            }
             const uint32_t fb = smem_u32(&bar_full[stage]);
             mbar_expect_tx(fb, (uint32_t)UM_A_BYTES + 2u * L.bh_bytes);
             tma_load_2d(smem_u32(sA_hi_p(stage)), &P.tmA[seg], fb, kb * UM_BK, mt * UM_BM);
@@ -178,6 +197,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
           }
         }
       }
+      U2_PUT(0, clock64() - t_begin);
+      U2_PUT(1, w_pe);
+      U2_PUT(9, n_kb);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA) =================================
@@ -189,15 +211,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
       int acc = 0;
       uint32_t acc_phase = 0;
       constexpr int nacc = SPLIT ? 1 : 2;
+      long long w_mt = 0, w_mr = 0;
+      const long long t_begin = clock64();
+      (void)w_mt; (void)w_mr; (void)t_begin;
       for (int t = cluster_id; t < total; t += nclusters) {
         stamp(t, 4);
-        mbar_wait_cluster(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+        {
+          U2_T0();
+          mbar_wait_cluster(smem_u32(&bar_tempty[acc]), acc_phase ^ 1);
+          U2_ACC(w_mt);
+        }
         tc_fence_after();
         stamp(t, 5);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * UM_ACC_STRIDE);
         const uint32_t d_cross = SPLIT ? tmem_base + UM_ACC_STRIDE : d_tmem;
         for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait_cluster(smem_u32(&bar_ready[stage]), phase);
+          {
+            U2_T0();
+            mbar_wait_cluster(smem_u32(&bar_ready[stage]), phase);
+            U2_ACC(w_mr);
+          }
           tc_fence_after();
           const uint64_t dah = make_desc_k_sw128(smem_u32(sA_hi_p(stage)));
           const uint64_t dal = make_desc_k_sw128(smem_u32(sA_lo_p(stage)));
@@ -217,6 +250,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
         umma_commit_pair(smem_u32(&bar_tfull[acc]));
         if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
+      U2_PUT(4, w_mt);
+      U2_PUT(5, w_mr);
+      U2_PUT(6, clock64() - t_begin);
     }
   } else if (warp < U2_EPI_WARP0 || warp >= U2_EPI_WARP0 + U2_EPI_WARPS) {
     // ================================ operand split (warps 2, 3, 12, 13) ======================
@@ -224,9 +260,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
     const uint32_t ready_leader = mapa_shared(smem_u32(&bar_ready[0]), 0);
     int stage = 0;
     uint32_t phase = 0;
+    long long w_sf = 0, w_sw = 0;
+    (void)w_sf; (void)w_sw;
     for (int tile = cluster_id; tile < total; tile += nclusters) {
       for (int kb = 0; kb < kb_total; ++kb) {
-        mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
+        {
+          U2_T0();
+          mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
+          U2_ACC(w_sf);
+        }
+        U2_T0();
         const float4* hi = reinterpret_cast<const float4*>(sA_hi_p(stage));
         float4* lo = reinterpret_cast<float4*>(sA_lo_p(stage));
         // hi stays as TMA wrote it: kind::tf32 reads the top 19 bits of the fp32 word, i.e. a_hi = trunc(a); only the
@@ -243,8 +286,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ready_leader + (uint32_t)stage * 8u);
+        U2_ACC(w_sw);
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
+    }
+    if (t == 0) {
+      U2_PUT(2, w_sf);
+      U2_PUT(3, w_sw);
     }
   } else {
     // ================================ epilogue (warps 4..11) ===================================
@@ -265,10 +313,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
     const int cols_a = min(P.N, c_split * 32);
     const float n_a = (float)cols_a, n_b = (float)(P.N - cols_a), n_all = (float)P.N;
     const float my_n = half ? n_b : n_a;
+    long long w_et = 0, w_ew = 0;
+    (void)w_et; (void)w_ew;
     for (int t = cluster_id; t < total; t += nclusters) {
       const int mt = 2 * (t / P.ngroups) + (int)rank, grp = t % P.ngroups;
       if (ew == 0 && lane == 0) stamp(t, 0);
-      mbar_wait_cluster_backoff(smem_u32(&bar_tfull[acc]), acc_phase);
+      {
+        U2_T0();
+        mbar_wait_cluster_backoff(smem_u32(&bar_tfull[acc]), acc_phase);
+        U2_ACC(w_et);
+      }
+      U2_T0();
       tc_fence_after();
       if (ew == 0 && lane == 0) stamp(t, 1);
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * UM_ACC_STRIDE);
@@ -375,6 +430,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+      U2_ACC(w_ew);
+    }
+    if (ew == 0 && lane == 0) {
+      U2_PUT(7, w_et);
+      U2_PUT(8, w_ew);
     }
     if (lane == 0) tma_store_wait_all();  // shared store tiles must outlive their TMA reads
   }
@@ -448,6 +508,10 @@ int launch_umma_pair(UmmaArgs& a, cudaStream_t st) {
 
 int umma_pair_debug_times(int64_t* out_host, int32_t count) {
 #ifdef GTE_EXPERIMENTS
+  if (count == 148 * 16) {  // role accounting
+    GTE_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_umma2_acc, (size_t)count * 8), "gte_umma_debug_times");
+    return GTE_OK;
+  }
   GTE_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_umma2_dbg, (size_t)count * 8), "gte_umma_debug_times");
   return GTE_OK;
 #else

@@ -78,12 +78,16 @@ struct DwArgs {
   int32_t n, chunk_rows, nchunks;
   int32_t max_boxes;
   int32_t a_blocked[2];  // tmA[i] is a 3-D blocked map (box = 4 blocks = one m-tile)
+  int32_t a_real_boxes;  // 4, or fewer when A is a narrow operand: boxes [a_real_boxes, 4) of the A tile stay zero
   int32_t stages;        // operand ring depth (as many stages as fit: narrow operands get a deeper ring)
   int32_t dbg;           // GTE_EXPERIMENTS builds
   float* partial;        // [gridDim.x] tiles of [32 * max_boxes columns][128 rows] floats (column-major: row fastest)
   int64_t tile_stride;   // floats per partial tile
 };
 
+// AREAL: real 32-column boxes of the A tile (4; 1 for a narrow A operand -- compile time, so that the operand split keeps
+// constant bounds: with a run-time bound the hidden-layer launch measured 15 % slower)
+template <int AREAL>
 __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant__ DwArgs P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the shared address space visible to the compiler (pointer arithmetic only): LDS/STS, not generic LD/ST
@@ -129,6 +133,16 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
     tma_prefetch_desc(&P.tmA[G.a]);
     for (int r = 0; r < G.nruns; ++r) tma_prefetch_desc(&P.tmB[G.run[r].map]);
   }
+  if (AREAL < 4) {
+    // narrow A operand: the unused 32-column boxes of every stage's A tile (hi and lo) are zero for the whole launch
+    const int z0 = AREAL * DW_BOX_BYTES / 16, zn = a_bytes / 16;
+    for (int s = 0; s < DW_STAGES; ++s)
+      for (int i = z0 + threadIdx.x; i < zn; i += DW_THREADS) {
+        reinterpret_cast<float4*>(sA_hi(s))[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(sA_lo(s))[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    fence_proxy_async();
+  }
   if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
   tc_fence_before();
   __syncthreads();
@@ -165,10 +179,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
             DW_ACC(w_acc);
           }
           const uint32_t fb = smem_u32(&bar_full[stage]);
-          mbar_expect_tx(fb, (uint32_t)((4 + G.nboxes) * DW_BOX_BYTES));
+          mbar_expect_tx(fb, (uint32_t)((AREAL + G.nboxes) * DW_BOX_BYTES));
           const int row = r0 + kb * DW_KB;
           if (P.a_blocked[G.a]) tma_load_3d(smem_u32(sA_hi(stage)), &P.tmA[G.a], fb, 0, row, mt * 4);
-          else for (int b = 0; b < 4; ++b)
+          else for (int b = 0; b < AREAL; ++b)
             tma_load_2d(smem_u32(sA_hi(stage) + b * DW_BOX_BYTES), &P.tmA[G.a], fb, mt * 128 + b * 32, row);
           int box = 0;
           for (int r = 0; r < G.nruns; ++r) {
@@ -254,7 +268,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
     const int q = warp & 3, third = (warp - 2) >> 2;
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
-    const int na4 = a_bytes / 16, nb4 = G.nboxes * DW_BOX_BYTES / 16;
+    constexpr int na4 = AREAL * DW_BOX_BYTES / 16;
+    const int nb4 = G.nboxes * DW_BOX_BYTES / 16;
+    const bool epi_rows = q < AREAL;  // narrow A: only the first lane quarters hold real rows
     const int ones_col = G.ones_b_col >= 0 ? G.ones_b_col : ((G.ones_a_col >= 0 && G.ones_a_col / 128 == mt) ? G.ones_a_col % 128 : -1);
     float* const ptile = P.partial + (int64_t)blockIdx.x * P.tile_stride + q * 32 + lane;
     bool first = true;
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
       DW_T0();
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int c = third; c < G.nboxes; c += 3) {
+      for (int c = third; c < G.nboxes && epi_rows; c += 3) {
         uint32_t v[32], v2[32];
         tmem_ld_32x32b_x32_nowait(t_base + c * 32, v);
         tmem_ld_32x32b_x32_nowait(t_base + 256 + c * 32, v2);
@@ -355,7 +371,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_umma_dw(const __grid_constant
     }
 #endif
     if (first) {  // a CTA without any chunk still owns a partial tile: it must read as zero
-      for (int c = third; c < G.nboxes; c += 3)
+      for (int c = third; c < G.nboxes && epi_rows; c += 3)
         for (int j = 0; j < 32; ++j) ptile[(int64_t)(c * 32 + j) * 128] = 0.f;
     }
   }
@@ -441,10 +457,13 @@ static size_t dw_smem_bytes(int max_boxes, int stages) {
 static size_t dw_workspace_bytes(int max_boxes) { return (size_t)sm_count() * 32 * max_boxes * 128 * 4 + 256; }
 
 static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
+  if (a.a_real_boxes <= 0) a.a_real_boxes = 4;
   a.stages = DW_MAX_STAGES;
   while (a.stages > 2 && dw_smem_bytes(a.max_boxes, a.stages) > 227 * 1024) --a.stages;
   const size_t smem = dw_smem_bytes(a.max_boxes, a.stages);
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_umma_dw), smem, "k_umma_dw")) return rc;
+  if (a.a_real_boxes != 4 && a.a_real_boxes != 1) return fail(GTE_ERR_INVALID, "k_umma_dw: a_real_boxes = %d", a.a_real_boxes);
+  const void* kfn = a.a_real_boxes == 4 ? reinterpret_cast<const void*>(&k_umma_dw<4>) : reinterpret_cast<const void*>(&k_umma_dw<1>);
+  if (int rc = ensure_dynamic_smem(kfn, smem, "k_umma_dw")) return rc;
   // Rows per accumulation chunk: 384..640 rows (the accuracy experiments behind the default of 512 hold for this whole
   // range), chosen so that the persistent CTAs finish together: every sub-item is shared by grid / ipc CTAs that deal
   // its chunks round robin, cost = rounds * k-blocks with rounds = ceil(chunks / (grid / ipc)).
@@ -487,7 +506,8 @@ static int dw_launch(DwArgs& a, DwReduceArgs& r, cudaStream_t st) {
     r.grp_ncols[g] = a.grp[g].nboxes * 32;
   }
   if (grid >= 1) {
-    k_umma_dw<<<grid, DW_THREADS, smem, st>>>(a);
+    if (a.a_real_boxes == 4) k_umma_dw<4><<<grid, DW_THREADS, smem, st>>>(a);
+    else k_umma_dw<1><<<grid, DW_THREADS, smem, st>>>(a);
     GTE_CHECK_LAUNCH("k_umma_dw");
   }
   int64_t total = 0;
@@ -684,10 +704,38 @@ int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz
 }
 
 // Combined-operand forms: the two narrow blocks live side by side in ONE 32-column matrix (columns [0, w) and
-// [16, 16+w)), so the narrow side of the contraction is a single full-width TMA box instead of two short-row boxes.
+// [16, 16+w)).  The tcgen05.mma issue cost does not shrink with N, so the NARROW operand is the A side here (M = 128
+// with one real 32-column box; the other three boxes of the A tile stay zero in shared memory and only the first TMEM
+// lane quarter is read back) and the WIDE operand is the B side (N up to 256 in ONE MMA): one (group, m-tile) item
+// per row chunk instead of two, half the MMA instructions, and the narrow side is one full-row TMA box.
 //
 // Narrow-x form (input layer): xc[n, 32] = [h | ah]:  dW[:, 0:w] (+)= dz^T xc[:, 0:w] ; dW[:, w:2w] (+)= dz^T xc[:, 16:16+w] ;
-// db (+)= colsum(dz) through the free column w (w < 16).
+// db (+)= colsum(dz) through the free column w of xc (w < 16).
+static int dw_narrow_a(const float* narrow, int64_t ldn, const float* wide, int64_t ldwide, int32_t kwide, int32_t n,
+                       void* ws, DwArgs& a, DwReduceArgs& r) {
+  a.n = n;
+  a.partial = static_cast<float*>(ws);
+  a.a_real_boxes = 1;
+  const int nbw = boxes_of(kwide);
+  int b_blocked = 0;
+  if (n > 0) {
+    int rc = dw_make_map(&a.tmA[0], &a.a_blocked[0], narrow, n, 32, ldn, 1);  // 2-D: one 32-column box per stage
+    if (rc) return rc;
+    rc = dw_make_map(&a.tmB[0], &b_blocked, wide, n, kwide, ldwide, nbw);
+    if (rc) return rc;
+  }
+  DwGroup& G = a.grp[0];
+  G.a = 0; G.nboxes = nbw; G.nruns = 1; G.pcol0 = 0; G.ones_b_col = -1; G.ones_a_col = -1;
+  G.run[0] = DwRun{0, 0, nbw, b_blocked};
+  a.max_boxes = nbw;
+  a.items_per_chunk = 1;
+  a.item_g[0] = 0;
+  a.item_mt[0] = 0;
+  r.partial = a.partial;
+  r.nseg = 0;
+  return GTE_OK;
+}
+
 int gte_umma_linear_bwd_weight_comb(const float* dz, int64_t lddz, int32_t fo, const float* xc, int64_t ldx, int32_t w,
                                     float* dW, int64_t lddw, float* db, int accumulate, int32_t n, void* ws,
                                     size_t ws_bytes, gte_stream_t stream) {
@@ -697,42 +745,24 @@ int gte_umma_linear_bwd_weight_comb(const float* dz, int64_t lddz, int32_t fo, c
   GTE_CHECK_ARG(tma_ok(dz, lddz) && tma_ok(xc, ldx), "gte_umma_linear_bwd_weight_comb: operands must be 16-byte aligned with ld %% 4 == 0");
   GTE_CHECK_ARG(lddz >= fo && ldx >= 32 && lddw >= 2 * (int64_t)w, "gte_umma_linear_bwd_weight_comb: leading dimension too small");
   if (db && w >= 16) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight_comb: db needs w < 16 (no free padding column)");
-  const size_t need = dw_workspace_bytes(1);
+  const size_t need = dw_workspace_bytes(boxes_of(fo));
   if (ws == nullptr || ws_bytes < need)
     return fail(GTE_ERR_WORKSPACE, "gte_umma_linear_bwd_weight_comb: workspace %zu < required %zu", ws_bytes, need);
   DwArgs a{};
   DwReduceArgs r{};
-  a.n = n;
-  const int mtiles = (fo + 127) / 128;
-  a.partial = static_cast<float*>(ws);
-  int b_blocked = 0;
-  if (n > 0) {
-    int rc = dw_make_map(&a.tmA[0], &a.a_blocked[0], dz, n, fo, lddz, 4);
-    if (rc) return rc;
-    rc = dw_make_map(&a.tmB[0], &b_blocked, xc, n, 32, ldx, 1);
-    if (rc) return rc;
-  }
-  DwGroup& G = a.grp[0];
-  G.a = 0; G.nboxes = 1; G.nruns = 1; G.pcol0 = 0; G.ones_b_col = db ? w : -1; G.ones_a_col = -1;
-  G.run[0] = DwRun{0, 0, 1, b_blocked};
-  a.max_boxes = 1;
-  a.items_per_chunk = 0;
-  for (int mt = 0; mt < mtiles; ++mt) {
-    a.item_g[a.items_per_chunk] = 0;
-    a.item_mt[a.items_per_chunk] = mt;
-    ++a.items_per_chunk;
-  }
-  r.partial = a.partial;
+  if (int rc = dw_narrow_a(xc, ldx, dz, lddz, fo, n, ws, a, r)) return rc;
+  if (db) a.grp[0].ones_a_col = w;  // row w of the result = column sums of dz
   r.accumulate = accumulate;
-  r.nseg = 0;
-  r.seg[r.nseg++] = DwSeg{0, fo, 0, w, dW, lddw, 1};
-  r.seg[r.nseg++] = DwSeg{0, fo, 16, w, dW + w, lddw, 1};
-  if (db) r.seg[r.nseg++] = DwSeg{0, fo, w, 1, db, 1, 0};
+  // result[i][o] = sum_rows xc[row][i] * dz[row][o]  ->  dW[o][i] (i < w), dW[o][w + i - 16] (16 <= i < 16 + w)
+  r.seg[r.nseg++] = DwSeg{0, w, 0, fo, dW, 1, lddw};
+  r.seg[r.nseg++] = DwSeg{16, w, 0, fo, dW + w, 1, lddw};
+  if (db) r.seg[r.nseg++] = DwSeg{w, 1, 0, fo, db, 0, 1};
   return dw_launch(a, r, as_stream(stream));
 }
 
-// Narrow-dz form (class layer) on dc[n, 32] = [dz | gq]: A = x [n, k <= 256];
+// Narrow-dz form (class layer) on dc[n, 32] = [dz | gq]; x [n, k <= 256]:
 //   dW[:, col1:col1+k] (+)= dc[:, 0:fo]^T x ; dW[:, col2:col2+k] (+)= dc[:, 16:16+fo]^T x ; db (+)= colsum(dc[:, 0:fo])
+// (db through an all-ones padding column of x: needs k % 32 != 0)
 int gte_umma_linear_bwd_weight2_comb(const float* dc, int64_t lddc, int32_t fo, const float* x, int64_t ldx, int32_t k,
                                      float* dW, int64_t lddw, int32_t col1, int32_t col2, float* db, int accumulate,
                                      int32_t n, void* ws, size_t ws_bytes, gte_stream_t stream) {
@@ -742,39 +772,19 @@ int gte_umma_linear_bwd_weight2_comb(const float* dc, int64_t lddc, int32_t fo, 
   GTE_CHECK_ARG(tma_ok(dc, lddc) && tma_ok(x, ldx), "gte_umma_linear_bwd_weight2_comb: operands must be 16-byte aligned with ld %% 4 == 0");
   GTE_CHECK_ARG(lddc >= 32 && ldx >= k && lddw >= (int64_t)col1 + k && lddw >= (int64_t)col2 + k,
                 "gte_umma_linear_bwd_weight2_comb: leading dimension too small");
-  const size_t need = dw_workspace_bytes(1);
+  const size_t need = dw_workspace_bytes(boxes_of(k));
   if (ws == nullptr || ws_bytes < need)
     return fail(GTE_ERR_WORKSPACE, "gte_umma_linear_bwd_weight2_comb: workspace %zu < required %zu", ws_bytes, need);
-  const bool db_fused = db != nullptr && (k % 128 != 0);
-  if (db && !db_fused) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight2_comb: db needs k %% 128 != 0");
+  if (db && k % 32 == 0) return fail(GTE_ERR_UNSUPPORTED, "gte_umma_linear_bwd_weight2_comb: db needs k %% 32 != 0");
   DwArgs a{};
   DwReduceArgs r{};
-  a.n = n;
-  const int mtiles = (k + (db_fused ? 1 : 0) + 127) / 128;
-  a.partial = static_cast<float*>(ws);
-  int b_blocked = 0;
-  if (n > 0) {
-    int rc = dw_make_map(&a.tmA[0], &a.a_blocked[0], x, n, k, ldx, 4);
-    if (rc) return rc;
-    rc = dw_make_map(&a.tmB[0], &b_blocked, dc, n, 32, lddc, 1);
-    if (rc) return rc;
-  }
-  DwGroup& G = a.grp[0];
-  G.a = 0; G.nboxes = 1; G.nruns = 1; G.pcol0 = 0; G.ones_b_col = -1; G.ones_a_col = db_fused ? k : -1;
-  G.run[0] = DwRun{0, 0, 1, b_blocked};
-  a.max_boxes = 1;
-  a.items_per_chunk = 0;
-  for (int mt = 0; mt < mtiles; ++mt) {
-    a.item_g[a.items_per_chunk] = 0;
-    a.item_mt[a.items_per_chunk] = mt;
-    ++a.items_per_chunk;
-  }
-  r.partial = a.partial;
+  if (int rc = dw_narrow_a(dc, lddc, x, ldx, k, n, ws, a, r)) return rc;
+  if (db) a.grp[0].ones_b_col = k;  // column k of the result = column sums of dc
   r.accumulate = accumulate;
-  r.nseg = 0;
-  r.seg[r.nseg++] = DwSeg{0, k, 0, fo, dW + col1, 1, lddw};   // out[j][o] -> dW[o][col1 + j]
-  r.seg[r.nseg++] = DwSeg{0, k, 16, fo, dW + col2, 1, lddw};
-  if (db_fused) r.seg[r.nseg++] = DwSeg{k, 1, 0, fo, db, 0, 1};  // ones row: column sums of dz
+  // result[i][j] = sum_rows dc[row][i] * x[row][j]  ->  dW[i][col1 + j] (i < fo), dW[i - 16][col2 + j] (16 <= i < 16 + fo)
+  r.seg[r.nseg++] = DwSeg{0, fo, 0, k, dW + col1, lddw, 1};
+  r.seg[r.nseg++] = DwSeg{16, fo, 0, k, dW + col2, lddw, 1};
+  if (db) r.seg[r.nseg++] = DwSeg{0, fo, k, 1, db, 1, 0};
   return dw_launch(a, r, as_stream(stream));
 }
 

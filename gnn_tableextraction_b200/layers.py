@@ -156,7 +156,8 @@ def class_grad_buffer(ctx: "LayerCtx", n: int, device) -> Optional[torch.Tensor]
     (d logits | A_hat^T d logits): a caller that PRODUCES that gradient (the trainer's loss backward) writes it into
     ``comb_views(buf, fout)[0]`` of the buffer returned here and passes the buffer as ``dy_comb``.  None: not wanted."""
     if (ctx.strategy == "proj" and not ctx.ln and not ctx.relu and ctx.fout <= ops.COMB_W and ctx.pack is not None
-            and _comb_rows(n) and ctx.fin <= 256 and ops._aligned_mat(ctx.h)):
+            and _comb_rows(n) and ctx.fin <= 256 and ctx.fin % 32 != 0 and ops._aligned_mat(ctx.h)):
+        # fin % 32 != 0: the bias gradient rides on a free padding column of the input operand
         return ops.comb_buffer(n, device)
     return None
 
@@ -300,7 +301,7 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
     # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
     #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn
     dc = dy_comb if dy_comb is not None else class_grad_buffer(ctx, dz.shape[0], dz.device)
-    if dc is not None and (db is None or fin % 128 != 0):
+    if dc is not None:
         # [dz | A_hat^T dz] side by side: one full-row TMA box for the weight gradient, one k-block for dh
         dzv, gqv = ops.comb_views(dc, fout)
         if dy_comb is None:

@@ -628,7 +628,7 @@ def umma_linear_bwd_weight_comb(dz, xc, w: int, dW, db, accumulate=False):
     if dW.shape[0] != fo or 2 * w > kw or xc.shape[0] != n:
         raise GteError("umma_linear_bwd_weight_comb: shape mismatch")
     l = lib()
-    ws = workspace(l.gte_umma_bwd_weight_workspace_bytes(n, fo, COMB_LD, 0), dz.device)
+    ws = workspace(l.gte_umma_bwd_weight_workspace_bytes(n, fo, 256, 0), dz.device)
     check(
         l.gte_umma_linear_bwd_weight_comb(dzp, lddz, fo, xp, ldx, w, dWp, lddw, _vec(db, "db", n=fo),
                                           1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),
@@ -645,7 +645,7 @@ def umma_linear_bwd_weight2_comb(dc, fo: int, x, dW, col1: int, col2: int, db, a
     if dW.shape[0] != fo or max(col1, col2) + k > kw or x.shape[0] != n:
         raise GteError("umma_linear_bwd_weight2_comb: shape mismatch")
     l = lib()
-    ws = workspace(l.gte_umma_bwd_weight2_workspace_bytes(n, fo, k), dc.device)
+    ws = workspace(l.gte_umma_bwd_weight_workspace_bytes(n, fo, 256, 0), dc.device)
     check(
         l.gte_umma_linear_bwd_weight2_comb(dp, ldd, fo, xp, ldx, k, dWp, lddw, col1, col2, _vec(db, "db", n=fo),
                                            1 if accumulate else 0, n, ws.data_ptr(), ws.numel(), _stream()),

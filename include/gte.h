@@ -360,9 +360,10 @@ int gte_umma_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz
  *   bwd_weight_comb   (w   <= 16)  dW[:, :w] (+)= dz^T xc[:, :w] ; dW[:, w:2w] (+)= dz^T xc[:, 16:16+w] ;
  *                                  db (+)= colsum(dz) (needs w < 16)
  *   bwd_weight2_comb  (fo  <= 16)  dW[:, col1:col1+k] (+)= dc[:, :fo]^T x ; dW[:, col2:col2+k] (+)=
- *                                  dc[:, 16:16+fo]^T x ; db (+)= colsum(dc[:, :fo]) (needs k % 128 != 0)
- * pack = gte_umma_pack_weights(..., nseg = 2) of the same W.  Workspace: the *_workspace_bytes of the
- * two-operand forms is sufficient.
+ *                                  dc[:, 16:16+fo]^T x ; db (+)= colsum(dc[:, :fo]) (needs k % 32 != 0)
+ * pack = gte_umma_pack_weights(..., nseg = 2) of the same W.  Workspace of the two weight-gradient forms:
+ * gte_umma_bwd_weight_workspace_bytes(n, fo, 256, 0) is sufficient.  In both, the narrow operand is the A side of
+ * the MMA (one real 32-column box of a 128-row tile) and the wide one the B side (N up to 256 in one instruction).
  */
 int gte_umma_linear_fwd_comb(const float* xc, int64_t ldx, int32_t fin, const float* pack,
                              const float* bias, const float* gamma, const float* beta, float eps,

@@ -1,0 +1,16 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+for i in 1 2; do
+  GTE_LIB=$PWD/gnn_tableextraction_b200/libgte_b200_prev.so timeout 100 python scripts/dw_time.py | sed 's/^/prev /'
+  timeout 100 python scripts/dw_time.py | sed 's/^/new  /'
+done
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2p_pytest.log 2>&1
+echo "pytest rc=$?"; tail -n 4 gpurun_out/r2p_pytest.log
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err
+echo "bench rc=$?"; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2p_bench.json'))
+print({k:d[k] for k in ['value','ms_per_step','launches_per_step']}, d['e2e']['value'])
+for r in d['ops']: print(r['op'], r['ms'], r['share'])
+PY

@@ -382,7 +382,9 @@ def test_tensor_core_route_matches_reference_golden(name, paged, monkeypatch, um
     assert calls["umma_linear_fwd_comb"] == 1 and calls["umma_linear_bwd_weight_comb"] == 1
     nh = len(model.layers) - 2  # hidden layers
     assert nh >= 1 and calls["umma_linear_fwd"] == nh and calls["umma_linear_bwd_weight"] == nh and calls["umma_linear_bwd_data"] == nh
-    assert calls["umma_linear_fwd_stacked"] == 1 and calls["umma_linear_bwd_weight2_comb"] == 1 and calls["umma_linear_bwd_data_comb"] == 1
+    assert calls["umma_linear_fwd_stacked"] == 1
+    # (the class layer's bias gradient rides on a free padding column of its input: hidden width % 32 != 0)
+    assert calls["umma_linear_bwd_weight2_comb"] == calls["umma_linear_bwd_data_comb"] == (1 if hid % 32 else 0)
     assert (calls["spmm_packed"] > 0) == paged
     if paged:
         g.check_page_structure()
