@@ -86,7 +86,7 @@ SIGNATURES = {
     "gte_dp_allreduce_adam": (ci, [vp, vp, i32, i32, i64, i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp, vp]),
 }
 
-GTE_TUNE_UMMA_PAIR, GTE_TUNE_DW_PAIR, GTE_TUNE_EPI_STORE = 0, 1, 2
+GTE_TUNE_UMMA_PAIR, GTE_TUNE_DW_PAIR, GTE_TUNE_EPI_STORE, GTE_TUNE_UMMA_SPLIT = 0, 1, 2, 3
 GTE_AGG_SUM, GTE_AGG_SUM_NORM, GTE_AGG_MEAN = 0, 1, 2
 GTE_NORM_INV_DEG_ZERO, GTE_NORM_INV_DEG_CLAMP = 0, 1
 GTE_LABEL_I64, GTE_LABEL_I32, GTE_LABEL_F32 = 0, 1, 2

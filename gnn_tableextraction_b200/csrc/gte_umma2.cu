@@ -498,7 +498,7 @@ int launch_umma_pair(UmmaArgs& a, cudaStream_t st) {
   if (clusters < 1) return GTE_OK;
   // same SPLIT rule as the single-CTA kernel: contractions of one or two k-blocks keep one accumulator per TMEM stage
   // (two stages: the epilogue of tile i overlaps the MMAs of tile i+1)
-  if (kb_total > 2)
+  if (kb_total > 2 && tuning(GTE_TUNE_UMMA_SPLIT) != 0)
     k_umma_gemm_pair<true><<<2 * clusters, U2_THREADS, smem, st>>>(a);
   else
     k_umma_gemm_pair<false><<<2 * clusters, U2_THREADS, smem, st>>>(a);

@@ -74,13 +74,16 @@ int64_t gte_launch_count(void);
  *   GTE_TUNE_UMMA_PAIR   1 (default): tensor-core projections run on CTA pairs (tcgen05 cta_group::2) when the shape
  *                        allows it; 0: always the single-CTA kernel
  *   GTE_TUNE_DW_PAIR     same for the tensor-core weight gradients
+ *   GTE_TUNE_UMMA_SPLIT  1 (default): contractions of more than two k-blocks keep the 3xTF32 cross terms in their own
+ *                        TMEM accumulator; 0: one accumulator (and two accumulator stages) for every shape
  *   GTE_TUNE_EPI_STORE   0 (default): the pair kernel's epilogue leaves through TMA stores; 1: through the epilogue
  *                        warps' own row-contiguous 128-bit global stores
  */
 #define GTE_TUNE_UMMA_PAIR 0
 #define GTE_TUNE_DW_PAIR 1
 #define GTE_TUNE_EPI_STORE 2
-#define GTE_TUNE_COUNT 3
+#define GTE_TUNE_UMMA_SPLIT 3
+#define GTE_TUNE_COUNT 4
 int gte_set_tuning(int key, int value);
 int gte_get_tuning(int key);
 /* SM count and compute capability of the current device. */
