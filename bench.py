@@ -130,7 +130,8 @@ class OpTimer:
     NAMES = ["csx_from_coo", "gather_f32", "degree_norm", "spmm", "spmm_packed", "paged_pack_edges", "build_page_formats", "gram_stream", "wide_out", "linear_fwd", "linear_bwd_data",
              "linear_bwd_weight", "layernorm_act_fwd", "layernorm_act_bwd", "cross_entropy_fwd",
              "cross_entropy_bwd", "adam_step", "umma_pack_weights", "umma_linear_fwd", "umma_linear_bwd_data", "linear_bwd_data2", "linear_bwd_weight2", "umma_linear_bwd_weight", "umma_linear_bwd_weight2", "umma_linear_fwd_stacked", "umma_linear_bwd_data2",
-             "umma_linear_fwd_comb", "umma_linear_bwd_data_comb", "umma_linear_bwd_weight_comb", "umma_linear_bwd_weight2_comb"]
+             "umma_linear_fwd_comb", "umma_linear_bwd_data_comb", "umma_linear_bwd_weight_comb", "umma_linear_bwd_weight2_comb",
+             "comb_from", "cross_entropy_bwd_comb"]
 
     def __init__(self, ops, torch):
         self.ops, self.torch, self.rec, self.orig = ops, torch, [], {}

@@ -442,6 +442,61 @@ __global__ void k_ce_bwd(const float* __restrict__ logits, int64_t ld, const voi
   }
 }
 
+// the same, for a class layer that consumes [d logits | A_hat^T d logits] as one combined operand: the thread also
+// zeroes columns [c, zero_to) of its row (rows 16-byte aligned), so the caller needs no separate fill
+__global__ void k_ce_bwd_padded(const float* __restrict__ logits, int64_t ld, const void* __restrict__ labels,
+                                int label_dtype, const float* __restrict__ class_w, int32_t n, int32_t c,
+                                const float* __restrict__ denominator, float* __restrict__ dl, int64_t lddl,
+                                int32_t zero_to) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* lr = logits + i * ld;
+  float* dr = dl + i * lddl;
+  const int64_t yv = load_label(labels, label_dtype, i);
+  const bool valid = yv >= 0 && yv < c;
+  const float den = *denominator;
+  const float wv = valid ? (class_w ? __ldg(class_w + yv) : 1.0f) : 0.f;
+  const float scale = wv / den;
+  float mx = -INFINITY;
+  for (int j = 0; j < c; ++j) mx = fmaxf(mx, lr[j]);
+  float se = 0.f;
+  for (int j = 0; j < c; ++j) se += expf(lr[j] - mx);
+  const float inv = 1.0f / se;
+  for (int j0 = 0; j0 < zero_to; j0 += 4) {
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = j0 + e;
+      float p = 0.f;
+      if (j < c) {
+        p = expf(lr[j] - mx) * inv;
+        if (j == (int)yv) p -= 1.0f;
+        p *= scale;
+      }
+      v[e] = p;
+    }
+    *reinterpret_cast<float4*>(dr + j0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// Combined [n, 32] operand, self block: out[r, 0:w] = x[r, 0:w], every other column of the 32 zero (the neighbour block
+// [16, 16+w) is written afterwards by the aggregation).  One thread per (row, 4-column slot): 128-byte rows, coalesced.
+__global__ void k_comb_fill(const float* __restrict__ x, int64_t ldx, int32_t w, float* __restrict__ out, int64_t ldo,
+                            int64_t n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = t >> 3;
+  if (r >= n) return;
+  const int c0 = (int)(t & 7) * 4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c0 < w) {
+    const float* xr = x + r * ldx;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (c0 + e < w) v[e] = __ldg(xr + c0 + e);
+  }
+  *reinterpret_cast<float4*>(out + r * ldo + c0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 static int ce_grid(int32_t n) {
   int64_t b = ceil_div64(n, CE_THREADS);
   if (b > 296) b = 296;
@@ -710,6 +765,30 @@ int gte_cross_entropy_bwd(const float* logits, int64_t ld, const void* labels, i
   k_ce_bwd<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(logits, ld, labels, label_dtype, class_w, n, c,
                                                                        denominator, dlogits, lddl);
   GTE_CHECK_LAUNCH("k_ce_bwd");
+  return GTE_OK;
+}
+
+int gte_cross_entropy_bwd_padded(const float* logits, int64_t ld, const void* labels, int label_dtype, const float* class_w,
+                                 int32_t n, int32_t c, const float* denominator, float* dlogits, int64_t lddl,
+                                 int32_t zero_to, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && c >= 1, "gte_cross_entropy_bwd_padded: bad size");
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(logits && labels && denominator && dlogits && ld >= c, "gte_cross_entropy_bwd_padded: bad argument");
+  GTE_CHECK_ARG(zero_to >= c && zero_to % 4 == 0 && lddl >= zero_to && lddl % 4 == 0 && aligned16(dlogits),
+                "gte_cross_entropy_bwd_padded: zero_to must be a multiple of 4 in [c, lddl], rows 16-byte aligned");
+  k_ce_bwd_padded<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(logits, ld, labels, label_dtype, class_w, n, c,
+                                                                              denominator, dlogits, lddl, zero_to);
+  GTE_CHECK_LAUNCH("k_ce_bwd_padded");
+  return GTE_OK;
+}
+
+int gte_comb_fill(const float* x, int64_t ldx, int32_t w, float* out, int64_t ldo, int64_t n, gte_stream_t stream) {
+  GTE_CHECK_ARG(n >= 0 && w >= 0 && w <= 16, "gte_comb_fill: bad size (w <= 16)");
+  if (n == 0) return GTE_OK;
+  GTE_CHECK_ARG(out && (w == 0 || (x && ldx >= w)) && ldo >= 32 && ldo % 4 == 0 && aligned16(out),
+                "gte_comb_fill: out must be a 16-byte aligned [n, >= 32] matrix");
+  k_comb_fill<<<(unsigned)ceil_div64(n * 8, 256), 256, 0, as_stream(stream)>>>(x, ldx, w, out, ldo, n);
+  GTE_CHECK_LAUNCH("k_comb_fill");
   return GTE_OK;
 }
 

@@ -173,9 +173,11 @@ class SageTrainer:
 
     def _stage_backward(self, g: PageGraphBatch, labels: torch.Tensor, logits, ctxs):
         den = self._one if self.dp_fused else self.stats[1:2]
-        dc = L.class_grad_buffer(ctxs[-1], logits.shape[0], logits.device)
-        if dc is not None:  # the class layer consumes [d logits | A_hat^T d logits] as one operand: write it in place
-            dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, den, out=ops.comb_views(dc, logits.shape[1])[0])
+        dc = None
+        if L.wants_class_grad_comb(ctxs[-1], logits.shape[0]):
+            # the class layer consumes [d logits | A_hat^T d logits] as one operand: the loss backward writes its half in place
+            dc = ops.cross_entropy_bwd_comb(logits, labels, self.class_w, den)
+            dlogits = ops.comb_views(dc, logits.shape[1])[0]
         else:
             dlogits = ops.cross_entropy_bwd(logits, labels, self.class_w, den)
         self.backward(g, ctxs, dlogits, dy_comb=dc)

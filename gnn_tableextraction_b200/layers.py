@@ -151,15 +151,13 @@ def _comb_rows(n: int) -> bool:
     return COMB and GEMM_MODE != "ffma" and (GEMM_MODE == "umma" or n >= UMMA_MIN_ROWS)
 
 
-def class_grad_buffer(ctx: "LayerCtx", n: int, device) -> Optional[torch.Tensor]:
+def wants_class_grad_comb(ctx: "LayerCtx", n: int) -> bool:
     """The class layer's backward wants its incoming gradient as the self block of a combined [n, 32] operand
-    (d logits | A_hat^T d logits): a caller that PRODUCES that gradient (the trainer's loss backward) writes it into
-    ``comb_views(buf, fout)[0]`` of the buffer returned here and passes the buffer as ``dy_comb``.  None: not wanted."""
-    if (ctx.strategy == "proj" and not ctx.ln and not ctx.relu and ctx.fout <= ops.COMB_W and ctx.pack is not None
-            and _comb_rows(n) and ctx.fin <= 256 and ctx.fin % 32 != 0 and ops._aligned_mat(ctx.h)):
-        # fin % 32 != 0: the bias gradient rides on a free padding column of the input operand
-        return ops.comb_buffer(n, device)
-    return None
+    (d logits | A_hat^T d logits): a caller that PRODUCES that gradient (the trainer's loss backward) builds it with
+    ``ops.cross_entropy_bwd_comb`` (or ``ops.comb_from``) and passes the buffer as ``dy_comb``."""
+    return (ctx.strategy == "proj" and not ctx.ln and not ctx.relu and ctx.fout <= ops.COMB_W and ctx.pack is not None
+            and _comb_rows(n) and ctx.fin <= 256 and ctx.fin % 32 != 0 and ops._aligned_mat(ctx.h))
+    # fin % 32 != 0: the bias gradient rides on a free padding column of the input operand
 
 
 def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Optional[torch.Tensor],
@@ -182,9 +180,8 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
     if st == "agg" and fin <= ops.COMB_W and _comb_rows(h.shape[0]) and ops.umma_supported(fout, fin):
         # narrow input (the [N, 13] BBOX features): h and A_hat h side by side in one zero-padded [n, 32] operand --
         # aligned rows for the gather, ONE k-block for the projection, one full-row TMA box for the weight gradient
-        xc = ops.comb_buffer(h.shape[0], h.device)
+        xc = ops.comb_from(h)
         hs, ahs = ops.comb_views(xc, fin)
-        hs.copy_(h)
         h = hs
     elif GEMM_MODE != "ffma" and h.shape[0] >= UMMA_MIN_ROWS and not ops._aligned_mat(h):
         # unaligned rows: one padded copy gives 16-byte aligned rows for TMA / 128-bit loads
@@ -300,12 +297,12 @@ def sage_layer_backward(g: Optional[PageGraphBatch], ctx: LayerCtx, dy: torch.Te
         return aggregate_backward(g, d_ah, ctx.w_edge, addend=d_self)
     # proj: z = h Ws^T + b + A_hat (h Wn^T)  =>  with G = A_hat^T dz:
     #   dWs = dz^T h, dWn = G^T h, dh = dz Ws + G Wn
-    dc = dy_comb if dy_comb is not None else class_grad_buffer(ctx, dz.shape[0], dz.device)
+    dc = dy_comb
+    if dc is None and wants_class_grad_comb(ctx, dz.shape[0]):
+        dc = ops.comb_from(dz)
     if dc is not None:
         # [dz | A_hat^T dz] side by side: one full-row TMA box for the weight gradient, one k-block for dh
         dzv, gqv = ops.comb_views(dc, fout)
-        if dy_comb is None:
-            dzv.copy_(dz)
         aggregate_backward(g, dzv, ctx.w_edge, out=gqv)
         ops.umma_linear_bwd_weight2_comb(dc, fout, ctx.h, dW, 0, fin, db, accumulate)
         return ops.umma_linear_bwd_data_comb(dc, fout, ctx.pack, fin) if need_dh else None

@@ -573,6 +573,19 @@ def comb_buffer(n: int, device) -> torch.Tensor:
     return torch.zeros((n, COMB_LD), dtype=torch.float32, device=device)
 
 
+def comb_from(x: torch.Tensor) -> torch.Tensor:
+    """[n, 32] combined operand with ``x`` [n, w <= 16] as its self block and zeros elsewhere, in one native kernel
+    (x may have unaligned rows, e.g. the raw [N, 13] BBOX features); the neighbour block is written afterwards."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] <= COMB_W
+            and (x.shape[1] <= 1 or x.stride(1) == 1)):
+        raise GteError("comb_from: float32 CUDA matrix [n, w <= 16] with unit column stride expected")
+    n, w = x.shape
+    out = torch.empty((n, COMB_LD), dtype=torch.float32, device=x.device)
+    check(lib().gte_comb_fill(x.data_ptr(), x.stride(0) if n > 1 else max(w, 1), w, out.data_ptr(), COMB_LD, n, _stream()),
+          "gte_comb_fill")
+    return out
+
+
 def comb_views(buf: torch.Tensor, w: int):
     """(self block, neighbour block) column views of a combined operand."""
     return buf[:, :w], buf[:, COMB_W:COMB_W + w]
@@ -796,6 +809,23 @@ def cross_entropy_fwd(logits, labels, class_w=None, stats=None):
         "gte_cross_entropy_fwd",
     )
     return stats
+
+
+def cross_entropy_bwd_comb(logits, labels, class_w, denominator):
+    """d logits written in place as the self block of a fresh combined [n, 32] operand (other columns zero)."""
+    lp, ld, c = _mat(logits, "ce.logits")
+    n = logits.shape[0]
+    if c > COMB_W:
+        raise GteError("cross_entropy_bwd_comb: more than 16 classes")
+    yp, ydt = _labels(labels)
+    _req_cuda(denominator)
+    out = torch.empty((n, COMB_LD), dtype=torch.float32, device=logits.device)
+    check(
+        lib().gte_cross_entropy_bwd_padded(lp, ld, yp, ydt, _vec(class_w, "class_w", n=c), n, c, denominator.data_ptr(),
+                                           out.data_ptr(), COMB_LD, COMB_LD, _stream()),
+        "gte_cross_entropy_bwd_padded",
+    )
+    return out
 
 
 def cross_entropy_bwd(logits, labels, class_w, denominator, out=None):

@@ -444,6 +444,15 @@ int gte_cross_entropy_fwd(const float* logits, int64_t ld, const void* labels, i
 int gte_cross_entropy_bwd(const float* logits, int64_t ld, const void* labels, int label_dtype,
                           const float* class_w, int32_t n, int32_t c, const float* denominator,
                           float* dlogits, int64_t lddl, gte_stream_t stream);
+/* The same, and columns [c, zero_to) of every dlogits row are set to zero (zero_to % 4 == 0, rows 16-byte
+ * aligned): the self block of the class layer's combined [n, 32] gradient operand, written in place. */
+int gte_cross_entropy_bwd_padded(const float* logits, int64_t ld, const void* labels, int label_dtype,
+                                 const float* class_w, int32_t n, int32_t c, const float* denominator,
+                                 float* dlogits, int64_t lddl, int32_t zero_to, gte_stream_t stream);
+/* Self block of a combined [n, 32] operand (see the *_comb entries): out[r, 0:w] = x[r, 0:w] (x rows may be
+ * unaligned, e.g. the raw [N, 13] BBOX features), every other column of the 32 zero; w <= 16. */
+int gte_comb_fill(const float* x, int64_t ldx, int32_t w, float* out, int64_t ldo, int64_t n,
+                  gte_stream_t stream);
 
 /*
  * torch.optim.Adam(lr, betas, eps, weight_decay) with L2-in-gradient decay over

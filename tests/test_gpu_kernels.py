@@ -653,6 +653,25 @@ def test_umma_comb_class_layer_forms(n, fin, fo, umma_kernel):
     assert rel_err(dW2 - 1.0, torch.cat([dz.double().t() @ x.double(), gq.double().t() @ x.double()], 1)) < 1e-5
 
 
+@pytest.mark.parametrize("n,w", [(1, 13), (1000, 13), (4097, 16), (33, 1), (7, 9)])
+def test_comb_fill_and_padded_ce_bwd(n, w):
+    """the two native producers of combined [n, 32] operands: self block = the source (bit for bit), every other column 0"""
+    gen = torch.Generator().manual_seed(n * 31 + w)
+    x = (torch.randn(n, w, generator=gen) * 100).to(DEV)          # unaligned rows (ld = w)
+    xc = ops.comb_from(x)
+    assert xc.shape == (n, 32) and torch.equal(xc[:, :w], x) and torch.all(xc[:, w:] == 0)
+    xs = torch.randn(n, 40, generator=gen).to(DEV)[:, 3:3 + w]     # strided view
+    assert torch.equal(ops.comb_from(xs)[:, :w], xs)
+    c = min(w, 9)
+    logits = _padded(torch.randn(n, c, generator=gen) * 3)
+    labels = torch.randint(0, c, (n,), generator=gen).float().to(DEV)
+    cw = (torch.rand(c, generator=gen) + 0.5).to(DEV)
+    den = torch.tensor([float(n) * 0.7], device=DEV)
+    ref = ops.cross_entropy_bwd(logits, labels, cw, den)
+    dc = ops.cross_entropy_bwd_comb(logits, labels, cw, den)
+    assert dc.shape == (n, 32) and torch.equal(dc[:, :c], ref[:, :c]) and torch.all(dc[:, c:] == 0)
+
+
 # ------------------------------------------------- narrow dense streams ----
 @pytest.mark.parametrize("n,wide,nq1,nq2", [(5000, 218, 13, 13), (3001, 218, 9, 9), (2, 7, 3, 0), (777, 256, 16, 16),
                                             (40000, 218, 13, 13), (64, 100, 1, 0), (2049, 33, 5, 2)])
