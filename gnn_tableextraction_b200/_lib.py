@@ -62,6 +62,7 @@ SIGNATURES = {
     "gte_umma_linear_bwd_weight": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, vp, ci, i32, vp, sz, vp]),
     "gte_umma_bwd_weight2_workspace_bytes": (sz, [i32, i32, i32]),
     "gte_umma_linear_bwd_weight2": (ci, [vp, i64, vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, vp, ci, i32, vp, sz, vp]),
+    "gte_umma_pack_weights_batch": (ci, [vp, i32, vp]),
     "gte_umma_linear_fwd_comb": (ci, [vp, i64, i32, vp, vp, vp, vp, f32, ci, ci, vp, i64, vp, i64, vp, vp, i32, i32, vp]),
     "gte_umma_linear_bwd_data_comb": (ci, [vp, i64, i32, vp, vp, i64, i32, i32, vp]),
     "gte_umma_linear_bwd_weight_comb": (ci, [vp, i64, i32, vp, i64, i32, vp, i64, vp, ci, i32, vp, sz, vp]),
@@ -87,6 +88,15 @@ SIGNATURES = {
     "gte_adam_step": (ci, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, f32, vp, vp]),
     "gte_dp_allreduce_adam": (ci, [vp, vp, i32, i32, i64, i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp, vp]),
 }
+
+PACK_BATCH_MAX = 8
+
+
+class PackDesc(C.Structure):
+    """gte_pack_desc_t (gte.h)"""
+    _fields_ = [("W", C.c_void_p), ("ldw", C.c_int64), ("fo", C.c_int32), ("fin", C.c_int32), ("nseg", C.c_int32),
+                ("pack", C.c_void_p)]
+
 
 GTE_TUNE_UMMA_PAIR, GTE_TUNE_DW_PAIR, GTE_TUNE_EPI_STORE, GTE_TUNE_UMMA_SPLIT = 0, 1, 2, 3
 GTE_AGG_SUM, GTE_AGG_SUM_NORM, GTE_AGG_MEAN = 0, 1, 2

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_gemm(const __grid_consta
 //            [16, 16+w) = neighbour block, the rest zero), so that the whole contraction is a single k-block:
 //   Pc[half][BN][32]   (fin <= 16)  Pc[o][k] = W[o, k] (k < fin), W[o, fin + k-16] (16 <= k < 16+fin)     z = [h|ah] W^T
 //   Pd[half][BNb][32]  (fo <= 16)   Pd[j][k] = W[k, j] (k < fo),  W[k-16, fin + j] (16 <= k < 16+fo)      dx = [dz|gq] W
-__global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
+__device__ __forceinline__ void pack_one(const float* __restrict__ W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
                             float* __restrict__ Pf, int32_t BN, int32_t Kp, float* __restrict__ Pb, int32_t BNb,
                             int32_t Kpb, float* __restrict__ Ps, float* __restrict__ Pc, float* __restrict__ Pd) {
   const int64_t per_f = (int64_t)BN * Kp, per_b = (int64_t)BNb * Kpb;
@@ -345,7 +345,7 @@ __global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo
   const int64_t total_d = Pd ? (int64_t)BNb * 32 : 0;
   const int64_t end_b = total_f + total_b, end_s = end_b + total_s, end_c = end_s + total_c;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // (gridDim.x only: blockIdx.y selects the matrix in the batch form)
   for (; i < end_c + total_d; i += stride) {
     float w = 0.f;
     float* dst;
@@ -391,6 +391,27 @@ __global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo
     dst[0] = h;
     dst[half_stride] = tf32_rna(w - h);
   }
+}
+
+__global__ void k_umma_pack(const float* __restrict__ W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
+                            float* __restrict__ Pf, int32_t BN, int32_t Kp, float* __restrict__ Pb, int32_t BNb,
+                            int32_t Kpb, float* __restrict__ Ps, float* __restrict__ Pc, float* __restrict__ Pd) {
+  pack_one(W, ldw, fo, fin, nseg, Pf, BN, Kp, Pb, BNb, Kpb, Ps, Pc, Pd);
+}
+
+// several weight matrices in one launch (blockIdx.y = matrix): the train step packs all its layers at once
+struct PackOne {
+  const float* W;
+  int64_t ldw;
+  int32_t fo, fin, nseg, BN, Kp, BNb, Kpb;
+  float *Pf, *Pb, *Ps, *Pc, *Pd;
+};
+struct PackBatch {
+  PackOne m[GTE_PACK_BATCH_MAX];
+};
+__global__ void k_umma_pack_batch(const PackBatch B) {
+  const PackOne& p = B.m[blockIdx.y];
+  pack_one(p.W, p.ldw, p.fo, p.fin, p.nseg, p.Pf, p.BN, p.Kp, p.Pb, p.BNb, p.Kpb, p.Ps, p.Pc, p.Pd);
 }
 
 // ------------------------------------------------------------ host side ----
@@ -524,6 +545,36 @@ int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, 
       d.stacked_floats ? pack + d.off_stacked() : nullptr, d.combf_floats ? pack + d.off_combf() : nullptr,
       d.combb_floats ? pack + d.off_combb() : nullptr);
   GTE_CHECK_LAUNCH("k_umma_pack");
+  return GTE_OK;
+}
+
+int gte_umma_pack_weights_batch(const gte_pack_desc_t* descs, int32_t count, gte_stream_t stream) {
+  GTE_CHECK_ARG(count >= 0 && count <= GTE_PACK_BATCH_MAX && (count == 0 || descs), "gte_umma_pack_weights_batch: 0 <= count <= %d", GTE_PACK_BATCH_MAX);
+  if (count == 0) return GTE_OK;
+  PackBatch B{};
+  int64_t max_total = 0;
+  for (int i = 0; i < count; ++i) {
+    const gte_pack_desc_t& q = descs[i];
+    GTE_CHECK_ARG(q.W && q.pack, "gte_umma_pack_weights_batch: null argument");
+    GTE_CHECK_ARG(q.nseg >= 1 && q.nseg <= 2 && q.ldw >= (int64_t)q.nseg * q.fin, "gte_umma_pack_weights_batch: bad nseg/ldw");
+    if (!gte_umma_supported(q.fo, q.fin))
+      return fail(GTE_ERR_UNSUPPORTED, "gte_umma_pack_weights_batch: fo=%d fin=%d unsupported", q.fo, q.fin);
+    GTE_CHECK_ARG(aligned16(q.pack), "gte_umma_pack_weights_batch: pack buffer must be 16-byte aligned");
+    PackDims d = pack_dims(q.fo, q.fin, q.nseg);
+    PackOne& m = B.m[i];
+    m.W = q.W; m.ldw = q.ldw; m.fo = q.fo; m.fin = q.fin; m.nseg = q.nseg;
+    m.BN = d.BN; m.Kp = d.Kp; m.BNb = d.BNb; m.Kpb = d.Kpb;
+    m.Pf = q.pack;
+    m.Pb = q.pack + d.fwd_floats;
+    m.Ps = d.stacked_floats ? q.pack + d.off_stacked() : nullptr;
+    m.Pc = d.combf_floats ? q.pack + d.off_combf() : nullptr;
+    m.Pd = d.combb_floats ? q.pack + d.off_combb() : nullptr;
+    const int64_t total = (int64_t)(d.total() / PK_PLANES);
+    if (total > max_total) max_total = total;
+  }
+  dim3 grid((unsigned)ceil_div64(max_total, 256), (unsigned)count);
+  k_umma_pack_batch<<<grid, 256, 0, as_stream(stream)>>>(B);
+  GTE_CHECK_LAUNCH("k_umma_pack_batch");
   return GTE_OK;
 }
 

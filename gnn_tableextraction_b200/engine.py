@@ -132,6 +132,15 @@ class SageTrainer:
         if drop_on and self._drop_p[0] > 0:  # models.py:113: dropout on the input features (they need no gradient)
             h, _ = ops.dropout_concat(h, None, self._drop_p[0], rng_dev=self.rng_dev, offset=used)
             used += ops.dropout_counters(h.shape[0], h.shape[1])
+        # tf32 hi / lo tiles of every layer's W in ONE launch (the layers would otherwise pack one by one)
+        packs: Dict[int, torch.Tensor] = {}
+        n_rows = h.shape[0]
+        todo = [(li, layer.linear.weight.data, layer.linear.weight.shape[1] // 2)
+                for li, layer in enumerate(self.model.layers)
+                if L.wants_pack(n_rows, layer.linear.weight.shape[1] // 2, layer.linear.weight.shape[0], layer.use_pp)]
+        if len(todo) > 1:
+            for (li, _, _), pk in zip(todo, ops.umma_pack_weights_batch([(W, fin, 2) for _, W, fin in todo])):
+                packs[li] = pk
         for li, layer in enumerate(self.model.layers):
             W, b, gamma, beta, has_ln, eps, relu = self._layer_args(layer)
             drop = None
@@ -139,7 +148,8 @@ class SageTrainer:
                 drop = L.DropoutSpec(self._drop_p[1 + li], 0, used, self.rng_dev)
                 used += ops.dropout_counters(h.shape[0], W.shape[1])
             h, ctx = L.sage_layer_forward(g, h, w_edge, W, b, gamma, beta, ln=has_ln, relu=relu, eps=eps, agg=L.GCN,
-                                          use_pp=layer.use_pp, save_for_backward=keep_ctx, dropout=drop)
+                                          use_pp=layer.use_pp, save_for_backward=keep_ctx, dropout=drop,
+                                          pack=packs.get(li))
             ctxs.append(ctx if keep_ctx else None)
             if layer_outputs is not None:
                 layer_outputs.append(h)

@@ -151,6 +151,11 @@ def _comb_rows(n: int) -> bool:
     return COMB and GEMM_MODE != "ffma" and (GEMM_MODE == "umma" or n >= UMMA_MIN_ROWS)
 
 
+def wants_pack(n: int, fin: int, fout: int, use_pp: bool) -> bool:
+    """Could sage_layer_forward take a tensor-core branch for this layer (so a caller may pre-pack W for it)?"""
+    return (not use_pp) and GEMM_MODE != "ffma" and (GEMM_MODE == "umma" or n >= UMMA_MIN_ROWS) and ops.umma_supported(fout, fin)
+
+
 def wants_class_grad_comb(ctx: "LayerCtx", n: int) -> bool:
     """The class layer's backward wants its incoming gradient as the self block of a combined [n, 32] operand
     (d logits | A_hat^T d logits): a caller that PRODUCES that gradient (the trainer's loss backward) builds it with
@@ -164,10 +169,12 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
                        W: torch.Tensor, b: Optional[torch.Tensor], gamma: Optional[torch.Tensor],
                        beta: Optional[torch.Tensor], *, ln: bool, relu: bool, eps: float = 1e-5, agg: str = GCN,
                        use_pp: bool = False, strategy: Optional[str] = None, save_for_backward: bool = True,
-                       dropout: Optional[DropoutSpec] = None):
+                       dropout: Optional[DropoutSpec] = None, pack: Optional[torch.Tensor] = None):
     """Returns (out [N, Fout], LayerCtx).  ``save_for_backward=False`` (inference): the fused tensor-core epilogue does not
     write the pre-activation z (it only exists for the backward pass).  ``dropout`` (training): nn.Dropout on the
-    concatenation [h | ah * norm] before the linear (models.py:60-61), in-kernel Philox, never materialising the concat."""
+    concatenation [h | ah * norm] before the linear (models.py:60-61), in-kernel Philox, never materialising the concat.
+    ``pack``: ``ops.umma_pack_weights(W, fin, 2)`` of the CURRENT W when the caller already made it (the trainer packs all
+    layers in one launch); otherwise the tensor-core branches pack W themselves."""
     fout = W.shape[0]
     fin = W.shape[1] if use_pp else W.shape[1] // 2
     if h.shape[1] != (W.shape[1] if use_pp else fin):
@@ -207,14 +214,14 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
         ctx.ah = ah
         if xc is not None:
             ctx.comb = xc
-            ctx.pack = ops.umma_pack_weights(W, fin, 2)
+            ctx.pack = pack if pack is not None else ops.umma_pack_weights(W, fin, 2)
             z, y, ctx.mean, ctx.rstd = ops.umma_linear_fwd_comb(xc, fin, ctx.pack, b, fout, gamma=gamma, beta=beta,
                                                                 eps=eps, relu=relu, fuse_ln=ln, want_z=save_for_backward)
             ctx.z = z
             return (y if y is not None else z), ctx
         if use_umma(h.shape[0], fin, fout, h, ah):
             # tensor cores: projection + bias + LayerNorm + ReLU in one kernel
-            ctx.pack = ops.umma_pack_weights(W, fin, 2)
+            ctx.pack = pack if pack is not None else ops.umma_pack_weights(W, fin, 2)
             z, y, ctx.mean, ctx.rstd = ops.umma_linear_fwd(h, ah, fin, ctx.pack, b, fout, gamma=gamma, beta=beta,
                                                            eps=eps, relu=relu, fuse_ln=ln, want_z=save_for_backward)
             ctx.z = z
@@ -229,7 +236,7 @@ def sage_layer_forward(g: Optional[PageGraphBatch], h: torch.Tensor, w_edge: Opt
     elif st == "proj":
         if fout <= 16 and use_umma(h.shape[0], fin, fout, h):
             # one tensor-core pass over h: [h Ws^T + b | h Wn^T] side by side, aggregated through column views
-            ctx.pack = ops.umma_pack_weights(W, fin, 2)
+            ctx.pack = pack if pack is not None else ops.umma_pack_weights(W, fin, 2)
             sp = ops.umma_linear_fwd_stacked(h, fin, ctx.pack, b, fout)
             s, p = sp[:, :fout], sp[:, 16:16 + fout]
         else:

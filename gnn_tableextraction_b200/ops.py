@@ -11,6 +11,8 @@ from __future__ import annotations
 import os
 from typing import Optional, Tuple
 
+import ctypes as C
+
 import torch
 
 from . import _lib
@@ -441,6 +443,28 @@ def umma_pack_weights(W: torch.Tensor, fin: int, nseg: int, out: Optional[torch.
     check(l.gte_umma_pack_weights(Wp, ldw, fo, fin, nseg, _vec(out, "pack", n=nbytes // 4), _stream()),
           "gte_umma_pack_weights")
     return out
+
+
+def umma_pack_weights_batch(items, outs=None):
+    """``umma_pack_weights`` for several ``(W, fin, nseg)`` in ONE launch; returns the list of pack buffers
+    (``outs``: reuse these buffers)."""
+    l = lib()
+    res = []
+    for lo in range(0, len(items), _lib.PACK_BATCH_MAX):
+        chunk = items[lo:lo + _lib.PACK_BATCH_MAX]
+        arr = (_lib.PackDesc * len(chunk))()
+        for i, (W, fin, nseg) in enumerate(chunk):
+            Wp, ldw, kw = _mat(W, "umma_pack.W")
+            fo = W.shape[0]
+            nbytes = l.gte_umma_pack_bytes(fo, fin, nseg)
+            if nbytes == 0 or kw < nseg * fin:
+                raise GteError(f"umma_pack_weights_batch: unsupported shape fo={fo} fin={fin} nseg={nseg}")
+            out = outs[lo + i] if outs is not None else torch.empty(nbytes // 4, dtype=torch.float32, device=W.device)
+            arr[i].W, arr[i].ldw, arr[i].fo, arr[i].fin, arr[i].nseg = Wp, ldw, fo, fin, nseg
+            arr[i].pack = _vec(out, "pack", n=nbytes // 4)
+            res.append(out)
+        check(l.gte_umma_pack_weights_batch(C.cast(arr, C.c_void_p), len(chunk), _stream()), "gte_umma_pack_weights_batch")
+    return res
 
 
 def set_tuning(key: int, value: int) -> None:

@@ -299,6 +299,15 @@ int gte_linear_bwd_weight2(const float* dz1, int64_t lddz1, const float* dz2, in
  */
 int gte_umma_supported(int32_t fo, int32_t fin);
 size_t gte_umma_pack_bytes(int32_t fo, int32_t fin, int32_t nseg);
+/* Several matrices in ONE launch (the train step packs all its layers at once): `descs` is a HOST array. */
+#define GTE_PACK_BATCH_MAX 8
+typedef struct {
+  const float* W;
+  int64_t ldw;
+  int32_t fo, fin, nseg;
+  float* pack;
+} gte_pack_desc_t;
+int gte_umma_pack_weights_batch(const gte_pack_desc_t* descs, int32_t count, gte_stream_t stream);
 int gte_umma_pack_weights(const float* W, int64_t ldw, int32_t fo, int32_t fin, int32_t nseg,
                           float* pack, gte_stream_t stream);
 /*

@@ -672,6 +672,19 @@ def test_comb_fill_and_padded_ce_bwd(n, w):
     assert dc.shape == (n, 32) and torch.equal(dc[:, :c], ref[:, :c]) and torch.all(dc[:, c:] == 0)
 
 
+def test_umma_pack_weights_batch_equals_single():
+    """one launch for several weight matrices = the per-matrix packs, bit for bit (all planes, incl. the combined ones)"""
+    gen = torch.Generator().manual_seed(11)
+    shapes = [(218, 13), (218, 218), (9, 218), (64, 100), (256, 256), (16, 16), (1, 1), (130, 7), (33, 250)]
+    Ws = [((torch.rand(fo, 2 * fin, generator=gen) - 0.5) * 3).to(DEV) for fo, fin in shapes]
+    batch = ops.umma_pack_weights_batch([(W, fin, 2) for W, (_, fin) in zip(Ws, shapes)])  # 9 > GTE_PACK_BATCH_MAX: two launches
+    assert len(batch) == len(shapes)
+    for W, (fo, fin), pk in zip(Ws, shapes, batch):
+        assert torch.equal(pk, ops.umma_pack_weights(W, fin, 2)), (fo, fin)
+    one = ops.umma_pack_weights_batch([(Ws[3][:, :100].contiguous(), 100, 1)])[0]
+    assert torch.equal(one, ops.umma_pack_weights(Ws[3][:, :100].contiguous(), 100, 1))
+
+
 # ------------------------------------------------- narrow dense streams ----
 @pytest.mark.parametrize("n,wide,nq1,nq2", [(5000, 218, 13, 13), (3001, 218, 9, 9), (2, 7, 3, 0), (777, 256, 16, 16),
                                             (40000, 218, 13, 13), (64, 100, 1, 0), (2049, 33, 5, 2)])
