@@ -266,7 +266,7 @@ def ncu_traffic(op_key):
 
     name, want = op_key[0], None
     if name == "umma_linear_bwd_weight" and op_key[3] > 64:
-        r = recs("k_umma_dw grid")
+        r = recs("k_umma_dw<4>") or recs("k_umma_dw grid")
         want = r[0] if r else None
     elif name == "umma_linear_fwd" and op_key[2] > 64:  # hidden layer: the longest launch of the pair kernel
         r = recs("k_umma_gemm_pair<1>")
