@@ -133,7 +133,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tfull[a]), 1);
-      mbar_init(smem_u32(&bar_tempty[a]), 2 * U2_EPI_WARPS);
+      // SPLIT: all eight epilogue warps of both CTAs drain the one accumulator stage; otherwise every stage has its own
+      // group of four warps per CTA (see the epilogue)
+      mbar_init(smem_u32(&bar_tempty[a]), SPLIT ? 2 * U2_EPI_WARPS : U2_EPI_WARPS);
     }
     fence_barrier_init();
     for (int s = 0; s < P.nseg; ++s) tma_prefetch_desc(&P.tmA[s]);
@@ -307,16 +309,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
     uint32_t acc_phase = 0;
     int par = 0;
     constexpr int nacc = SPLIT ? 1 : 2;
+    // SPLIT (one accumulator stage): the two warps of a lane quarter share a tile, each takes half of the column chunks
+    // and the LayerNorm statistics of the halves are merged through shared memory.
+    // !SPLIT (two accumulator stages, the store-bound one- and two-k-block shapes): warp group `half` owns accumulator
+    // stage `half` -- it takes every second tile, whole rows, no exchange and no barrier inside a tile (the named
+    // barrier between unevenly loaded halves was 40 % of the epilogue warps' stall samples).
     const int nchunks = (P.N + 31) / 32;
-    const int c_split = (nchunks + 1) / 2;
-    const int c_beg = half ? c_split : 0, c_end = half ? nchunks : c_split;
+    const int c_split = SPLIT ? (nchunks + 1) / 2 : nchunks;
+    const int c_beg = (SPLIT && half) ? c_split : 0, c_end = (SPLIT && half) ? nchunks : c_split;
     const int cols_a = min(P.N, c_split * 32);
     const float n_a = (float)cols_a, n_b = (float)(P.N - cols_a), n_all = (float)P.N;
-    const float my_n = half ? n_b : n_a;
+    const float my_n = (SPLIT && half) ? n_b : n_a;
     long long w_et = 0, w_ew = 0;
     (void)w_et; (void)w_ew;
-    for (int t = cluster_id; t < total; t += nclusters) {
+    int it = 0;
+    for (int t = cluster_id; t < total; t += nclusters, ++it) {
       const int mt = 2 * (t / P.ngroups) + (int)rank, grp = t % P.ngroups;
+      if constexpr (!SPLIT) {
+        if ((it & 1) != half) continue;  // the other warp group's tile
+        acc = half;
+        acc_phase = (uint32_t)(it >> 1) & 1u;
+      }
       if (ew == 0 && lane == 0) stamp(t, 0);
       {
         U2_T0();
@@ -383,20 +396,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
           mh = shift + s1 / my_n;
           m2h = fmaxf(s2 - s1 * s1 / my_n, 0.f);
         }
-        float2* const st = s_stat + (par * 2) * 128 + q * 32 + lane;
-        st[half * 128] = make_float2(mh, m2h);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of this lane quarter
-        const float2 pa = st[0], pb = st[128];
-        par ^= 1;
-        // parallel-variance merge of the two halves (both warps compute the same bits: fixed operand order)
-        float mean = pa.x, m2 = pa.y;
-        if (n_b > 0.f) {
-          const float delta = pb.x - pa.x;
-          mean = pa.x + delta * (n_b / n_all);
-          m2 = pa.y + pb.y + delta * delta * (n_a * n_b / n_all);
+        float mean = mh, m2 = m2h;
+        if constexpr (SPLIT) {
+          float2* const st = s_stat + (par * 2) * 128 + q * 32 + lane;
+          st[half * 128] = make_float2(mh, m2h);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of this lane quarter
+          const float2 pa = st[0], pb = st[128];
+          par ^= 1;
+          // parallel-variance merge of the two halves (both warps compute the same bits: fixed operand order)
+          mean = pa.x;
+          m2 = pa.y;
+          if (n_b > 0.f) {
+            const float delta = pb.x - pa.x;
+            mean = pa.x + delta * (n_b / n_all);
+            m2 = pa.y + pb.y + delta * delta * (n_a * n_b / n_all);
+          }
         }
         const float rstd = 1.0f / sqrtf(m2 / n_all + P.eps);
-        if (half == 0) {
+        if (!SPLIT || half == 0) {
           const int64_t grow = row0 + lane;
           if (grow < P.M) {
             P.mean[grow] = mean;
@@ -429,7 +446,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U2_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
-      if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+      if constexpr (SPLIT) {
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+      }
       U2_ACC(w_ew);
     }
     if (ew == 0 && lane == 0) {
