@@ -685,6 +685,36 @@ def test_umma_pack_weights_batch_equals_single():
     assert torch.equal(one, ops.umma_pack_weights(Ws[3][:, :100].contiguous(), 100, 1))
 
 
+def test_umma_tuning_switches_compute_the_same_results():
+    """gte_set_tuning A/B switches: the epilogue store path is bit-neutral; the single-accumulator mode stays within the
+    documented 3xTF32 error (it trades the cross-term accumulator for a second TMEM stage)"""
+    n, fin, fo = 5000, 218, 218
+    gen = torch.Generator().manual_seed(77)
+    h, ah = torch.randn(n, fin, generator=gen), torch.randn(n, fin, generator=gen)
+    W = (torch.rand(fo, 2 * fin, generator=gen) - 0.5) * (2 / (2 * fin) ** 0.5)
+    b = torch.randn(fo, generator=gen) * 0.1
+    gamma, beta = torch.rand(fo, generator=gen) + 0.5, torch.randn(fo, generator=gen) * 0.1
+    pack = ops.umma_pack_weights(W.to(DEV), fin, 2)
+    run = lambda: ops.umma_linear_fwd(_padded(h), _padded(ah), fin, pack, b.to(DEV), fo, gamma=gamma.to(DEV),
+                                      beta=beta.to(DEV), relu=True, fuse_ln=True)
+    z0, y0, m0, r0 = run()
+    z64 = torch.cat([h, ah], 1).double() @ W.double().t() + b.double()
+    try:
+        ops.set_tuning(_lib.GTE_TUNE_EPI_STORE, 1)
+        z1, y1, m1, r1 = run()
+        assert torch.equal(z1[:, :fo], z0[:, :fo]) and torch.equal(y1[:, :fo], y0[:, :fo]) and torch.equal(m1, m0)
+        ops.set_tuning(_lib.GTE_TUNE_EPI_STORE, 0)
+        ops.set_tuning(_lib.GTE_TUNE_UMMA_SPLIT, 0)
+        z2, y2, _, _ = run()
+        e_split, e_single = rel_err(z0, z64), rel_err(z2, z64)
+        _log_err(f"accumulator split n={n}: split={e_split:.2e} single", e_single)
+        assert e_split < 3e-6 and e_single < 1e-5
+    finally:
+        ops.set_tuning(_lib.GTE_TUNE_EPI_STORE, 0)
+        ops.set_tuning(_lib.GTE_TUNE_UMMA_SPLIT, 1)
+    assert ops.get_tuning(_lib.GTE_TUNE_UMMA_SPLIT) == 1 and ops.get_tuning(_lib.GTE_TUNE_EPI_STORE) == 0
+
+
 # ------------------------------------------------- narrow dense streams ----
 @pytest.mark.parametrize("n,wide,nq1,nq2", [(5000, 218, 13, 13), (3001, 218, 9, 9), (2, 7, 3, 0), (777, 256, 16, 16),
                                             (40000, 218, 13, 13), (64, 100, 1, 0), (2049, 33, 5, 2)])
