@@ -434,7 +434,17 @@ __global__ void __launch_bounds__(32 * DWR_SLICES) k_umma_dw_reduce(const DwRedu
     const int nb = (R.grid - sub + R.ipc - 1) / R.ipc;  // CTAs sub, sub + ipc, ... hold the partials of this output tile
     const float* p = R.partial + (int64_t)sub * R.tile_stride + (int64_t)c * 128 + r;
     const int64_t stride = (int64_t)R.ipc * R.tile_stride;
-    for (int b = sy; b < nb; b += DWR_SLICES) v += p[(int64_t)b * stride];
+    // four loads in flight per thread (the partials sit in L2: one dependent load at a time was a 600-clock chain per
+    // partial); still a fixed order: slice s adds partials s, s + 8, ... four at a time, then the four sub-sums
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    int b = sy;
+    for (; b + 3 * DWR_SLICES < nb; b += 4 * DWR_SLICES) {
+      const float a0 = p[(int64_t)b * stride], a1 = p[(int64_t)(b + DWR_SLICES) * stride];
+      const float a2 = p[(int64_t)(b + 2 * DWR_SLICES) * stride], a3 = p[(int64_t)(b + 3 * DWR_SLICES) * stride];
+      v0 += a0; v1 += a1; v2 += a2; v3 += a3;
+    }
+    for (; b < nb; b += DWR_SLICES) v0 += p[(int64_t)b * stride];
+    v = (v0 + v1) + (v2 + v3);
   }
   red[sy][ox] = v;
   __syncthreads();

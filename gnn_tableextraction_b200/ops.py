@@ -835,18 +835,19 @@ def cross_entropy_fwd(logits, labels, class_w=None, stats=None):
     return stats
 
 
-def cross_entropy_bwd_comb(logits, labels, class_w, denominator):
-    """d logits written in place as the self block of a fresh combined [n, 32] operand (other columns zero)."""
+def cross_entropy_bwd_comb(logits, labels, class_w, denominator, width: int = COMB_LD):
+    """d logits written in place as the self block of a fresh combined [n, 32] operand (other columns zero).
+    ``width`` (tests): any multiple of 4 >= c gives an [n, width] matrix with columns [c, width) zeroed."""
     lp, ld, c = _mat(logits, "ce.logits")
     n = logits.shape[0]
-    if c > COMB_W:
+    if width == COMB_LD and c > COMB_W:
         raise GteError("cross_entropy_bwd_comb: more than 16 classes")
     yp, ydt = _labels(labels)
     _req_cuda(denominator)
-    out = torch.empty((n, COMB_LD), dtype=torch.float32, device=logits.device)
+    out = torch.empty((n, width), dtype=torch.float32, device=logits.device)
     check(
         lib().gte_cross_entropy_bwd_padded(lp, ld, yp, ydt, _vec(class_w, "class_w", n=c), n, c, denominator.data_ptr(),
-                                           out.data_ptr(), COMB_LD, COMB_LD, _stream()),
+                                           out.data_ptr(), width, width, _stream()),
         "gte_cross_entropy_bwd_padded",
     )
     return out

@@ -670,6 +670,8 @@ def test_comb_fill_and_padded_ce_bwd(n, w):
     ref = ops.cross_entropy_bwd(logits, labels, cw, den)
     dc = ops.cross_entropy_bwd_comb(logits, labels, cw, den)
     assert dc.shape == (n, 32) and torch.equal(dc[:, :c], ref[:, :c]) and torch.all(dc[:, c:] == 0)
+    d12 = ops.cross_entropy_bwd_comb(logits, labels, cw, den, width=12)  # the general padded kernel
+    assert d12.shape == (n, 12) and torch.equal(d12[:, :c], ref[:, :c]) and torch.all(d12[:, c:] == 0)
 
 
 def test_umma_pack_weights_batch_equals_single():
