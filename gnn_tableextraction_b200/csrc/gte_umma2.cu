@@ -22,10 +22,12 @@
 //                   arrive per warp on the LEADER's ready[s] (remote for the peer CTA)
 //   warp 1          leader CTA only: elected lane issues 12 tcgen05.mma.cta_group::2 (M = 256, N = BN, K = 8) per
 //                   k-block; tcgen05.commit multicasts "stage free" / "accumulator complete" to both CTAs
-//   warps 4-11      epilogue, TWO warps per TMEM lane quarter (each takes half of the column chunks): bias, LayerNorm
-//                   statistics in ONE TMEM pass (shifted sums per half, merged with the parallel-variance formula
-//                   through shared memory), second pass normalises + ReLU; z and y leave through swizzled shared
-//                   tiles and TMA stores; one arrive per warp on the leader's tempty
+//   warps 4-11      epilogue, TWO warps per TMEM lane quarter.  Split accumulator (long k loops, one TMEM stage): the two
+//                   share a tile, each takes half of the column chunks -- bias, LayerNorm statistics in ONE TMEM pass
+//                   (shifted sums per half, merged with the parallel-variance formula through shared memory), second
+//                   pass normalises + ReLU.  One accumulator (k loops of one or two k-blocks, two TMEM stages): each
+//                   group of four warps owns a stage and takes every second tile, whole rows, no exchange.  z and y
+//                   leave through swizzled shared tiles and TMA stores; one arrive per warp on the leader's tempty
 //
 // Results contract, packing and the SPLIT (separate cross-term accumulator) rule are those of gte_umma.cu.
 #include "gte_umma_args.cuh"
