@@ -73,7 +73,8 @@ int64_t gte_launch_count(void);
  * path; every value computes the same results through a different kernel).
  *   GTE_TUNE_UMMA_PAIR   1 (default): tensor-core projections run on CTA pairs (tcgen05 cta_group::2) when the shape
  *                        allows it; 0: always the single-CTA kernel
- *   GTE_TUNE_DW_PAIR     same for the tensor-core weight gradients
+ *   GTE_TUNE_DW_PAIR     reserved, no effect (the weight-gradient kernel has one form: a CTA-pair variant would not raise
+ *                        its MMA rate and was not built -- DESIGN.md section d)
  *   GTE_TUNE_UMMA_SPLIT  1 (default): contractions of more than two k-blocks keep the 3xTF32 cross terms in their own
  *                        TMEM accumulator; 0: one accumulator (and two accumulator stages) for every shape
  *   GTE_TUNE_EPI_STORE   0 (default): the pair kernel's epilogue leaves through TMA stores; 1: through the epilogue

@@ -60,7 +60,5 @@ def umma_kernel(request):
 
     v = 1 if request.param == "pair" else 0
     ops.set_tuning(_lib.GTE_TUNE_UMMA_PAIR, v)
-    ops.set_tuning(_lib.GTE_TUNE_DW_PAIR, v)
     yield request.param
     ops.set_tuning(_lib.GTE_TUNE_UMMA_PAIR, 1)
-    ops.set_tuning(_lib.GTE_TUNE_DW_PAIR, 1)
