@@ -104,6 +104,25 @@ def test_strategy_choice():
     assert pick_strategy(13, 9, True) == "pp"
 
 
+def test_narrow_layer_policy_and_cpu_rejection():
+    """host logic of the combined-operand route (layers.py): which layers pre-pack their weights / take the combined
+    [n, 32] operands, and that its producers refuse CPU tensors instead of computing"""
+    from gnn_tableextraction_b200 import layers as L, ops
+
+    n = 153600
+    assert L.wants_pack(n, 13, 218, False) and L.wants_pack(n, 218, 218, False) and L.wants_pack(n, 218, 9, False)
+    assert not L.wants_pack(n, 13, 218, True)        # pre-propagated input: plain linear, no tensor-core pack
+    assert not L.wants_pack(100, 218, 218, False)    # below the tensor-core row threshold
+    assert not L.wants_pack(n, 300, 218, False)      # wider than the tensor-core tiles
+    ctx = L.LayerCtx(strategy="proj", agg=L.GCN, h=None, ln=False, relu=False, fin=218, fout=9)
+    assert not L.wants_class_grad_comb(ctx, n)       # no packed weights on the context: the layer ran on CUDA cores
+    with pytest.raises(gte.GteError):
+        ops.comb_from(torch.zeros(4, 13))
+    with pytest.raises(gte.GteError):
+        ops.umma_linear_fwd_comb(torch.zeros(4, 32), 13, torch.zeros(8), torch.zeros(218), 218)
+    assert ops.COMB_W == 16 and ops.COMB_LD == 32
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver times beside ours) runs without a GPU and prints ONE JSON
     line with the agreed keys; under torchrun only rank 0 prints."""
